@@ -1,0 +1,194 @@
+/* b200meters.h — C ABI of the B200-native batched audio-metering engine.
+ *
+ * One "bank" = N independent instances of one reference DSP class, all processed by one CUDA
+ * kernel launch per process() call.  Entry points mirror, one for one, the methods an LV2 host
+ * reaches through x42/meters.lv2's run() callbacks; each declaration cites the reference
+ * interface it replaces (paths relative to the reference tree).
+ *
+ * Conventions
+ *  - plain C, no CUDA/torch types: device pointers and streams travel as void*.
+ *  - every function returns 0 on success or a negative B200M_E_* code; nothing throws.
+ *  - audio is planar float32, exactly what an LV2 host connects to an audio port
+ *    (src/meters.cc:257-296): channel k (k = inst*nchan + c) of a process call starts at
+ *    in + k*stride and holds nfram samples.  `*_process_device` takes a device pointer and is
+ *    asynchronous on `stream` (a cudaStream_t, NULL = legacy default stream);
+ *    `*_process_host` takes a host pointer (pinned memory recommended: b200m_host_alloc),
+ *    performs the host->device copy itself and is asynchronous on the bank's own stream.
+ *  - `*_read_device` mirrors the reference's read()/getter step on the device (including its
+ *    reset-latch side effects) and stores the values in a device result block;
+ *    `*_results` copies that block to the host (synchronises the stream it was given).
+ *  - there is NO CPU fallback: a bank cannot be created without a CUDA device, and every
+ *    sample is processed by the sm_100a kernels in meters.lv2_b200/csrc/.
+ */
+#ifndef B200METERS_H
+#define B200METERS_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+#define B200M_ABI_VERSION 1
+
+enum {
+    B200M_OK            =  0,
+    B200M_E_INVAL       = -1,   /* bad argument (NULL handle, n out of range, bad stride ...) */
+    B200M_E_NOMEM       = -2,   /* host or device allocation failed */
+    B200M_E_CUDA        = -3,   /* CUDA runtime error: see b200m_last_error() */
+    B200M_E_UNSUPPORTED = -4,   /* valid in the reference, not provided by this engine */
+    B200M_E_NODEVICE    = -5    /* no CUDA device: the engine has no CPU path */
+};
+
+#define B200M_MAX_BLOCK 8192u     /* TruePeakdsp::process asserts n <= 8192 (jmeters/truepeakdsp.cc:43-44);
+                                     robtk/jackwrap.c:35 MAXPERIOD 8192 */
+#define B200M_HIST_LEN  751       /* Ebu_r128_hist bins, -70.0 .. +5.0 dB (ebumeter/ebu_r128_proc.cc:34) */
+
+int         b200m_abi_version (void);
+const char* b200m_last_error (void);            /* thread-local text of the last failure */
+int         b200m_device_count (void);
+/* pinned host memory for process_host()/results(): cudaHostAlloc / cudaFreeHost */
+int         b200m_host_alloc (void** p, size_t bytes);
+int         b200m_host_free (void* p);
+/* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
+uint64_t    b200m_launch_count (void);
+
+/* ======================================================================================
+ * EBU R128 loudness bank — replaces LV2M::Ebu_r128_proc (ebumeter/ebu_r128_proc.h:66-125)
+ * as driven by ebur128_run (src/ebulv2.cc:341-358).
+ * ====================================================================================== */
+typedef struct b200m_ebu b200m_ebu;
+
+typedef struct b200m_ebu_result {          /* getters, ebumeter/ebu_r128_proc.h:81-89 */
+    float loudness_M, maxloudn_M, loudness_S, maxloudn_S;
+    float integrated, integ_thr, range_min, range_max, range_thr;
+    int32_t hist_M_count, hist_S_count;    /* :93-94 */
+    float   frag_power;                    /* last completed 50 ms fragment power (_power[_wrind-1]) */
+} b200m_ebu_result;
+
+/* Ebu_r128_proc() + init(nchan, fsamp) (:166-173) for n_inst instances.  nchan in {1,2}
+ * (the EBUr128 plugin uses 2, src/ebulv2.cc:190); 3..5 -> B200M_E_UNSUPPORTED. */
+int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nchan, float fsamp);
+int b200m_ebu_destroy (b200m_ebu* h);
+/* Ebu_r128_proc::reset (:176-190).  All instances share the 50 ms fragment clock, so only
+ * inst = -1 (every instance) is accepted. */
+int b200m_ebu_reset (b200m_ebu* h, int32_t inst, void* stream);
+/* integr_start / integr_pause (ebu_r128_proc.h:77-78) / integr_reset (.cc:193-204); inst = -1: all */
+int b200m_ebu_integr_start (b200m_ebu* h, int32_t inst, void* stream);
+int b200m_ebu_integr_pause (b200m_ebu* h, int32_t inst, void* stream);
+int b200m_ebu_integr_reset (b200m_ebu* h, int32_t inst, void* stream);
+/* Ebu_r128_proc::process(nfram, input[]) (:207-248) for every instance. 0 < nfram <= 8192. */
+int b200m_ebu_process_device (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
+int b200m_ebu_process_host (b200m_ebu* h, const float* in, size_t stride, uint32_t nfram);
+/* getters -> host array of n_inst results.  stream = the stream last used for processing
+ * (ignored after process_host, which uses the bank's stream). */
+int b200m_ebu_results (b200m_ebu* h, b200m_ebu_result* out, void* stream);
+/* histogram_M()/histogram_S() (:91-92) of one instance: 751 + 751 int32 */
+int b200m_ebu_histogram (b200m_ebu* h, uint32_t inst, int32_t* hist_M, int32_t* hist_S, void* stream);
+/* K-weighting coefficients as designed on the host (detect_init, :263-293): a0 a1 a2 b1 b2 c3 c4 */
+int b200m_ebu_coeffs (const b200m_ebu* h, float out7[7]);
+/* internal state of one instance for differential tests: z[nchan][4], power ring[64], frpwr,
+ * counters {frcnt, wrind, div1, div2} */
+int b200m_ebu_state (b200m_ebu* h, uint32_t inst, float* z, float* power64, float* frpwr, int32_t counters4[4], void* stream);
+/* Whole-mix gated loudness (an extension; the reference has no cross-instance quantity):
+ * sums hist_M/hist_S/counts of all instances on the device into d_out[2*752+...]; the caller
+ * may all-reduce that int32 vector across GPUs (NCCL) and hand it to b200m_ebu_mix_finish. */
+#define B200M_MIX_WORDS 1508      /* histM[752] histS[752] cntM cntS errM errS */
+int b200m_ebu_mix_reduce (b200m_ebu* h, int32_t* d_out, void* stream);
+/* calc_integ + calc_range (:105-150) on a summed histogram vector (device pointer);
+ * out5 (host) = integrated, integ_thr, range_min, range_max, range_thr */
+int b200m_ebu_mix_finish (b200m_ebu* h, const int32_t* d_mix, float out5[5], void* stream);
+
+/* ======================================================================================
+ * True-peak + K-meter bank — replaces LV2M::TruePeakdsp (jmeters/truepeakdsp.h:28-61) and
+ * LV2M::Kmeterdsp (jmeters/kmeterdsp.h:27-62), one mono meter of each kind per channel, as
+ * driven by dr14_run in TPnRMS mode (src/dr14.c:391-394,425-450), dbtp_run / kmeter_run
+ * (src/meters.cc:333-508) and ebur128_run's dBTP option (src/ebulv2.cc:344-347,360-367).
+ * ====================================================================================== */
+typedef struct b200m_tpk b200m_tpk;
+
+#define B200M_TPK_TRUEPEAK 1u     /* run TruePeakdsp per channel */
+#define B200M_TPK_KMETER   2u     /* run Kmeterdsp per channel   */
+#define B200M_TP_MODE_PROCESS 0u  /* TruePeakdsp::process      (:41-99)  */
+#define B200M_TP_MODE_MAX     1u  /* TruePeakdsp::process_max  (:101-124) */
+
+typedef struct b200m_tpk_result {
+    float tp_m, tp_p;             /* TruePeakdsp::read(m,p) (:133-138) — linear */
+    float km_rms, km_peak;        /* Kmeterdsp::read(rms,peak) (kmeterdsp.cc:150-155) — linear */
+} b200m_tpk_result;
+
+int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp, uint32_t flags);
+int b200m_tpk_destroy (b200m_tpk* h);
+/* process() of every enabled meter over one block; tp_mode selects process / process_max */
+int b200m_tpk_process_device (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, void* stream);
+int b200m_tpk_process_host (b200m_tpk* h, const float* in, size_t stride, uint32_t nfram, uint32_t tp_mode);
+/* read() of every enabled meter (sets TruePeakdsp::_res / Kmeterdsp::_flag) */
+int b200m_tpk_read_device (b200m_tpk* h, void* stream);
+int b200m_tpk_results (b200m_tpk* h, b200m_tpk_result* out, void* stream);
+/* TruePeakdsp::reset (:140-145) / Kmeterdsp::reset (kmeterdsp.cc:157-162); chan = -1: all */
+int b200m_tpk_reset (b200m_tpk* h, int32_t chan, void* stream);
+/* host-designed constants: w[4] = w1 w2 w3 g (truepeakdsp.cc:153-157); ctab[120] = zita table
+ * (zita-resampler/resampler-table.cc:52-75, hl=24 np=4 fr=1); km[2] = omega, (float)hold */
+int b200m_tpk_coeffs (const b200m_tpk* h, float w[4], float ctab[120], float km[2]);
+/* internal state for differential tests, arrays of n_chan: tp {m,p,z1,z2,res}, km [n][8] as
+ * z1 z2 rms peak fall cnt fpp flag */
+int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float* tp_z2, int32_t* tp_res, float* km8, void* stream);
+/* the raw 4x oversampled stream of the LAST processed block of one channel (4*nfram floats),
+ * only kept when enabled with b200m_tpk_debug_capture(h,1): FIR bit-exactness tests */
+int b200m_tpk_debug_capture (b200m_tpk* h, int enable);
+int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t n_out, void* stream);
+
+/* ======================================================================================
+ * Stereo correlation bank — replaces LV2M::Stcorrdsp (jmeters/stcorrdsp.h:27-55) as driven by
+ * cor_run (src/meters.cc:511-536) and xfer_run (src/xfer.c:248-251).
+ * ====================================================================================== */
+typedef struct b200m_cor b200m_cor;
+int b200m_cor_create (b200m_cor** out, int device, uint32_t n_inst, int fsamp, float flp, float tcf);
+int b200m_cor_destroy (b200m_cor* h);
+int b200m_cor_process_device (b200m_cor* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
+int b200m_cor_process_host (b200m_cor* h, const float* in, size_t stride, uint32_t nfram);
+int b200m_cor_results (b200m_cor* h, float* out, void* stream);           /* Stcorrdsp::read (:79-82) */
+int b200m_cor_state (b200m_cor* h, float* state5, void* stream);          /* [n][5] zl zr zlr zll zrr */
+int b200m_cor_coeffs (const b200m_cor* h, float w[2]);
+
+/* ======================================================================================
+ * 30-band 1/3-octave spectrum bank — replaces spectrum_instantiate / spectrum_run
+ * (src/spectrumlv2.c:73-121,159-257) over bandpass_setup / bandpass_process (src/spectr.c:68-206).
+ * ====================================================================================== */
+typedef struct b200m_spec b200m_spec;
+int b200m_spec_create (b200m_spec** out, int device, uint32_t n_inst, uint32_t nchan, double rate);
+int b200m_spec_destroy (b200m_spec* h);
+/* one spectrum_run(): speed = *port 60, reset = *port 61 (same value for every instance) */
+int b200m_spec_process_device (b200m_spec* h, const float* d_in, size_t stride, uint32_t nfram, float speed, float reset, void* stream);
+int b200m_spec_process_host (b200m_spec* h, const float* in, size_t stride, uint32_t nfram, float speed, float reset);
+/* ports 0..59 of every instance: 30 band levels (dB), 30 band maxima (dB) */
+int b200m_spec_results (b200m_spec* h, float* out60, void* stream);
+int b200m_spec_state (b200m_spec* h, uint32_t inst, double* z360, float* val30, float* max30, void* stream);
+int b200m_spec_coeffs (const b200m_spec* h, double* W1080);              /* [30][6][6] a0 a1 a2 b0 b1 b2 */
+
+/* ======================================================================================
+ * Phasewheel FFT analysis bank — replaces fftx_init / fftx_run / ft_analyze (gui/fft.c:208-361)
+ * for both channels plus process_audio (gui/phasewheel.c:1307-1342).
+ * ====================================================================================== */
+typedef struct b200m_pw b200m_pw;
+int b200m_pw_create (b200m_pw** out, int device, uint32_t n_inst, uint32_t fft_bins, double rate);
+int b200m_pw_destroy (b200m_pw* h);
+/* returns (via *fired) whether this call completed an analysis (fftx_run()==0) */
+int b200m_pw_process_device (b200m_pw* h, const float* d_in, size_t stride, uint32_t nfram, float db_thresh, int* fired, void* stream);
+int b200m_pw_process_host (b200m_pw* h, const float* in, size_t stride, uint32_t nfram, float db_thresh, int* fired);
+/* phase[n_inst][fft_bins], level[n_inst][fft_bins], peak[n_inst] (ui->phase/level/peak) */
+int b200m_pw_results (b200m_pw* h, float* phase, float* level, float* peak, void* stream);
+int b200m_pw_raw (b200m_pw* h, uint32_t inst, float* powL, float* powR, float* phL, float* phR, void* stream);
+/* device pointers of the result planes, for callers that keep the spectra on the GPU */
+int b200m_pw_device_results (b200m_pw* h, const float** d_phase, const float** d_level, const float** d_peak);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200METERS_H */

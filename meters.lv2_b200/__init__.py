@@ -1,0 +1,249 @@
+"""meters.lv2_b200 — host-side mirror (Python/ctypes) of the b200meters C ABI (include/b200meters.h).
+
+The product is the CUDA library `libb200meters.so` built in-tree from csrc/ by build.py; this module
+only binds its C entry points for tests and bench.py.  Class and method names follow the reference's
+DSP classes (Ebu_r128_proc, TruePeakdsp, Kmeterdsp, Stcorrdsp, the spectr30 plugin, the phasewheel
+FFT analysis), each batched over N instances.  There is no CPU path: constructing a bank without the
+built library or without a CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libb200meters.so")
+HIST_LEN = 751
+MIX_WORDS = 1508
+MAX_BLOCK = 8192
+_v = C.c_void_p
+_lib = None
+
+
+class B200MError(RuntimeError):
+    pass
+
+
+class EbuResult(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("loudness_M", "maxloudn_M", "loudness_S", "maxloudn_S", "integrated",
+                                          "integ_thr", "range_min", "range_max", "range_thr")] + \
+               [("hist_M_count", C.c_int32), ("hist_S_count", C.c_int32), ("frag_power", C.c_float)]
+
+
+EBU_RESULT_DTYPE = np.dtype([(n, "<f4") for n in ("loudness_M", "maxloudn_M", "loudness_S", "maxloudn_S", "integrated",
+                                                    "integ_thr", "range_min", "range_max", "range_thr")] +
+                            [("hist_M_count", "<i4"), ("hist_S_count", "<i4"), ("frag_power", "<f4")])
+TPK_RESULT_DTYPE = np.dtype([("tp_m", "<f4"), ("tp_p", "<f4"), ("km_rms", "<f4"), ("km_peak", "<f4")])
+
+_PROTOS = {
+    "b200m_abi_version": (C.c_int, []),
+    "b200m_last_error": (C.c_char_p, []),
+    "b200m_device_count": (C.c_int, []),
+    "b200m_host_alloc": (C.c_int, [C.POINTER(_v), C.c_size_t]),
+    "b200m_host_free": (C.c_int, [_v]),
+    "b200m_launch_count": (C.c_uint64, []),
+    # EBU
+    "b200m_ebu_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_float]),
+    "b200m_ebu_destroy": (C.c_int, [_v]),
+    "b200m_ebu_reset": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_ebu_integr_start": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_ebu_integr_pause": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_ebu_integr_reset": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_ebu_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
+    "b200m_ebu_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
+    "b200m_ebu_results": (C.c_int, [_v, _v, _v]),
+    "b200m_ebu_histogram": (C.c_int, [_v, C.c_uint32, _v, _v, _v]),
+    "b200m_ebu_coeffs": (C.c_int, [_v, _v]),
+    "b200m_ebu_state": (C.c_int, [_v, C.c_uint32, _v, _v, _v, _v, _v]),
+    "b200m_ebu_mix_reduce": (C.c_int, [_v, _v, _v]),
+    "b200m_ebu_mix_finish": (C.c_int, [_v, _v, _v, _v]),
+    # True peak + K-meter
+    "b200m_tpk_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_float, C.c_uint32]),
+    "b200m_tpk_destroy": (C.c_int, [_v]),
+    "b200m_tpk_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_uint32, _v]),
+    "b200m_tpk_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_uint32]),
+    "b200m_tpk_read_device": (C.c_int, [_v, _v]),
+    "b200m_tpk_results": (C.c_int, [_v, _v, _v]),
+    "b200m_tpk_reset": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_tpk_coeffs": (C.c_int, [_v, _v, _v, _v]),
+    "b200m_tpk_state": (C.c_int, [_v, _v, _v, _v, _v, _v, _v, _v]),
+    "b200m_tpk_debug_capture": (C.c_int, [_v, C.c_int]),
+    "b200m_tpk_debug_upsampled": (C.c_int, [_v, C.c_uint32, _v, C.c_uint32, _v]),
+    # Stcorr
+    "b200m_cor_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_int, C.c_float, C.c_float]),
+    "b200m_cor_destroy": (C.c_int, [_v]),
+    "b200m_cor_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
+    "b200m_cor_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
+    "b200m_cor_results": (C.c_int, [_v, _v, _v]),
+    "b200m_cor_state": (C.c_int, [_v, _v, _v]),
+    "b200m_cor_coeffs": (C.c_int, [_v, _v]),
+    # spectr30
+    "b200m_spec_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_double]),
+    "b200m_spec_destroy": (C.c_int, [_v]),
+    "b200m_spec_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_float, C.c_float, _v]),
+    "b200m_spec_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_float, C.c_float]),
+    "b200m_spec_results": (C.c_int, [_v, _v, _v]),
+    "b200m_spec_state": (C.c_int, [_v, C.c_uint32, _v, _v, _v, _v]),
+    "b200m_spec_coeffs": (C.c_int, [_v, _v]),
+    # phasewheel
+    "b200m_pw_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_double]),
+    "b200m_pw_destroy": (C.c_int, [_v]),
+    "b200m_pw_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_int), _v]),
+    "b200m_pw_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_int)]),
+    "b200m_pw_results": (C.c_int, [_v, _v, _v, _v, _v]),
+    "b200m_pw_raw": (C.c_int, [_v, C.c_uint32, _v, _v, _v, _v, _v]),
+    "b200m_pw_device_results": (C.c_int, [_v, C.POINTER(_v), C.POINTER(_v), C.POINTER(_v)]),
+}
+EXPORTS = tuple(_PROTOS)
+
+
+def lib():
+    """Load libb200meters.so (fails loudly if it has not been built: there is no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200MError("%s is missing: run `python meters.lv2_b200/build.py` "
+                             "(or __graft_entry__.build()); there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            try:
+                fn = getattr(L, name)
+            except AttributeError:      # reported by missing_exports(); calling it raises AttributeError
+                continue
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def missing_exports():
+    """Names declared in include/b200meters.h that the built library does not export."""
+    L = lib()
+    return [n for n in _PROTOS if not hasattr(L, n)]
+
+
+def _ck(rc):
+    if rc != 0:
+        raise B200MError("b200meters error %d: %s" % (rc, lib().b200m_last_error().decode()))
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dev_ptr(x):
+    """torch CUDA tensor | int device pointer -> (pointer, row stride in floats, rows, cols)."""
+    if isinstance(x, int):
+        raise TypeError("pass (ptr, stride, nfram) explicitly via process_ptr()")
+    assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1, "need a [channels, nfram] float32 CUDA tensor"
+    return C.c_void_p(x.data_ptr()), x.stride(0), x.shape[0], x.shape[1]
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        except ImportError:
+            pass
+        return C.c_void_p(0)
+    if isinstance(stream, int):
+        return C.c_void_p(stream)
+    return C.c_void_p(stream.cuda_stream)
+
+
+def _host_planar(x):
+    """numpy [channels, nfram] float32 (row-contiguous) or a pinned torch CPU tensor."""
+    if isinstance(x, np.ndarray):
+        assert x.dtype == np.float32 and x.ndim == 2 and x.strides[1] == 4
+        return _np_ptr(x), x.strides[0] // 4, x.shape[0], x.shape[1]
+    assert (not x.is_cuda) and x.dim() == 2 and x.stride(1) == 1
+    return C.c_void_p(x.data_ptr()), x.stride(0), x.shape[0], x.shape[1]
+
+
+def launch_count():
+    return int(lib().b200m_launch_count())
+
+
+class _Bank:
+    _destroy = None
+
+    def __init__(self):
+        self.h = _v()
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            getattr(lib(), self._destroy)(self.h)
+            self.h = _v()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Ebu_r128_proc(_Bank):
+    """N x LV2M::Ebu_r128_proc (ebumeter/ebu_r128_proc.h:66-125)."""
+    _destroy = "b200m_ebu_destroy"
+
+    def __init__(self, n_inst, nchan=2, fsamp=48000.0, device=0):
+        super().__init__()
+        self.n_inst, self.nchan = n_inst, nchan
+        _ck(lib().b200m_ebu_create(C.byref(self.h), device, n_inst, nchan, fsamp))
+
+    def reset(self, stream=None):
+        _ck(lib().b200m_ebu_reset(self.h, -1, _stream_ptr(stream)))
+
+    def integr_start(self, inst=-1, stream=None):
+        _ck(lib().b200m_ebu_integr_start(self.h, inst, _stream_ptr(stream)))
+
+    def integr_pause(self, inst=-1, stream=None):
+        _ck(lib().b200m_ebu_integr_pause(self.h, inst, _stream_ptr(stream)))
+
+    def integr_reset(self, inst=-1, stream=None):
+        _ck(lib().b200m_ebu_integr_reset(self.h, inst, _stream_ptr(stream)))
+
+    def process(self, x, stream=None):
+        """x: [n_inst*nchan, nfram] float32 CUDA tensor (device path) or numpy/pinned CPU (host path)."""
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == self.n_inst * self.nchan
+            _ck(lib().b200m_ebu_process_host(self.h, p, s, n))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == self.n_inst * self.nchan
+            _ck(lib().b200m_ebu_process_device(self.h, p, s, n, _stream_ptr(stream)))
+
+    def process_ptr(self, ptr, stride, nfram, stream=None):
+        _ck(lib().b200m_ebu_process_device(self.h, C.c_void_p(ptr), stride, nfram, _stream_ptr(stream)))
+
+    def results(self, stream=None):
+        out = np.empty(self.n_inst, EBU_RESULT_DTYPE)
+        _ck(lib().b200m_ebu_results(self.h, _np_ptr(out), _stream_ptr(stream)))
+        return out
+
+    def histogram(self, inst, stream=None):
+        hm = np.empty(HIST_LEN, np.int32); hs = np.empty(HIST_LEN, np.int32)
+        _ck(lib().b200m_ebu_histogram(self.h, inst, _np_ptr(hm), _np_ptr(hs), _stream_ptr(stream)))
+        return hm, hs
+
+    def coeffs(self):
+        o = np.empty(7, np.float32)
+        _ck(lib().b200m_ebu_coeffs(self.h, _np_ptr(o)))
+        return o
+
+    def state(self, inst, stream=None):
+        z = np.empty((self.nchan, 4), np.float32); pw = np.empty(64, np.float32)
+        fr = np.empty(1, np.float32); c = np.empty(4, np.int32)
+        _ck(lib().b200m_ebu_state(self.h, inst, _np_ptr(z), _np_ptr(pw), _np_ptr(fr), _np_ptr(c), _stream_ptr(stream)))
+        return z, pw, fr[0], c
+
+    def mix_reduce(self, d_out, stream=None):
+        """d_out: int32 CUDA tensor of MIX_WORDS elements."""
+        _ck(lib().b200m_ebu_mix_reduce(self.h, C.c_void_p(d_out.data_ptr()), _stream_ptr(stream)))
+
+    def mix_finish(self, d_mix, stream=None):
+        out = np.empty(5, np.float32)
+        _ck(lib().b200m_ebu_mix_finish(self.h, C.c_void_p(d_mix.data_ptr()), _np_ptr(out), _stream_ptr(stream)))
+        return out

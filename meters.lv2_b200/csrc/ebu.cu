@@ -1,0 +1,627 @@
+// ebu.cu — EBU R128 loudness bank: kernels K1 (K-weighting + fragment power) and K2 (loudness,
+// histograms, gating) and the b200m_ebu_* C ABI.
+//
+// Replaces LV2M::Ebu_r128_proc (ebumeter/ebu_r128_proc.{h,cc} of the reference) for N independent
+// instances.  Nothing here is translated from the reference's control flow: the per-sample loop
+// (detect_process, ebu_r128_proc.cc:302-337) becomes one thread per mono channel fed by a
+// cp.async shared-memory tile pipeline; the 20 Hz bookkeeping (process/addfrags, :207-260) and
+// the histogram statistics (Ebu_r128_hist, :66-150) become one warp per instance that walks the
+// 751 bins with ballot/shuffle.  Arithmetic ORDER is the reference's, operation by operation
+// (no FMA contraction, IEEE div/sqrt, glibc-exact log10f), because the results feed integer
+// histogram bins that must be bit-exact.
+#include <math.h>
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+
+namespace b200m {
+
+constexpr int EBU_TILE   = 64;            // samples per smem tile
+constexpr int EBU_ROWP   = EBU_TILE + 4;  // padded row pitch (floats): 68 = 4 mod 32 -> LDS.128 conflict free
+constexpr int EBU_STAGES = 4;             // cp.async pipeline depth
+constexpr int EBU_MAXCHUNK = 32;          // chunks (block/fragment edges) handled per K1 launch
+constexpr int HIST_PITCH = 752;           // 751 bins padded to a 16-byte multiple
+
+struct EbuCoef { float a0, a1, a2, b1, b2, c3, c4; };
+
+struct EbuChunks {                        // bit31: chunk ends a 50 ms fragment
+    int n;
+    uint32_t v[EBU_MAXCHUNK];
+};
+
+// ---- K1: K-weighting recurrence + per-chunk power sums ------------------------------------
+// One warp = 32 consecutive mono channels (lane = channel).  Tiles of [32 ch x 64 samples] are
+// copied global->shared with cp.async (each row of the planar input is contiguous, so every
+// 16-byte copy is fully coalesced), four tiles in flight; lane l then walks row l with LDS.128.
+B200M_DEV void kw_step (float p, const EbuCoef& c, float& z1, float& z2, float& z3, float& z4, float& sj)
+{
+    // x = p - b1*z1 - b2*z2 + 1e-15f;  y = a0*x + a1*z1 + a2*z2 - c3*z3 - c4*z4   (:321-322)
+    float x = __fsub_rn (p, __fmul_rn (c.b1, z1));
+    x = __fsub_rn (x, __fmul_rn (c.b2, z2));
+    x = __fadd_rn (x, 1e-15f);
+    float y = __fadd_rn (__fmul_rn (c.a0, x), __fmul_rn (c.a1, z1));
+    y = __fadd_rn (y, __fmul_rn (c.a2, z2));
+    y = __fsub_rn (y, __fmul_rn (c.c3, z3));
+    y = __fsub_rn (y, __fmul_rn (c.c4, z4));
+    z2 = z1; z1 = x;
+    z4 = __fadd_rn (z4, z3);
+    z3 = __fadd_rn (z3, y);
+    sj = __fadd_rn (sj, __fmul_rn (y, y));
+}
+
+template <int NCHAN, bool ALIGNED>
+__global__ void __launch_bounds__ (32)
+ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int nfram, EbuCoef cf, EbuChunks ck,
+                  float fragm_f, float* __restrict__ zst, float* __restrict__ frpwr, float* __restrict__ fragpw, int n_inst)
+{
+    __shared__ __align__ (16) float tile[EBU_STAGES][32 * EBU_ROWP];
+    const int lane = threadIdx.x;
+    const int k0 = blockIdx.x * 32;
+    const int k = min (k0 + lane, nchans - 1);       // tail lanes shadow the last channel (no stores)
+    const bool live = (k0 + lane) < nchans;
+    const int ntiles = (nfram + EBU_TILE - 1) / EBU_TILE;
+
+    auto issue = [&] (int t) {
+        if (t < ntiles) {
+            float* dst = tile[t % EBU_STAGES];
+            const int s0 = t * EBU_TILE;
+            if (ALIGNED) {
+                const int c4 = (lane & 15) * 4;                  // column of this lane's 16-byte piece
+                const int left = (nfram - (s0 + c4)) * 4;        // bytes still inside the block
+                const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int r = 2 * i + (lane >> 4);
+                    const int kr = min (k0 + r, nchans - 1);
+                    const float* src = in + (size_t)kr * stride + s0 + c4;
+                    cp_async16 (dst + r * EBU_ROWP + c4, nb ? src : in, nb);
+                }
+            } else {
+#pragma unroll 4
+                for (int r = 0; r < 32; ++r) {
+                    const int kr = min (k0 + r, nchans - 1);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c = lane + 32 * h;
+                        const bool ok = (s0 + c) < nfram;
+                        cp_async4 (dst + r * EBU_ROWP + c, ok ? in + (size_t)kr * stride + s0 + c : in, ok ? 4 : 0);
+                    }
+                }
+            }
+        }
+        cp_async_commit ();
+    };
+
+    float z1 = zst[0 * (size_t)nchans + k], z2 = zst[1 * (size_t)nchans + k];
+    float z3 = zst[2 * (size_t)nchans + k], z4 = zst[3 * (size_t)nchans + k];
+    const int inst = k / NCHAN;
+    float fp = frpwr[inst];
+    float sj = 0.0f;
+    int ci = 0, nfr = 0;
+    int cend = (int)(ck.v[0] & 0x7fffffffu);           // end position (exclusive) of the current chunk
+    bool cfrag = (ck.v[0] >> 31) != 0;
+
+#pragma unroll
+    for (int t = 0; t < EBU_STAGES - 1; ++t) issue (t);
+
+    for (int t = 0; t < ntiles; ++t) {
+        cp_async_wait<EBU_STAGES - 2> ();
+        __syncwarp ();
+        const float* row = tile[t % EBU_STAGES] + lane * EBU_ROWP;
+        int a = t * EBU_TILE;
+        const int b = min (a + EBU_TILE, nfram);
+        while (a < b) {
+            const int e = min (b, cend);
+            int j = a;
+            // scalar head up to a 4-aligned position, vector body, scalar tail
+            for (; j < e && (j & 3); ++j) kw_step (row[j - t * EBU_TILE], cf, z1, z2, z3, z4, sj);
+            for (; j + 4 <= e; j += 4) {
+                const float4 v = *reinterpret_cast<const float4*> (row + (j - t * EBU_TILE));
+                kw_step (v.x, cf, z1, z2, z3, z4, sj);
+                kw_step (v.y, cf, z1, z2, z3, z4, sj);
+                kw_step (v.z, cf, z1, z2, z3, z4, sj);
+                kw_step (v.w, cf, z1, z2, z3, z4, sj);
+            }
+            for (; j < e; ++j) kw_step (row[j - t * EBU_TILE], cf, z1, z2, z3, z4, sj);
+            a = e;
+            if (a == cend) {
+                // end of one detect_process() call (:324-335): state scrub, channel sum, _frpwr +=
+                z1 = scrub (z1); z2 = scrub (z2); z3 = scrub (z3); z4 = scrub (z4);
+                float si;
+                if (NCHAN == 1) si = __fmul_rn (2.0f, sj);
+                else si = __fadd_rn (sj, __shfl_xor_sync (0xffffffffu, sj, 1));   // 1.0f*sjL + 1.0f*sjR
+                fp = __fadd_rn (fp, si);
+                if (cfrag) {                                                  // :217-221
+                    if (live && (k % NCHAN) == 0) fragpw[(size_t)nfr * n_inst + inst] = __fdiv_rn (fp, fragm_f);
+                    fp = 1e-30f;
+                    ++nfr;
+                }
+                sj = 0.0f;
+                ++ci;
+                if (ci < ck.n) { cend = (int)(ck.v[ci] & 0x7fffffffu); cfrag = (ck.v[ci] >> 31) != 0; }
+                else cend = 0x7fffffff;
+            }
+        }
+        __syncwarp ();
+        issue (t + EBU_STAGES - 1);
+    }
+    cp_async_wait<0> ();
+    if (live) {
+        zst[0 * (size_t)nchans + k] = z1; zst[1 * (size_t)nchans + k] = z2;
+        zst[2 * (size_t)nchans + k] = z3; zst[3 * (size_t)nchans + k] = z4;
+        if ((k % NCHAN) == 0) frpwr[inst] = fp;
+    }
+}
+
+// ---- K2: per-fragment loudness, histograms, gated integration ------------------------------
+struct EbuCtl { int div1, div2, integr, pad; };
+
+// Ebu_r128_hist::integrate (:82-102).  `c[t]` holds bin t*32+lane.  Only non-zero bins change the
+// running float sum, so the warp walks them in bin order (ballot) and applies the "/= 10 after
+// every bin = 99 mod 100" steps in between: identical rounding sequence, ~#non-zero-bins steps.
+B200M_DEV float hist_integrate (const int (&c)[24], int i0, const float* bp, int lane)
+{
+    float s = 0.0f; int n = 0;
+    int next_div = i0 - (i0 % 100) + 99;
+#pragma unroll
+    for (int t = 0; t < 24; ++t) {
+        const int bin_l = t * 32 + lane;
+        unsigned m = __ballot_sync (0xffffffffu, c[t] != 0 && bin_l >= i0 && bin_l <= 750);
+        while (m) {
+            const int l = __ffs (m) - 1; m &= m - 1;
+            const int kk = __shfl_sync (0xffffffffu, c[t], l);
+            const int bin = t * 32 + l;
+            while (next_div < bin) { s = __fdiv_rn (s, 10.0f); next_div += 100; }
+            s = __fadd_rn (s, __fmul_rn ((float)kk, bp[bin % 100]));
+            n += kk;
+        }
+    }
+    while (next_div <= 750) { s = __fdiv_rn (s, 10.0f); next_div += 100; }
+    return __fdiv_rn (s, (float)n);
+}
+
+B200M_DEV void hist_load (const int* row, int (&c)[24], int lane)
+{
+#pragma unroll
+    for (int t = 0; t < 24; ++t) { const int b = t * 32 + lane; c[t] = (b <= 750) ? row[b] : 0; }
+}
+
+// Ebu_r128_hist::calc_integ (:105-125)
+B200M_DEV void hist_calc_integ (const int* row, int count, const float* bp, int lane, float& vi, float& th)
+{
+    if (count < 50) { vi = -200.0f; return; }
+    int c[24]; hist_load (row, c, lane);
+    float s = hist_integrate (c, 0, bp, lane);
+    const float lg = log10f_glibc (s);
+    th = __fsub_rn (__fmul_rn (10.0f, lg), 10.0f);
+    int k = (int)floorf (__fadd_rn (__fmul_rn (100.0f, lg), 0.5f)) + 600;
+    if (k < 0) k = 0;
+    s = hist_integrate (c, k, bp, lane);
+    vi = __fmul_rn (10.0f, log10f_glibc (s));
+}
+
+// Ebu_r128_hist::calc_range (:128-150)
+B200M_DEV void hist_calc_range (const int* row, int count, const float* bp, int lane, float& v0, float& v1, float& th)
+{
+    if (count < 20) { v0 = -200.0f; v1 = -200.0f; return; }
+    int c[24]; hist_load (row, c, lane);
+    float s = hist_integrate (c, 0, bp, lane);
+    const float lg = log10f_glibc (s);
+    th = __fsub_rn (__fmul_rn (10.0f, lg), 20.0f);
+    // floorf (100 * log10f (s) + 0.5): the 0.5 literal is a double in the reference (:141)
+    int k = (int)floorf ((float)((double)__fmul_rn (100.0f, lg) + 0.5)) + 500;
+    if (k < 0) k = 0;
+    int n = 0;
+#pragma unroll
+    for (int t = 0; t < 24; ++t) { const int b = t * 32 + lane; if (b >= k && b <= 750) n += c[t]; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) n += __shfl_xor_sync (0xffffffffu, n, o);
+    const float a = __fmul_rn (0.10f, (float)n), b95 = __fmul_rn (0.95f, (float)n);
+    // for (i = k, s = 0; s < a; i++) s += histc[i];
+    int i = k; s = 0.0f; bool done = !(s < a);
+#pragma unroll
+    for (int t = 0; t < 24; ++t) {
+        const int bin_l = t * 32 + lane;
+        unsigned m = done ? 0u : __ballot_sync (0xffffffffu, c[t] != 0 && bin_l >= k && bin_l <= 750);
+        while (m && !done) {
+            const int l = __ffs (m) - 1; m &= m - 1;
+            s = __fadd_rn (s, (float)__shfl_sync (0xffffffffu, c[t], l));
+            if (!(s < a)) { i = t * 32 + l + 1; done = true; }
+        }
+    }
+    // for (j = 750, s = n; s > b; j--) s -= histc[j];
+    int j = 750; s = (float)n; done = !(s > b95);
+#pragma unroll
+    for (int t = 23; t >= 0; --t) {
+        const int bin_l = t * 32 + lane;
+        unsigned m = done ? 0u : __ballot_sync (0xffffffffu, c[t] != 0 && bin_l <= 750);
+        while (m && !done) {
+            const int l = 31 - __clz (m); m &= ~(1u << l);
+            s = __fsub_rn (s, (float)__shfl_sync (0xffffffffu, c[t], l));
+            if (!(s > b95)) { j = t * 32 + l - 1; done = true; }
+        }
+    }
+    v0 = __fdiv_rn ((float)(i - 701), 10.0f);
+    v1 = __fdiv_rn ((float)(j - 699), 10.0f);
+}
+
+// Ebu_r128_hist::addpoint (:66-79); lane 0 performs the update
+B200M_DEV void hist_addpoint (int* row, int* cnt, int* err, float v, int lane)
+{
+    int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, v), 700.5f));
+    if (k < 0) return;
+    if (lane == 0) {
+        if (k > 750) { k = 750; (*err)++; }
+        row[k]++; (*cnt)++;
+    }
+}
+
+constexpr int K2_WARPS = 4;
+
+__global__ void __launch_bounds__ (K2_WARPS * 32)
+ebu_loudness_hist (int n_inst, int nfrag, int wrind0, const float* __restrict__ fragpw, float* __restrict__ ring,
+                   EbuCtl* __restrict__ ctl, b200m_ebu_result* __restrict__ res, int* __restrict__ histM,
+                   int* __restrict__ histS, int* __restrict__ cnt, const float* __restrict__ bin_power)
+{
+    __shared__ float sring[K2_WARPS][64];
+    __shared__ float sbp[100];
+    for (int i = threadIdx.x; i < 100; i += blockDim.x) sbp[i] = bin_power[i];
+    __syncthreads ();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int inst = blockIdx.x * K2_WARPS + w;
+    if (inst >= n_inst) return;
+    float* rg = sring[w];
+    rg[lane] = ring[(size_t)inst * 64 + lane];
+    rg[lane + 32] = ring[(size_t)inst * 64 + lane + 32];
+    EbuCtl c = ctl[inst];
+    b200m_ebu_result r = res[inst];
+    int* hM = histM + (size_t)inst * HIST_PITCH;
+    int* hS = histS + (size_t)inst * HIST_PITCH;
+    int* ct = cnt + (size_t)inst * 4;
+    int cntM = ct[0], cntS = ct[1];
+    int wr = wrind0;
+    __syncwarp ();
+    for (int f = 0; f < nfrag; ++f) {
+        const float p = fragpw[(size_t)f * n_inst + inst];
+        if (lane == 0) rg[wr] = p;                         // _power[_wrind++] = _frpwr / _fragm (:218)
+        wr = (wr + 1) & 63;
+        __syncwarp ();
+        r.frag_power = p;
+        // addfrags (8), addfrags (60) (:251-260): sequential sums, oldest fragment first
+        float s8 = 0.0f, s60 = 0.0f;
+        { const int k = (wr - 8) & 63;  for (int i = 0; i < 8; ++i)  s8  = __fadd_rn (s8,  rg[(i + k) & 63]); }
+        { const int k = (wr - 60) & 63; for (int i = 0; i < 60; ++i) s60 = __fadd_rn (s60, rg[(i + k) & 63]); }
+        float lm = __fadd_rn (-0.6976f, __fmul_rn (10.0f, log10f_glibc (__fdiv_rn (s8, 8.0f))));
+        float ls = __fadd_rn (-0.6976f, __fmul_rn (10.0f, log10f_glibc (__fdiv_rn (s60, 60.0f))));
+        if (!finitef_ (lm) || lm < -200.0f) lm = -200.0f;  // :224-225
+        if (!finitef_ (ls) || ls < -200.0f) ls = -200.0f;
+        r.loudness_M = lm; r.loudness_S = ls;
+        if (lm > r.maxloudn_M) r.maxloudn_M = lm;
+        if (ls > r.maxloudn_S) r.maxloudn_S = ls;
+        if (c.integr) {                                     // :228-242
+            if (++c.div1 == 2) {
+                const int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, lm), 700.5f));
+                hist_addpoint (hM, ct + 0, ct + 2, lm, lane);
+                if (k >= 0) ++cntM;
+                c.div1 = 0;
+            }
+            if (++c.div2 == 10) {
+                const int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, ls), 700.5f));
+                hist_addpoint (hS, ct + 1, ct + 3, ls, lane);
+                if (k >= 0) ++cntS;
+                c.div2 = 0;
+                __syncwarp ();                              // lane 0's bin updates -> visible to the warp
+                hist_calc_integ (hM, cntM, sbp, lane, r.integrated, r.integ_thr);
+                hist_calc_range (hS, cntS, sbp, lane, r.range_min, r.range_max, r.range_thr);
+            }
+        }
+    }
+    __syncwarp ();
+    ring[(size_t)inst * 64 + lane] = rg[lane];
+    ring[(size_t)inst * 64 + lane + 32] = rg[lane + 32];
+    if (lane == 0) {
+        r.hist_M_count = cntM; r.hist_S_count = cntS;
+        ctl[inst] = c; res[inst] = r;
+    }
+}
+
+// reset / integration control, one thread per instance
+__global__ void ebu_ctl_kernel (int n_inst, int inst_sel, int cmd, int nchan, float* zst, float* frpwr, float* ring,
+                                EbuCtl* ctl, b200m_ebu_result* res, int* histM, int* histS, int* cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_inst || (inst_sel >= 0 && i != inst_sel)) return;
+    if (cmd == 0) { ctl[i].integr = 0; return; }            // integr_pause
+    if (cmd == 1) { ctl[i].integr = 1; return; }            // integr_start
+    // cmd 2: integr_reset (:193-204); cmd 3: reset (:176-190) = integr off + filter/ring clear + integr_reset
+    for (int b = 0; b < HIST_PITCH; ++b) { histM[(size_t)i * HIST_PITCH + b] = 0; histS[(size_t)i * HIST_PITCH + b] = 0; }
+    for (int b = 0; b < 4; ++b) cnt[(size_t)i * 4 + b] = 0;
+    b200m_ebu_result r = res[i];
+    r.maxloudn_M = r.maxloudn_S = r.integrated = r.integ_thr = -200.0f;
+    r.range_min = r.range_max = r.range_thr = -200.0f;
+    r.hist_M_count = r.hist_S_count = 0;
+    ctl[i].div1 = ctl[i].div2 = 0;
+    if (cmd == 3) {
+        ctl[i].integr = 0;
+        frpwr[i] = 1e-30f;
+        r.loudness_M = r.loudness_S = -200.0f; r.frag_power = 0.0f;
+        for (int b = 0; b < 64; ++b) ring[(size_t)i * 64 + b] = 0.0f;
+        const size_t nch = (size_t)n_inst * nchan;
+        for (int c = 0; c < nchan; ++c) for (int z = 0; z < 4; ++z) zst[z * nch + (size_t)i * nchan + c] = 0.0f;
+    }
+    res[i] = r;
+}
+
+// whole-mix histogram sum: grid-stride atomics into one int32[B200M_MIX_WORDS] vector
+__global__ void ebu_mix_reduce_kernel (int n_inst, const int* __restrict__ histM, const int* __restrict__ histS,
+                                       const int* __restrict__ cnt, int* __restrict__ out)
+{
+    // block b handles bin column(s); thread t strides over instances: coalescing is across bins
+    const int col = blockIdx.x * blockDim.x + threadIdx.x;    // 0..1507
+    if (col >= B200M_MIX_WORDS) return;
+    int acc = 0;
+    if (col < 752)       for (int i = 0; i < n_inst; ++i) acc += histM[(size_t)i * HIST_PITCH + col];
+    else if (col < 1504) for (int i = 0; i < n_inst; ++i) acc += histS[(size_t)i * HIST_PITCH + (col - 752)];
+    else                 for (int i = 0; i < n_inst; ++i) acc += cnt[(size_t)i * 4 + (col - 1504)];
+    out[col] = acc;
+}
+
+__global__ void ebu_mix_finish_kernel (const int* __restrict__ mix, const float* __restrict__ bin_power, float* out5)
+{
+    __shared__ float sbp[100];
+    for (int i = threadIdx.x; i < 100; i += blockDim.x) sbp[i] = bin_power[i];
+    __syncthreads ();
+    const int lane = threadIdx.x;
+    float vi = -200.0f, th = -200.0f, v0 = -200.0f, v1 = -200.0f, rt = -200.0f;
+    hist_calc_integ (mix, mix[1504], sbp, lane, vi, th);
+    hist_calc_range (mix + 752, mix[1505], sbp, lane, v0, v1, rt);
+    if (lane == 0) { out5[0] = vi; out5[1] = th; out5[2] = v0; out5[3] = v1; out5[4] = rt; }
+}
+
+}  // namespace b200m
+
+using namespace b200m;
+
+// ---------------------------------------------------------------------------- host side
+struct b200m_ebu {
+    int device; uint32_t n_inst, nchan; float fsamp; int fragm;
+    int frcnt, wrind;                    // shared 50 ms fragment clock (host-tracked, see b200meters.h)
+    EbuCoef cf;
+    float *d_z = nullptr, *d_frpwr = nullptr, *d_fragpw = nullptr, *d_ring = nullptr, *d_binpow = nullptr, *d_out5 = nullptr;
+    EbuCtl* d_ctl = nullptr; b200m_ebu_result* d_res = nullptr;
+    int *d_histM = nullptr, *d_histS = nullptr, *d_cnt = nullptr;
+    cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
+};
+
+// Host-side coefficient design; restates Ebu_r128_proc::detect_init (ebu_r128_proc.cc:263-293).
+// Same literals and the same float expression types (tan on a float argument is the float
+// overload in C++), evaluated with the host libm, so every coefficient is bitwise the oracle's.
+static void ebu_design (float fsamp, EbuCoef& k)
+{
+    const float rt = 1 / tanf (4712.3890f / fsamp);
+    const float wa = rt / 1.12201f, wb = rt * 1.12201f;
+    const float u = 1.4085f + 210.0f / fsamp;
+    const float pa = u * wa, pb = wa * wa, pc = u * wb, pd = wb * wb;
+    const float den = 1 + pa + pb;
+    k.a0 = (1 + pc + pd) / den;
+    k.a1 = (2 - 2 * pd) / den;
+    k.a2 = (1 - pc + pd) / den;
+    k.b1 = (2 - 2 * pb) / den;
+    k.b2 = (1 - pa + pb) / den;
+    const float q = 48.0f / fsamp;
+    float ha = 4.9886075f * q, hb = 6.2298014f * q * q;
+    const float hden = 1 + ha + hb;
+    ha *= 2 / hden; hb *= 4 / hden;
+    k.c3 = ha + hb; k.c4 = hb;
+    const float g = 1.004995f / hden;
+    k.a0 *= g; k.a1 *= g; k.a2 *= g;
+}
+
+static int ebu_ctl (b200m_ebu* h, int32_t inst, int cmd, void* stream)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    if (inst >= (int32_t)h->n_inst) return set_err (B200M_E_INVAL, "instance %d out of range", inst);
+    DeviceGuard g (h->device);
+    ebu_ctl_kernel<<<(h->n_inst + 127) / 128, 128, 0, (cudaStream_t)stream>>> (
+        (int)h->n_inst, inst, cmd, (int)h->nchan, h->d_z, h->d_frpwr, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+extern "C" {
+
+int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nchan, float fsamp)
+{
+    if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");
+    *out = nullptr;
+    if (n_inst == 0 || !(fsamp >= 1000.0f)) return set_err (B200M_E_INVAL, "bad n_inst/fsamp");
+    if (nchan < 1 || nchan > 5) return set_err (B200M_E_INVAL, "nchan %u outside 1..5", nchan);
+    if (nchan > 2) return set_err (B200M_E_UNSUPPORTED, "nchan %u: only mono and stereo banks are provided", nchan);
+    if (b200m_device_count () <= 0) return set_err (B200M_E_NODEVICE, "no CUDA device: b200meters has no CPU path");
+    DeviceGuard g (device);
+    if (!g.ok) return set_err (B200M_E_NODEVICE, "cannot select CUDA device %d", device);
+    b200m_ebu* h = new (std::nothrow) b200m_ebu;
+    if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
+    h->device = device; h->n_inst = n_inst; h->nchan = nchan; h->fsamp = fsamp;
+    h->fragm = (int)fsamp / 20;                     // :170
+    h->frcnt = h->fragm; h->wrind = 0;
+    ebu_design (fsamp, h->cf);
+    const size_t nch = (size_t)n_inst * nchan;
+    float bp[100];
+    for (int i = 0; i < 100; ++i) bp[i] = powf (10.0f, i / 100.0f);   // Ebu_r128_hist::initstat (:54-63)
+    cudaError_t e = cudaSuccess;
+    auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
+    A ((void**)&h->d_z, 4 * nch * sizeof (float));
+    A ((void**)&h->d_frpwr, n_inst * sizeof (float));
+    A ((void**)&h->d_fragpw, (size_t)EBU_MAXCHUNK * n_inst * sizeof (float));
+    A ((void**)&h->d_ring, (size_t)64 * n_inst * sizeof (float));
+    A ((void**)&h->d_binpow, 100 * sizeof (float));
+    A ((void**)&h->d_out5, 8 * sizeof (float));
+    A ((void**)&h->d_ctl, n_inst * sizeof (EbuCtl));
+    A ((void**)&h->d_res, n_inst * sizeof (b200m_ebu_result));
+    A ((void**)&h->d_histM, (size_t)HIST_PITCH * n_inst * sizeof (int));
+    A ((void**)&h->d_histS, (size_t)HIST_PITCH * n_inst * sizeof (int));
+    A ((void**)&h->d_cnt, (size_t)4 * n_inst * sizeof (int));
+    if (e == cudaSuccess) e = cudaMemcpy (h->d_binpow, bp, sizeof (bp), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { int rc = cuda_fail (e, "ebu_create allocations", __FILE__, __LINE__); b200m_ebu_destroy (h); return rc; }
+    int rc = b200m_ebu_reset (h, -1, nullptr);       // constructor + init() end in reset() (:153-173)
+    if (rc == 0 && cudaDeviceSynchronize () != cudaSuccess) rc = set_err (B200M_E_CUDA, "reset kernel failed");
+    if (rc) { b200m_ebu_destroy (h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int b200m_ebu_destroy (b200m_ebu* h)
+{
+    if (!h) return 0;
+    DeviceGuard g (h->device);
+    cudaDeviceSynchronize ();
+    cudaFree (h->d_z); cudaFree (h->d_frpwr); cudaFree (h->d_fragpw); cudaFree (h->d_ring); cudaFree (h->d_binpow);
+    cudaFree (h->d_out5); cudaFree (h->d_ctl); cudaFree (h->d_res); cudaFree (h->d_histM); cudaFree (h->d_histS); cudaFree (h->d_cnt);
+    h->stage.release ();
+    if (h->own) cudaStreamDestroy (h->own);
+    delete h;
+    return 0;
+}
+
+int b200m_ebu_reset (b200m_ebu* h, int32_t inst, void* stream)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    if (inst != -1) return set_err (B200M_E_UNSUPPORTED, "reset() restarts the shared fragment clock: only inst = -1");
+    h->frcnt = h->fragm; h->wrind = 0;
+    return ebu_ctl (h, -1, 3, stream);
+}
+int b200m_ebu_integr_start (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 1, stream); }
+int b200m_ebu_integr_pause (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 0, stream); }
+int b200m_ebu_integr_reset (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 2, stream); }
+
+static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
+{
+    const int nch = (int)(h->n_inst * h->nchan);
+    const bool aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
+    uint32_t done = 0;
+    while (done < nfram) {
+        // cut [done, nfram) at fragment edges, at most EBU_MAXCHUNK pieces per launch (:212-216)
+        EbuChunks ck; ck.n = 0;
+        int nfrag = 0; uint32_t pos = 0;
+        while (done + pos < nfram && ck.n < EBU_MAXCHUNK) {
+            const uint32_t rem = nfram - done - pos;
+            const uint32_t k = (uint32_t)h->frcnt < rem ? (uint32_t)h->frcnt : rem;
+            pos += k; h->frcnt -= (int)k;
+            uint32_t v = pos;
+            if (h->frcnt == 0) { v |= 0x80000000u; h->frcnt = h->fragm; ++nfrag; }
+            ck.v[ck.n++] = v;
+        }
+        const float* src = d_in + done;
+        const bool al = aligned && (done % 4 == 0);
+        dim3 grid ((nch + 31) / 32), blk (32);
+#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, 0, st>>> (src, stride, nch, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
+        if (h->nchan == 1) { if (al) EBU_K1 (1, true); else EBU_K1 (1, false); }
+        else               { if (al) EBU_K1 (2, true); else EBU_K1 (2, false); }
+#undef EBU_K1
+        B200M_LAUNCHED (1);
+        if (nfrag) {
+            ebu_loudness_hist<<<(h->n_inst + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>> (
+                (int)h->n_inst, nfrag, h->wrind, h->d_fragpw, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt, h->d_binpow);
+            B200M_LAUNCHED (1);
+            h->wrind = (h->wrind + nfrag) & 63;
+        }
+        done += pos;
+    }
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+int b200m_ebu_process_device (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, void* stream)
+{
+    if (int rc = check_block_args (h, d_in, stride, nfram)) return rc;
+    DeviceGuard g (h->device);
+    h->last_host = false;
+    return ebu_process (h, d_in, stride, nfram, (cudaStream_t)stream);
+}
+
+int b200m_ebu_process_host (b200m_ebu* h, const float* in, size_t stride, uint32_t nfram)
+{
+    if (int rc = check_block_args (h, in, stride, nfram)) return rc;
+    DeviceGuard g (h->device);
+    const size_t nch = (size_t)h->n_inst * h->nchan;
+    if (h->stage.ensure (nch, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
+    B200M_CUDA (cudaMemcpy2DAsync (h->stage.d, h->stage.cap * sizeof (float), in, stride * sizeof (float),
+                                   (size_t)nfram * sizeof (float), nch, cudaMemcpyHostToDevice, h->own));
+    h->last_host = true;
+    return ebu_process (h, h->stage.d, h->stage.cap, nfram, h->own);
+}
+
+static cudaStream_t ebu_stream (b200m_ebu* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
+
+int b200m_ebu_results (b200m_ebu* h, b200m_ebu_result* out, void* stream)
+{
+    if (!h || !out) return set_err (B200M_E_INVAL, "NULL argument");
+    DeviceGuard g (h->device);
+    cudaStream_t st = ebu_stream (h, stream);
+    B200M_CUDA (cudaMemcpyAsync (out, h->d_res, h->n_inst * sizeof (b200m_ebu_result), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_ebu_histogram (b200m_ebu* h, uint32_t inst, int32_t* hist_M, int32_t* hist_S, void* stream)
+{
+    if (!h || !hist_M || !hist_S || inst >= h->n_inst) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    cudaStream_t st = ebu_stream (h, stream);
+    B200M_CUDA (cudaMemcpyAsync (hist_M, h->d_histM + (size_t)inst * HIST_PITCH, 751 * sizeof (int), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaMemcpyAsync (hist_S, h->d_histS + (size_t)inst * HIST_PITCH, 751 * sizeof (int), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_ebu_coeffs (const b200m_ebu* h, float o[7])
+{
+    if (!h || !o) return set_err (B200M_E_INVAL, "NULL argument");
+    o[0] = h->cf.a0; o[1] = h->cf.a1; o[2] = h->cf.a2; o[3] = h->cf.b1; o[4] = h->cf.b2; o[5] = h->cf.c3; o[6] = h->cf.c4;
+    return 0;
+}
+
+int b200m_ebu_state (b200m_ebu* h, uint32_t inst, float* z, float* power64, float* frpwr, int32_t c4[4], void* stream)
+{
+    if (!h || !z || !power64 || !frpwr || !c4 || inst >= h->n_inst) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    cudaStream_t st = ebu_stream (h, stream);
+    const size_t nch = (size_t)h->n_inst * h->nchan;
+    for (uint32_t c = 0; c < h->nchan; ++c)
+        for (int q = 0; q < 4; ++q)
+            B200M_CUDA (cudaMemcpyAsync (z + 4 * c + q, h->d_z + q * nch + (size_t)inst * h->nchan + c, sizeof (float), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaMemcpyAsync (power64, h->d_ring + (size_t)inst * 64, 64 * sizeof (float), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaMemcpyAsync (frpwr, h->d_frpwr + inst, sizeof (float), cudaMemcpyDeviceToHost, st));
+    EbuCtl c;
+    B200M_CUDA (cudaMemcpyAsync (&c, h->d_ctl + inst, sizeof (c), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    c4[0] = h->frcnt; c4[1] = h->wrind; c4[2] = c.div1; c4[3] = c.div2;
+    return 0;
+}
+
+int b200m_ebu_mix_reduce (b200m_ebu* h, int32_t* d_out, void* stream)
+{
+    if (!h || !d_out) return set_err (B200M_E_INVAL, "NULL argument");
+    DeviceGuard g (h->device);
+    ebu_mix_reduce_kernel<<<(B200M_MIX_WORDS + 63) / 64, 64, 0, ebu_stream (h, stream)>>> ((int)h->n_inst, h->d_histM, h->d_histS, h->d_cnt, d_out);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+int b200m_ebu_mix_finish (b200m_ebu* h, const int32_t* d_mix, float out5[5], void* stream)
+{
+    if (!h || !d_mix || !out5) return set_err (B200M_E_INVAL, "NULL argument");
+    DeviceGuard g (h->device);
+    cudaStream_t st = ebu_stream (h, stream);
+    ebu_mix_finish_kernel<<<1, 32, 0, st>>> (d_mix, h->d_binpow, h->d_out5);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaMemcpyAsync (out5, h->d_out5, 5 * sizeof (float), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+}  // extern "C"

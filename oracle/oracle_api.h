@@ -1,0 +1,93 @@
+/* oracle_api.h — C API shared by the two CPU oracles of this repo.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * `--impl reference` leg may load these libraries, and only as the checker
+ * (or as the timed CPU baseline), never as the thing shipped.
+ *
+ * Two shared objects export exactly this API:
+ *   oracle/_ref/libmeters_ref.so   kind "reference": the UNMODIFIED reference
+ *        sources compiled by path from /root/reference (oracle/Makefile),
+ *        driven through thin extern "C" shims (oracle/ref_wrap.cc).
+ *   oracle/liboracle_port.so       kind "port": a from-scratch CPU restatement
+ *        of the same algorithms (oracle/oracle_port.cc), each function citing
+ *        the reference file:line it follows.  It is pinned against the
+ *        reference build and the committed golden vectors by tests/.
+ *
+ * Layout convention for every process call: channel k (k = inst*nchan + c)
+ * starts at  in + k*stride  and holds nfram float32 samples (planar audio,
+ * as an LV2 host hands it to run(), src/meters.cc:257-296).
+ */
+#ifndef B200M_ORACLE_API_H
+#define B200M_ORACLE_API_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* orc_kind (void);            /* "reference" | "port" */
+int         orc_hw_threads (void);
+
+/* ---- EBU R128  (ebumeter/ebu_r128_proc.h:66-125) ---- */
+void* orc_ebu_create  (int n_inst, int nchan, float fsamp);
+void  orc_ebu_destroy (void* h);
+void  orc_ebu_integr  (void* h, int inst, int cmd);   /* 0 pause 1 start 2 reset; inst<0 = all */
+void  orc_ebu_reset   (void* h, int inst);             /* Ebu_r128_proc::reset */
+void  orc_ebu_process (void* h, const float* in, size_t stride, int nfram, int nthreads);
+void  orc_ebu_read    (void* h, float* out);           /* [n_inst][9] M maxM S maxS I Ithr Rmin Rmax Rthr */
+void  orc_ebu_hist    (void* h, int inst, int* histM, int* histS, int* counts4); /* 751,751,{cntM,cntS,errM,errS} */
+void  orc_ebu_coeffs  (void* h, float* out7);          /* a0 a1 a2 b1 b2 c3 c4 */
+void  orc_ebu_state   (void* h, int inst, float* z, float* power64, float* frpwr, int* counters4);
+                       /* z: [nchan][4]; counters: frcnt wrind div1 div2 */
+
+/* ---- True peak (jmeters/truepeakdsp.h:28-61), one mono meter per channel ---- */
+void* orc_tp_create   (int n, float fsamp);
+void  orc_tp_destroy  (void* h);
+void  orc_tp_process  (void* h, const float* in, size_t stride, int nfram, int mode, int nthreads);
+                       /* mode 0: process()   mode 1: process_max() */
+void  orc_tp_read     (void* h, float* m, float* p);   /* TruePeakdsp::read(m,p) for every meter */
+void  orc_tp_peek     (void* h, float* m, float* p, float* z1, float* z2, int* res); /* no side effect */
+void  orc_tp_reset    (void* h, int inst);
+void  orc_tp_coeffs   (void* h, float* w4, float* ctab120); /* w1 w2 w3 g ; resampler table (np+1)*hl */
+/* raw 4x stream of a fresh meter (after init's pre-roll): out has 4*n floats */
+void  orc_tp_upsample (float fsamp, const float* in, int n, int block, float* out);
+
+/* ---- K-meter (jmeters/kmeterdsp.h:27-62) ---- */
+void* orc_km_create   (int n, float fsamp);
+void  orc_km_destroy  (void* h);
+void  orc_km_process  (void* h, const float* in, size_t stride, int nfram, int nthreads);
+void  orc_km_read     (void* h, float* rms, float* peak);        /* Kmeterdsp::read(rms,peak) */
+void  orc_km_peek     (void* h, float* state8);                  /* [n][8] z1 z2 rms peak fall cnt fpp flag */
+void  orc_km_reset    (void* h, int inst);
+void  orc_km_coeffs   (void* h, float* omega, int* hold);
+
+/* ---- Stereo correlation (jmeters/stcorrdsp.h:27-55) ---- */
+void* orc_cor_create  (int n, int fsamp, float flp, float tcf);
+void  orc_cor_destroy (void* h);
+void  orc_cor_process (void* h, const float* in, size_t stride, int nfram, int nthreads); /* L,R = ch 2i,2i+1 */
+void  orc_cor_read    (void* h, float* out);
+void  orc_cor_peek    (void* h, float* state5);                  /* [n][5] zl zr zlr zll zrr */
+void  orc_cor_coeffs  (void* h, float* w2);
+
+/* ---- 30 band 1/3 octave spectrum (src/spectrumlv2.c:73-257, src/spectr.c:68-206) ---- */
+void* orc_spec_create (int n_inst, int nchan, double rate);
+void  orc_spec_destroy(void* h);
+void  orc_spec_process(void* h, const float* in, size_t stride, int nfram, float speed, float reset, int nthreads);
+void  orc_spec_read   (void* h, float* out60);                   /* [n_inst][60]: 30 band dB, 30 max dB (ports 0-59) */
+void  orc_spec_state  (void* h, int inst, double* z360, float* val30, float* max30);
+void  orc_spec_coeffs (void* h, double* W);                      /* [30][6][6] a0 a1 a2 b0 b1 b2 */
+
+/* ---- phasewheel / stereoscope FFT analysis (gui/fft.c:208-340, gui/phasewheel.c:1307-1342) ----
+ * kind "reference" returns NULL from orc_pw_create: FFTW3 is not vendored and absent here. */
+void* orc_pw_create   (int n_inst, int fft_bins, double rate);
+void  orc_pw_destroy  (void* h);
+int   orc_pw_process  (void* h, const float* in, size_t stride, int nfram, float db_thresh, int nthreads);
+                       /* returns 1 if an analysis fired (all instances are in lock step) */
+void  orc_pw_read     (void* h, float* phase, float* level, float* peak); /* [n_inst][fft_bins] x2, [n_inst] */
+void  orc_pw_raw      (void* h, int inst, float* powL, float* powR, float* phL, float* phR);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

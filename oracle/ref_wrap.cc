@@ -1,0 +1,248 @@
+// ref_wrap.cc — extern "C" shims (oracle_api.h) over the UNMODIFIED reference classes.
+//
+// TEST INFRASTRUCTURE ONLY (see oracle_api.h).  This file contains no DSP: every
+// sample is processed by the reference's own objects, compiled by path from
+// /root/reference by oracle/Makefile into oracle/_ref/ (never copied into the repo):
+//   jmeters/{truepeakdsp,kmeterdsp,stcorrdsp}.cc, ebumeter/ebu_r128_proc.cc,
+//   zita-resampler/{resampler,resampler-table}.cc, src/spectr.c + src/spectrumlv2.c
+// `#define private public` around the reference headers only exposes internal state
+// (filter registers, counters) to the parity tests; it does not change any layout.
+#include <math.h>
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define private public
+#include "jmeters/truepeakdsp.h"
+#include "jmeters/kmeterdsp.h"
+#include "jmeters/stcorrdsp.h"
+#include "ebumeter/ebu_r128_proc.h"
+#include "zita-resampler/resampler-table.h"
+#undef private
+
+#include "oracle_api.h"
+
+// The spectrum plugin is a pair of "static include" files (src/meters.cc:672-681);
+// ref_spectr_tu.cc compiles them untouched behind a types-only LV2 stub and exports
+// these five hooks.
+extern "C" {
+void* refspec_new (double rate, int nchan);
+void  refspec_free (void* s);
+void  refspec_run (void* s, const float* l, const float* r, uint32_t n, float speed, float reset, float* ports60);
+void  refspec_state (void* s, double* z360, float* val30, float* max30);
+void  refspec_coeffs (void* s, double* W);
+}
+
+using namespace LV2M;
+
+static void par_for (int n, int nthreads, const std::function<void(int, int)>& fn)
+{
+    if (nthreads <= 1 || n <= 1) { fn (0, n); return; }
+    if (nthreads > n) nthreads = n;
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; ++t) {
+        int a = (int)((int64_t)n * t / nthreads), b = (int)((int64_t)n * (t + 1) / nthreads);
+        th.emplace_back ([=, &fn] { fn (a, b); });
+    }
+    for (auto& t : th) t.join ();
+}
+
+extern "C" {
+
+const char* orc_kind (void) { return "reference"; }
+int orc_hw_threads (void) { return (int)std::thread::hardware_concurrency (); }
+
+/* ------------------------------------------------------------------ EBU */
+struct EbuB { int n, nchan; std::vector<Ebu_r128_proc*> p; };
+
+void* orc_ebu_create (int n_inst, int nchan, float fsamp)
+{
+    EbuB* b = new EbuB; b->n = n_inst; b->nchan = nchan;
+    for (int i = 0; i < n_inst; ++i) { Ebu_r128_proc* e = new Ebu_r128_proc; e->init (nchan, fsamp); b->p.push_back (e); }
+    return b;
+}
+void orc_ebu_destroy (void* h) { EbuB* b = (EbuB*)h; for (auto e : b->p) delete e; delete b; }
+void orc_ebu_integr (void* h, int inst, int cmd)
+{
+    EbuB* b = (EbuB*)h;
+    for (int i = 0; i < b->n; ++i) {
+        if (inst >= 0 && i != inst) continue;
+        if (cmd == 0) b->p[i]->integr_pause (); else if (cmd == 1) b->p[i]->integr_start (); else b->p[i]->integr_reset ();
+    }
+}
+void orc_ebu_reset (void* h, int inst)
+{
+    EbuB* b = (EbuB*)h;
+    for (int i = 0; i < b->n; ++i) if (inst < 0 || i == inst) b->p[i]->reset ();
+}
+void orc_ebu_process (void* h, const float* in, size_t stride, int nfram, int nthreads)
+{
+    EbuB* b = (EbuB*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            float* ip[MAXCH];
+            for (int c = 0; c < b->nchan; ++c) ip[c] = const_cast<float*> (in + ((size_t)i * b->nchan + c) * stride);
+            b->p[i]->process (nfram, ip);
+        }
+    });
+}
+void orc_ebu_read (void* h, float* out)
+{
+    EbuB* b = (EbuB*)h;
+    for (int i = 0; i < b->n; ++i) {
+        Ebu_r128_proc* e = b->p[i]; float* o = out + 9 * i;
+        o[0] = e->loudness_M (); o[1] = e->maxloudn_M (); o[2] = e->loudness_S (); o[3] = e->maxloudn_S ();
+        o[4] = e->integrated (); o[5] = e->integ_thr (); o[6] = e->range_min (); o[7] = e->range_max (); o[8] = e->range_thr ();
+    }
+}
+void orc_ebu_hist (void* h, int inst, int* hm, int* hs, int* c4)
+{
+    Ebu_r128_proc* e = ((EbuB*)h)->p[inst];
+    memcpy (hm, e->histogram_M (), 751 * sizeof (int)); memcpy (hs, e->histogram_S (), 751 * sizeof (int));
+    c4[0] = e->hist_M_count (); c4[1] = e->hist_S_count (); c4[2] = e->_hist_M._error; c4[3] = e->_hist_S._error;
+}
+void orc_ebu_coeffs (void* h, float* o)
+{
+    Ebu_r128_proc* e = ((EbuB*)h)->p[0];
+    o[0] = e->_a0; o[1] = e->_a1; o[2] = e->_a2; o[3] = e->_b1; o[4] = e->_b2; o[5] = e->_c3; o[6] = e->_c4;
+}
+void orc_ebu_state (void* h, int inst, float* z, float* pw, float* frpwr, int* c4)
+{
+    EbuB* b = (EbuB*)h; Ebu_r128_proc* e = b->p[inst];
+    for (int c = 0; c < b->nchan; ++c) { z[4*c] = e->_fst[c]._z1; z[4*c+1] = e->_fst[c]._z2; z[4*c+2] = e->_fst[c]._z3; z[4*c+3] = e->_fst[c]._z4; }
+    memcpy (pw, e->_power, 64 * sizeof (float)); *frpwr = e->_frpwr;
+    c4[0] = e->_frcnt; c4[1] = e->_wrind; c4[2] = e->_div1; c4[3] = e->_div2;
+}
+
+/* ------------------------------------------------------------------ True peak */
+struct TpB { int n; std::vector<TruePeakdsp*> p; };
+void* orc_tp_create (int n, float fsamp)
+{
+    TpB* b = new TpB; b->n = n;
+    for (int i = 0; i < n; ++i) { TruePeakdsp* t = new TruePeakdsp; t->init (fsamp); b->p.push_back (t); }
+    return b;
+}
+void orc_tp_destroy (void* h) { TpB* b = (TpB*)h; for (auto t : b->p) delete t; delete b; }
+void orc_tp_process (void* h, const float* in, size_t stride, int nfram, int mode, int nthreads)
+{
+    TpB* b = (TpB*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            float* p = const_cast<float*> (in + (size_t)i * stride);
+            if (mode) b->p[i]->process_max (p, nfram); else b->p[i]->process (p, nfram);
+        }
+    });
+}
+void orc_tp_read (void* h, float* m, float* p) { TpB* b = (TpB*)h; for (int i = 0; i < b->n; ++i) b->p[i]->read (m[i], p[i]); }
+void orc_tp_peek (void* h, float* m, float* p, float* z1, float* z2, int* res)
+{
+    TpB* b = (TpB*)h;
+    for (int i = 0; i < b->n; ++i) { TruePeakdsp* t = b->p[i]; m[i] = t->_m; p[i] = t->_p; z1[i] = t->_z1; z2[i] = t->_z2; res[i] = t->_res; }
+}
+void orc_tp_reset (void* h, int inst) { TpB* b = (TpB*)h; for (int i = 0; i < b->n; ++i) if (inst < 0 || i == inst) b->p[i]->reset (); }
+void orc_tp_coeffs (void* h, float* w4, float* ctab)
+{
+    TruePeakdsp* t = ((TpB*)h)->p[0];
+    w4[0] = t->_w1; w4[1] = t->_w2; w4[2] = t->_w3; w4[3] = t->_g;
+    Resampler_table* T = t->_src._table;
+    memcpy (ctab, T->_ctab, sizeof (float) * T->_hl * (T->_np + 1));
+}
+void orc_tp_upsample (float fsamp, const float* in, int n, int block, float* out)
+{
+    TruePeakdsp t; t.init (fsamp);
+    for (int o = 0; o < n; o += block) {
+        int k = n - o < block ? n - o : block;
+        t._src.inp_count = k; t._src.inp_data = const_cast<float*> (in + o);
+        t._src.out_count = 4 * k; t._src.out_data = out + 4 * o;
+        t._src.process ();
+    }
+}
+
+/* ------------------------------------------------------------------ K-meter */
+struct KmB { int n; std::vector<Kmeterdsp*> p; };
+void* orc_km_create (int n, float fsamp)
+{
+    KmB* b = new KmB; b->n = n;
+    for (int i = 0; i < n; ++i) { Kmeterdsp* k = new Kmeterdsp; k->init (fsamp); b->p.push_back (k); }
+    return b;
+}
+void orc_km_destroy (void* h) { KmB* b = (KmB*)h; for (auto k : b->p) delete k; delete b; }
+void orc_km_process (void* h, const float* in, size_t stride, int nfram, int nthreads)
+{
+    KmB* b = (KmB*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) { for (int i = a; i < e; ++i) b->p[i]->process (const_cast<float*> (in + (size_t)i * stride), nfram); });
+}
+void orc_km_read (void* h, float* rms, float* peak) { KmB* b = (KmB*)h; for (int i = 0; i < b->n; ++i) b->p[i]->read (rms[i], peak[i]); }
+void orc_km_peek (void* h, float* s)
+{
+    KmB* b = (KmB*)h;
+    for (int i = 0; i < b->n; ++i) {
+        Kmeterdsp* k = b->p[i]; float* o = s + 8 * i;
+        o[0] = k->_z1; o[1] = k->_z2; o[2] = k->_rms; o[3] = k->_peak; o[4] = k->_fall; o[5] = (float)k->_cnt; o[6] = (float)k->_fpp; o[7] = k->_flag;
+    }
+}
+void orc_km_reset (void* h, int inst) { KmB* b = (KmB*)h; for (int i = 0; i < b->n; ++i) if (inst < 0 || i == inst) b->p[i]->reset (); }
+void orc_km_coeffs (void*, float* omega, int* hold) { *omega = Kmeterdsp::_omega; *hold = Kmeterdsp::_hold; }
+
+/* ------------------------------------------------------------------ Stcorr */
+struct CorB { int n; std::vector<Stcorrdsp*> p; };
+void* orc_cor_create (int n, int fsamp, float flp, float tcf)
+{
+    CorB* b = new CorB; b->n = n;
+    for (int i = 0; i < n; ++i) { Stcorrdsp* c = new Stcorrdsp; c->init (fsamp, flp, tcf); b->p.push_back (c); }
+    return b;
+}
+void orc_cor_destroy (void* h) { CorB* b = (CorB*)h; for (auto c : b->p) delete c; delete b; }
+void orc_cor_process (void* h, const float* in, size_t stride, int nfram, int nthreads)
+{
+    CorB* b = (CorB*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i)
+            b->p[i]->process (const_cast<float*> (in + (size_t)(2 * i) * stride), const_cast<float*> (in + (size_t)(2 * i + 1) * stride), nfram);
+    });
+}
+void orc_cor_read (void* h, float* out) { CorB* b = (CorB*)h; for (int i = 0; i < b->n; ++i) out[i] = b->p[i]->read (); }
+void orc_cor_peek (void* h, float* s)
+{
+    CorB* b = (CorB*)h;
+    for (int i = 0; i < b->n; ++i) { Stcorrdsp* c = b->p[i]; float* o = s + 5 * i; o[0] = c->_zl; o[1] = c->_zr; o[2] = c->_zlr; o[3] = c->_zll; o[4] = c->_zrr; }
+}
+void orc_cor_coeffs (void*, float* w2) { w2[0] = Stcorrdsp::_w1; w2[1] = Stcorrdsp::_w2; }
+
+/* ------------------------------------------------------------------ spectr30 */
+struct SpB { int n, nchan; std::vector<void*> p; std::vector<float> ports; };
+void* orc_spec_create (int n_inst, int nchan, double rate)
+{
+    SpB* b = new SpB; b->n = n_inst; b->nchan = nchan; b->ports.assign ((size_t)n_inst * 60, 0.f);
+    for (int i = 0; i < n_inst; ++i) { void* s = refspec_new (rate, nchan); if (!s) { delete b; return 0; } b->p.push_back (s); }
+    return b;
+}
+void orc_spec_destroy (void* h) { SpB* b = (SpB*)h; for (auto s : b->p) refspec_free (s); delete b; }
+void orc_spec_process (void* h, const float* in, size_t stride, int nfram, float speed, float reset, int nthreads)
+{
+    SpB* b = (SpB*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            const float* l = in + (size_t)i * b->nchan * stride;
+            const float* r = b->nchan == 2 ? l + stride : l;
+            refspec_run (b->p[i], l, r, (uint32_t)nfram, speed, reset, &b->ports[(size_t)i * 60]);
+        }
+    });
+}
+void orc_spec_read (void* h, float* out) { SpB* b = (SpB*)h; memcpy (out, b->ports.data (), b->ports.size () * sizeof (float)); }
+void orc_spec_state (void* h, int inst, double* z, float* v, float* m) { refspec_state (((SpB*)h)->p[inst], z, v, m); }
+void orc_spec_coeffs (void* h, double* W) { refspec_coeffs (((SpB*)h)->p[0], W); }
+
+/* ------------------------------------------------------------------ phasewheel: FFTW3 absent */
+void* orc_pw_create (int, int, double) { return 0; }
+void  orc_pw_destroy (void*) {}
+int   orc_pw_process (void*, const float*, size_t, int, float, int) { return 0; }
+void  orc_pw_read (void*, float*, float*, float*) {}
+void  orc_pw_raw (void*, int, float*, float*, float*, float*) {}
+
+} // extern "C"

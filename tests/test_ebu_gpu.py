@@ -1,0 +1,149 @@
+"""GPU parity: b200m_ebu_* (CUDA) vs the CPU oracle, same seeded inputs, same block sequence."""
+import numpy as np
+import pytest
+
+import _oracle as O
+import _signals as S
+
+pytestmark = pytest.mark.gpu
+RES = ("loudness_M", "maxloudn_M", "loudness_S", "maxloudn_S", "integrated", "integ_thr", "range_min", "range_max", "range_thr")
+
+
+def _run_both(x, blocks, nchan=2, start=True, host=False, check_state=True):
+    """x: [C, total] ; blocks: list of block lengths.  Returns (gpu results, oracle results)."""
+    import torch
+    import meters_lv2_b200 as B
+    C = x.shape[0]
+    n_inst = C // nchan
+    g = B.Ebu_r128_proc(n_inst, nchan)
+    o = O.Ebu(n_inst, nchan)
+    if start:
+        g.integr_start(); o.integr("start")
+    xd = None if host else torch.from_numpy(x).cuda()
+    pos = 0
+    for n in blocks:
+        blk = np.ascontiguousarray(x[:, pos:pos + n])
+        o.process(blk, nthreads=8)
+        if host:
+            g.process(blk)
+        else:
+            g.process(xd[:, pos:pos + n])
+        pos += n
+    gr = g.results()
+    orr = o.read()
+    return g, o, gr, orr
+
+
+def _assert_equal(g, o, gr, orr, n_inst, nchan=2, exact=True):
+    for i, name in enumerate(RES):
+        a, b = gr[name], orr[:, i]
+        if exact:
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), (name, a[:4], b[:4], int((a != b).sum()))
+        else:
+            assert np.allclose(a, b, atol=1e-4, rtol=0), name      # +-1e-4 dB (north_star tolerance)
+    for inst in sorted(set([0, n_inst // 2, n_inst - 1])):
+        hm, hs = g.histogram(inst)
+        om, os_, oc = o.hist(inst)
+        assert np.array_equal(hm, om) and np.array_equal(hs, os_), "histogram counts must be bit-exact"
+        assert gr["hist_M_count"][inst] == oc[0] and gr["hist_S_count"][inst] == oc[1]
+        z, pw, fr, c = g.state(inst)
+        oz, opw, ofr, oc4 = o.state(inst)
+        assert np.array_equal(z.view(np.uint32), oz.view(np.uint32)), "filter state"
+        assert np.array_equal(pw.view(np.uint32), opw.view(np.uint32)), "fragment power ring"
+        assert np.float32(fr).view(np.uint32) == np.float32(ofr).view(np.uint32)
+        assert list(c) == list(oc4)
+
+
+def test_coeffs_bitwise():
+    import meters_lv2_b200 as B
+    for fs in (48000.0, 44100.0, 96000.0):
+        g = B.Ebu_r128_proc(1, 2, fs)
+        o = O.Ebu(1, 2, fs)
+        assert np.array_equal(g.coeffs().view(np.uint32), o.coeffs().view(np.uint32))
+
+
+@pytest.mark.parametrize("n_inst,blocks", [
+    (37, [1024] * 60),                        # ~1.3 s : M, S live, I not yet (count < 50)
+    (64, [1024] * 300),                       # 6.4 s : integrated loudness + LRA gate live
+    (5, [64] * 100 + [480] * 40 + [8192] * 6 + [1, 3, 7, 1023, 2401, 4799]),   # ragged sequence
+])
+def test_white_noise_bit_exact(n_inst, blocks):
+    x = S.white(2 * n_inst, sum(blocks))
+    g, o, gr, orr = _run_both(x, blocks)
+    _assert_equal(g, o, gr, orr, n_inst)
+
+
+def test_mono_bank():
+    x = S.white(33, 1024 * 120)
+    g, o, gr, orr = _run_both(x, [1024] * 120, nchan=1)
+    _assert_equal(g, o, gr, orr, 33, nchan=1)
+
+
+def test_host_path_and_unaligned_stride():
+    x = S.white(2 * 9, 1000 * 130 + 3)[:, 3:]              # rows start 12 bytes off a 16-byte boundary
+    x = x[:, :1000 * 130]
+    assert not x.flags.c_contiguous
+    import meters_lv2_b200 as B
+    g = B.Ebu_r128_proc(9, 2); o = O.Ebu(9, 2)
+    g.integr_start(); o.integr("start")
+    for b in range(130):
+        blk = x[:, b * 1000:(b + 1) * 1000]
+        g.process(blk)                                      # host path (numpy view, odd stride)
+        o.process(np.ascontiguousarray(blk))
+    _assert_equal(g, o, g.results(), o.read(), 9)
+
+
+def test_nan_inf_denormal_scrub():
+    x = S.nasty(2 * 8, 1024 * 64)
+    g, o, gr, orr = _run_both(x, [1024] * 64)
+    for i, name in enumerate(RES):
+        a, b = gr[name], orr[:, i]
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), name
+    z, pw, fr, c = g.state(3); oz, opw, ofr, oc4 = o.state(3)
+    assert np.array_equal(z.view(np.uint32), oz.view(np.uint32))
+
+
+def test_ebu_tech3341_tone():
+    # 997 Hz, -23 dBFS, L = R  =>  -23.0 LUFS (EBU Tech 3341 case 1); oracle gives M = -23.007
+    n = 1024 * 200
+    s = S.sine(n, 997.0, amp=10 ** (-23 / 20))
+    x = np.ascontiguousarray(np.stack([s, s]))
+    g, o, gr, orr = _run_both(x, [1024] * 200)
+    _assert_equal(g, o, gr, orr, 1)
+    assert abs(gr["loudness_M"][0] + 23.0) < 0.02 and abs(gr["integrated"][0] + 23.0) < 0.05
+
+
+def test_integration_controls_and_pause():
+    import torch
+    import meters_lv2_b200 as B
+    x = S.white(2 * 6, 1024 * 150)
+    g = B.Ebu_r128_proc(6, 2); o = O.Ebu(6, 2)
+    xd = torch.from_numpy(x).cuda()
+    for b in range(150):
+        if b == 10:
+            g.integr_start(); o.integr("start")
+        if b == 80:
+            g.integr_pause(2); o.integr("pause", 2)
+        if b == 100:
+            g.integr_reset(4); o.integr("reset", 4)
+        if b == 120:
+            g.integr_start(2); o.integr("start", 2)
+        g.process(xd[:, b * 1024:(b + 1) * 1024]); o.process(np.ascontiguousarray(x[:, b * 1024:(b + 1) * 1024]))
+    _assert_equal(g, o, g.results(), o.read(), 6)
+
+
+def test_whole_mix_histogram_extension():
+    import torch
+    import meters_lv2_b200 as B
+    n_inst = 48
+    x = S.white(2 * n_inst, 1024 * 260)
+    g, o, gr, orr = _run_both(x, [1024] * 260)
+    mix = torch.zeros(B.MIX_WORDS, dtype=torch.int32, device="cuda")
+    g.mix_reduce(mix)
+    m = mix.cpu().numpy()
+    hm = np.zeros(751, np.int64); hs = np.zeros(751, np.int64); cm = cs = 0
+    for i in range(n_inst):
+        a, b, c = o.hist(i); hm += a; hs += b; cm += c[0]; cs += c[1]
+    assert np.array_equal(m[:751], hm) and np.array_equal(m[752:752 + 751], hs) and m[1504] == cm and m[1505] == cs
+    out = g.mix_finish(mix)
+    assert np.isfinite(out).all() and -40 < out[0] < 0
