@@ -247,3 +247,184 @@ class Ebu_r128_proc(_Bank):
         out = np.empty(5, np.float32)
         _ck(lib().b200m_ebu_mix_finish(self.h, C.c_void_p(d_mix.data_ptr()), _np_ptr(out), _stream_ptr(stream)))
         return out
+
+
+TPK_TRUEPEAK, TPK_KMETER = 1, 2
+TP_MODE_PROCESS, TP_MODE_MAX = 0, 1
+
+
+class TruePeakKmeter(_Bank):
+    """N x (LV2M::TruePeakdsp + LV2M::Kmeterdsp), one mono meter of each per channel
+    (jmeters/truepeakdsp.h:28-61, jmeters/kmeterdsp.h:27-62; combined as in src/dr14.c:391-394)."""
+    _destroy = "b200m_tpk_destroy"
+
+    def __init__(self, n_chan, fsamp=48000.0, flags=TPK_TRUEPEAK | TPK_KMETER, device=0):
+        super().__init__()
+        self.n_chan, self.flags = n_chan, flags
+        _ck(lib().b200m_tpk_create(C.byref(self.h), device, n_chan, fsamp, flags))
+
+    def process(self, x, tp_mode=TP_MODE_PROCESS, stream=None):
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == self.n_chan
+            _ck(lib().b200m_tpk_process_host(self.h, p, s, n, tp_mode))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == self.n_chan
+            _ck(lib().b200m_tpk_process_device(self.h, p, s, n, tp_mode, _stream_ptr(stream)))
+
+    def process_ptr(self, ptr, stride, nfram, tp_mode=TP_MODE_PROCESS, stream=None):
+        _ck(lib().b200m_tpk_process_device(self.h, C.c_void_p(ptr), stride, nfram, tp_mode, _stream_ptr(stream)))
+
+    def process_max(self, x, stream=None):
+        self.process(x, TP_MODE_MAX, stream)
+
+    def read_device(self, stream=None):
+        _ck(lib().b200m_tpk_read_device(self.h, _stream_ptr(stream)))
+
+    def results(self, stream=None):
+        out = np.empty(self.n_chan, TPK_RESULT_DTYPE)
+        _ck(lib().b200m_tpk_results(self.h, _np_ptr(out), _stream_ptr(stream)))
+        return out
+
+    def read(self, stream=None):
+        """read() of every meter + fetch: the per-run() sequence of dr14_run (src/dr14.c:425-430)."""
+        self.read_device(stream)
+        return self.results(stream)
+
+    def reset(self, chan=-1, stream=None):
+        _ck(lib().b200m_tpk_reset(self.h, chan, _stream_ptr(stream)))
+
+    def coeffs(self):
+        w = np.empty(4, np.float32); t = np.empty(120, np.float32); k = np.empty(2, np.float32)
+        _ck(lib().b200m_tpk_coeffs(self.h, _np_ptr(w), _np_ptr(t), _np_ptr(k)))
+        return w, t, k
+
+    def state(self, stream=None):
+        n = self.n_chan
+        m, p, z1, z2 = (np.empty(n, np.float32) for _ in range(4))
+        res = np.empty(n, np.int32); km = np.empty((n, 8), np.float32)
+        _ck(lib().b200m_tpk_state(self.h, _np_ptr(m), _np_ptr(p), _np_ptr(z1), _np_ptr(z2), _np_ptr(res), _np_ptr(km), _stream_ptr(stream)))
+        return dict(m=m, p=p, z1=z1, z2=z2, res=res, km=km)
+
+    def debug_capture(self, enable=True):
+        _ck(lib().b200m_tpk_debug_capture(self.h, int(enable)))
+
+    def debug_upsampled(self, chan, n_out, stream=None):
+        out = np.empty(n_out, np.float32)
+        _ck(lib().b200m_tpk_debug_upsampled(self.h, chan, _np_ptr(out), n_out, _stream_ptr(stream)))
+        return out
+
+
+class Stcorrdsp(_Bank):
+    """N x LV2M::Stcorrdsp (jmeters/stcorrdsp.h:27-55); channels 2i, 2i+1 = L, R of pair i."""
+    _destroy = "b200m_cor_destroy"
+
+    def __init__(self, n_inst, fsamp=48000, flp=2e3, tcf=0.3, device=0):
+        super().__init__()
+        self.n_inst = n_inst
+        _ck(lib().b200m_cor_create(C.byref(self.h), device, n_inst, int(fsamp), flp, tcf))
+
+    def process(self, x, stream=None):
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == 2 * self.n_inst
+            _ck(lib().b200m_cor_process_host(self.h, p, s, n))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == 2 * self.n_inst
+            _ck(lib().b200m_cor_process_device(self.h, p, s, n, _stream_ptr(stream)))
+
+    def process_ptr(self, ptr, stride, nfram, stream=None):
+        _ck(lib().b200m_cor_process_device(self.h, C.c_void_p(ptr), stride, nfram, _stream_ptr(stream)))
+
+    def read(self, stream=None):
+        out = np.empty(self.n_inst, np.float32)
+        _ck(lib().b200m_cor_results(self.h, _np_ptr(out), _stream_ptr(stream)))
+        return out
+
+    def state(self, stream=None):
+        s = np.empty((self.n_inst, 5), np.float32)
+        _ck(lib().b200m_cor_state(self.h, _np_ptr(s), _stream_ptr(stream)))
+        return s
+
+    def coeffs(self):
+        w = np.empty(2, np.float32)
+        _ck(lib().b200m_cor_coeffs(self.h, _np_ptr(w)))
+        return w
+
+
+class Spectr30(_Bank):
+    """N x the spectr30 plugin (src/spectrumlv2.c:73-257): ports 0..59 per instance."""
+    _destroy = "b200m_spec_destroy"
+
+    def __init__(self, n_inst, nchan=2, rate=48000.0, device=0):
+        super().__init__()
+        self.n_inst, self.nchan = n_inst, nchan
+        _ck(lib().b200m_spec_create(C.byref(self.h), device, n_inst, nchan, rate))
+
+    def process(self, x, speed=1.0, reset=-4.0, stream=None):
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == self.n_inst * self.nchan
+            _ck(lib().b200m_spec_process_host(self.h, p, s, n, speed, reset))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == self.n_inst * self.nchan
+            _ck(lib().b200m_spec_process_device(self.h, p, s, n, speed, reset, _stream_ptr(stream)))
+
+    def process_ptr(self, ptr, stride, nfram, speed=1.0, reset=-4.0, stream=None):
+        _ck(lib().b200m_spec_process_device(self.h, C.c_void_p(ptr), stride, nfram, speed, reset, _stream_ptr(stream)))
+
+    def read(self, stream=None):
+        out = np.empty((self.n_inst, 60), np.float32)
+        _ck(lib().b200m_spec_results(self.h, _np_ptr(out), _stream_ptr(stream)))
+        return out
+
+    def state(self, inst, stream=None):
+        z = np.empty((30, 6, 2), np.float64); v = np.empty(30, np.float32); m = np.empty(30, np.float32)
+        _ck(lib().b200m_spec_state(self.h, inst, _np_ptr(z), _np_ptr(v), _np_ptr(m), _stream_ptr(stream)))
+        return z, v, m
+
+    def coeffs(self):
+        W = np.empty((30, 6, 6), np.float64)
+        _ck(lib().b200m_spec_coeffs(self.h, _np_ptr(W)))
+        return W
+
+
+class Phasewheel(_Bank):
+    """N x (2 x FFTAnalysis + phasewheel process_audio) (gui/fft.c:208-361, gui/phasewheel.c:1307-1342)."""
+    _destroy = "b200m_pw_destroy"
+
+    def __init__(self, n_inst, fft_bins=1024, rate=48000.0, device=0):
+        super().__init__()
+        self.n_inst, self.bins = n_inst, fft_bins
+        _ck(lib().b200m_pw_create(C.byref(self.h), device, n_inst, fft_bins, rate))
+
+    def process(self, x, db_thresh=1e-6, stream=None):
+        fired = C.c_int(0)
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == 2 * self.n_inst
+            _ck(lib().b200m_pw_process_host(self.h, p, s, n, db_thresh, C.byref(fired)))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == 2 * self.n_inst
+            _ck(lib().b200m_pw_process_device(self.h, p, s, n, db_thresh, C.byref(fired), _stream_ptr(stream)))
+        return fired.value
+
+    def process_ptr(self, ptr, stride, nfram, db_thresh=1e-6, stream=None):
+        fired = C.c_int(0)
+        _ck(lib().b200m_pw_process_device(self.h, C.c_void_p(ptr), stride, nfram, db_thresh, C.byref(fired), _stream_ptr(stream)))
+        return fired.value
+
+    def read(self, stream=None):
+        ph = np.empty((self.n_inst, self.bins), np.float32); lv = np.empty((self.n_inst, self.bins), np.float32)
+        pk = np.empty(self.n_inst, np.float32)
+        _ck(lib().b200m_pw_results(self.h, _np_ptr(ph), _np_ptr(lv), _np_ptr(pk), _stream_ptr(stream)))
+        return ph, lv, pk
+
+    def raw(self, inst, stream=None):
+        a = [np.empty(self.bins, np.float32) for _ in range(4)]
+        _ck(lib().b200m_pw_raw(self.h, inst, *[_np_ptr(v) for v in a], _stream_ptr(stream)))
+        return a

@@ -1,0 +1,285 @@
+// pw.cu — phasewheel FFT analysis bank (cuFFT-free radix-4 Stockham kernel).
+//
+// Replaces, for N stereo instances, the GUI-side analysis of the phasewheel: fftx_init / fftx_run /
+// ft_analyze (gui/fft.c:208-361, Hann window :69-79,122-161) for the left and right channel plus
+// process_audio (gui/phasewheel.c:1307-1342).  The reference calls FFTW3 (fftwf_plan_r2r_1d R2HC,
+// gui/fft.c:234) which is neither vendored nor pinned; this kernel computes the same DFT
+// (X_k = sum x_n e^{-2 pi i nk/N}) in fp32 with its own algorithm, so parity for this bank is
+// tolerance-based against a double-precision DFT.
+//
+// B200 design: the ring buffers of all instances advance in lock step, so the host tracks the write
+// offset and the 25 Hz analysis clock; one CTA per instance packs z = L + iR, runs ONE complex
+// N-point autosort (Stockham) FFT in shared memory (radix-4 passes, one radix-2 pass when log2 N is
+// odd), splits it into the two real spectra, and writes phase difference / level bins with coalesced
+// stores.
+#include <math.h>
+#include <stdlib.h>
+#include "common.cuh"
+
+namespace b200m {
+
+constexpr int PW_THREADS = 256;
+
+__global__ void pw_append_kernel (const float* __restrict__ in, size_t stride, int rows, int nfram, int N, int rboff,
+                                  float* __restrict__ ring)
+{
+    // r_buf[(i + n_off) % n_siz] = data[i]  (gui/fft.c:302-305)
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * nfram) return;
+    const int row = (int)(idx / nfram), j = (int)(idx % nfram);
+    ring[(size_t)row * N + ((rboff + j) & (N - 1))] = in[(size_t)row * stride + j];
+}
+
+B200M_DEV float2 cmul (float2 a, float2 b) { return make_float2 (fmaf (a.x, b.x, -a.y * b.y), fmaf (a.x, b.y, a.y * b.x)); }
+
+// ring: [inst][2][N]; oldest sample sits at offset `start`.  tw[k] = exp(-2 pi i k / N).
+__global__ void __launch_bounds__ (PW_THREADS)
+pw_analyze_kernel (const float* __restrict__ ring, int N, int log2n, int start, const float* __restrict__ window,
+                   const float2* __restrict__ tw, float db_thresh, float* __restrict__ rawp /* [inst][4][bins] */,
+                   float* __restrict__ phase, float* __restrict__ level, float* __restrict__ peak)
+{
+    extern __shared__ __align__ (16) float2 sm[];          // two ping-pong buffers of N complex values
+    __shared__ float red[PW_THREADS / 32];
+    float2* X = sm; float2* Y = sm + N;
+    const int inst = blockIdx.x, tid = threadIdx.x, bins = N / 2;
+    const float* rl = ring + (size_t)inst * 2 * N;
+    const float* rr = rl + N;
+    // last N samples in time order, times the window (gui/fft.c:318-333)
+    for (int t = tid; t < N; t += PW_THREADS) {
+        const int src = (start + t) & (N - 1);
+        const float wv = window[t];
+        X[t] = make_float2 (__fmul_rn (rl[src], wv), __fmul_rn (rr[src], wv));
+    }
+    __syncthreads ();
+    // autosort FFT: n = current sub-transform length, s = stride = N / n
+    int n = N, s = 1;
+    int passes4 = log2n / 2;
+    for (int ps = 0; ps < passes4; ++ps) {
+        const int n1 = n >> 2;
+        for (int t = tid; t < (N >> 2); t += PW_THREADS) {
+            const int p = t / s, q = t - p * s;
+            const float2 a = X[q + s * p], b = X[q + s * (p + n1)], c = X[q + s * (p + 2 * n1)], d = X[q + s * (p + 3 * n1)];
+            const float2 apc = make_float2 (a.x + c.x, a.y + c.y), amc = make_float2 (a.x - c.x, a.y - c.y);
+            const float2 bpd = make_float2 (b.x + d.x, b.y + d.y);
+            const float2 jbmd = make_float2 (-(b.y - d.y), b.x - d.x);             // i * (b - d)
+            const float2 w1 = tw[p * s], w2 = tw[2 * p * s], w3 = tw[3 * p * s];
+            Y[q + s * (4 * p)] = make_float2 (apc.x + bpd.x, apc.y + bpd.y);
+            Y[q + s * (4 * p + 1)] = cmul (w1, make_float2 (amc.x - jbmd.x, amc.y - jbmd.y));
+            Y[q + s * (4 * p + 2)] = cmul (w2, make_float2 (apc.x - bpd.x, apc.y - bpd.y));
+            Y[q + s * (4 * p + 3)] = cmul (w3, make_float2 (amc.x + jbmd.x, amc.y + jbmd.y));
+        }
+        __syncthreads ();
+        float2* T = X; X = Y; Y = T;
+        n >>= 2; s <<= 2;
+    }
+    if (log2n & 1) {                                        // final radix-2 pass: n == 2, s == N/2, twiddle 1
+        for (int t = tid; t < (N >> 1); t += PW_THREADS) {
+            const float2 a = X[t], b = X[t + s];
+            Y[t] = make_float2 (a.x + b.x, a.y + b.y);
+            Y[t + s] = make_float2 (a.x - b.x, a.y - b.y);
+        }
+        __syncthreads ();
+        float2* T = X; X = Y; Y = T;
+    }
+    // split Z = FFT(L + iR) into the two half spectra, then ft_analyze (gui/fft.c:163-180) and
+    // process_audio (gui/phasewheel.c:1313-1331)
+    float* pwl = rawp + (size_t)inst * 4 * bins; float* pwr = pwl + bins; float* phl = pwr + bins; float* phr = phl + bins;
+    float pk = 0.0f;
+    for (int k = tid; k < bins; k += PW_THREADS) {
+        float pl, pr, fl, fr;
+        if (k == 0) {
+            pl = X[0].x * X[0].x; pr = X[0].y * X[0].y; fl = 0.0f; fr = 0.0f;   // power[0] = out[0]^2, phase[0] = 0
+        } else if (k == bins - 1) {
+            pl = pwl[k]; pr = pwr[k]; fl = phl[k]; fr = phr[k];                  // never written by ft_analyze (i < data_size - 1)
+        } else {
+            const float2 zk = X[k], zn = X[N - k];
+            const float lre = 0.5f * (zk.x + zn.x), lim = 0.5f * (zk.y - zn.y);
+            const float rre = 0.5f * (zk.y + zn.y), rim = -0.5f * (zk.x - zn.x);
+            pl = fmaf (lre, lre, lim * lim); pr = fmaf (rre, rre, rim * rim);
+            fl = atan2f (lim, lre); fr = atan2f (rim, rre);
+        }
+        pwl[k] = pl; pwr[k] = pr; phl[k] = fl; phr[k] = fr;
+        if (k >= 1 && k < bins - 1) {
+            float ph, lv;
+            if (pl < db_thresh || pr < db_thresh) { ph = 0.0f; lv = -100.0f; }
+            else { ph = __fsub_rn (fr, fl); lv = pl > pr ? pl : pr; if (lv > pk) pk = lv; }   // MAX(a,b) = a > b ? a : b
+            phase[(size_t)inst * bins + k] = ph;
+            level[(size_t)inst * bins + k] = lv;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) pk = fmaxf (pk, __shfl_xor_sync (0xffffffffu, pk, o));
+    if ((tid & 31) == 0) red[tid >> 5] = pk;
+    __syncthreads ();
+    if (tid == 0) {
+        for (int i = 1; i < PW_THREADS / 32; ++i) pk = fmaxf (pk, red[i]);
+        // ui->peak += .04 * (peak - ui->peak) + 1e-15;  (double arithmetic on a float lvalue, :1333-1335)
+        float up = peak[inst];
+        up = __double2float_rn ((double)up + (.04 * (double)__fsub_rn (pk, up) + 1e-15));
+        if (isnan (up)) up = 0;
+        if (up > 1000) up = 1000;
+        peak[inst] = up;
+    }
+}
+
+__global__ void pw_init_kernel (size_t n, float* level) { const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) level[i] = -100.0f; }
+
+}  // namespace b200m
+
+using namespace b200m;
+
+struct b200m_pw {
+    int device; uint32_t n_inst, bins, N; int log2n; double rate;
+    uint32_t rboff, smps, sps, step;                       // shared ring offset + 25 Hz analysis clock (gui/fft.c:43-64)
+    float *d_ring = nullptr, *d_win = nullptr, *d_raw = nullptr, *d_phase = nullptr, *d_level = nullptr, *d_peak = nullptr;
+    float2* d_tw = nullptr;
+    cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
+};
+
+static cudaStream_t pw_stream (b200m_pw* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
+
+static int pw_process (b200m_pw* h, const float* d_in, size_t stride, uint32_t nfram, float db_thresh, int* fired, cudaStream_t st)
+{
+    int any = 0;
+    uint32_t done = 0;
+    while (done < nfram) {                                  // fftx_run: steps of at most window_size (gui/fft.c:346-360)
+        const uint32_t n = (nfram - done) < h->N ? (nfram - done) : h->N;
+        const size_t total = (size_t)h->n_inst * 2 * n;
+        pw_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>> (d_in + done, stride, (int)(h->n_inst * 2), (int)n, (int)h->N, (int)h->rboff, h->d_ring);
+        B200M_LAUNCHED (1);
+        h->rboff = (h->rboff + n) % h->N;
+        h->smps += n;
+        if (h->smps >= h->sps) {                            // :308-313
+            h->step = h->smps; h->smps = 0;
+            pw_analyze_kernel<<<h->n_inst, PW_THREADS, (size_t)2 * h->N * sizeof (float2), st>>> (
+                h->d_ring, (int)h->N, h->log2n, (int)h->rboff, h->d_win, h->d_tw, db_thresh, h->d_raw, h->d_phase, h->d_level, h->d_peak);
+            B200M_LAUNCHED (1);
+            any = 1;
+        }
+        done += n;
+    }
+    if (fired) *fired = any;
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+extern "C" {
+
+int b200m_pw_create (b200m_pw** out, int device, uint32_t n_inst, uint32_t fft_bins, double rate)
+{
+    if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");
+    *out = nullptr;
+    if (n_inst == 0 || !(rate >= 1000.0)) return set_err (B200M_E_INVAL, "bad n_inst/rate");
+    if (fft_bins < 64 || fft_bins > 8192 || (fft_bins & (fft_bins - 1))) return set_err (B200M_E_INVAL, "fft_bins must be a power of two in 64..8192");
+    if (fft_bins > 4096) return set_err (B200M_E_UNSUPPORTED, "fft_bins %u: transforms above 8192 points are not provided", fft_bins);
+    if (b200m_device_count () <= 0) return set_err (B200M_E_NODEVICE, "no CUDA device: b200meters has no CPU path");
+    DeviceGuard g (device);
+    if (!g.ok) return set_err (B200M_E_NODEVICE, "cannot select CUDA device %d", device);
+    b200m_pw* h = new (std::nothrow) b200m_pw;
+    if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
+    h->device = device; h->n_inst = n_inst; h->bins = fft_bins; h->N = 2 * fft_bins; h->rate = rate;
+    h->log2n = 0; while ((1u << h->log2n) < h->N) ++h->log2n;
+    h->rboff = h->smps = h->step = 0;
+    h->sps = (uint32_t)ceil (rate / 25);                    // fftx_init (..., rate, 25): gui/fft.c:219, phasewheel.c:193
+    const uint32_t N = h->N;
+    float* win = (float*)malloc (N * sizeof (float));
+    float2* tw = (float2*)malloc (N * sizeof (float2));
+    if (!win || !tw) { free (win); free (tw); delete h; return set_err (B200M_E_NOMEM, "host allocation failed"); }
+    {   // Hann window, normalised to sum 2 (ft_hannhamm + ft_gen_window, gui/fft.c:69-79,122-161)
+        double sum = 0.0; const double c = 2.0 * M_PI / (N - 1.0);
+        for (uint32_t i = 0; i < N; ++i) { win[i] = .5 - .5 * cos (c * i); sum += win[i]; }
+        const double isum = 2.0 / sum;
+        for (uint32_t i = 0; i < N; ++i) win[i] *= isum;
+    }
+    for (uint32_t k = 0; k < N; ++k) { const double a = -2.0 * M_PI * (double)k / (double)N; tw[k] = make_float2 ((float)cos (a), (float)sin (a)); }
+    cudaError_t e = cudaSuccess;
+    auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
+    A ((void**)&h->d_ring, (size_t)n_inst * 2 * N * sizeof (float));
+    A ((void**)&h->d_win, N * sizeof (float));
+    A ((void**)&h->d_tw, N * sizeof (float2));
+    A ((void**)&h->d_raw, (size_t)n_inst * 4 * fft_bins * sizeof (float));
+    A ((void**)&h->d_phase, (size_t)n_inst * fft_bins * sizeof (float));
+    A ((void**)&h->d_level, (size_t)n_inst * fft_bins * sizeof (float));
+    A ((void**)&h->d_peak, n_inst * sizeof (float));
+    if (e == cudaSuccess) e = cudaMemcpy (h->d_win, win, N * sizeof (float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy (h->d_tw, tw, N * sizeof (float2), cudaMemcpyHostToDevice);
+    free (win); free (tw);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (pw_analyze_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 8192 * sizeof (float2)));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        const size_t n = (size_t)n_inst * fft_bins;       // ui->level[i] = -100, ui->phase[i] = 0 (phasewheel.c:199-202)
+        pw_init_kernel<<<(unsigned)((n + 255) / 256), 256>>> (n, h->d_level);
+        B200M_LAUNCHED (1);
+        e = cudaDeviceSynchronize ();
+    }
+    if (e != cudaSuccess) { int rc = cuda_fail (e, "pw_create", __FILE__, __LINE__); b200m_pw_destroy (h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int b200m_pw_destroy (b200m_pw* h)
+{
+    if (!h) return 0;
+    DeviceGuard g (h->device);
+    cudaDeviceSynchronize ();
+    cudaFree (h->d_ring); cudaFree (h->d_win); cudaFree (h->d_tw); cudaFree (h->d_raw); cudaFree (h->d_phase); cudaFree (h->d_level); cudaFree (h->d_peak);
+    h->stage.release ();
+    if (h->own) cudaStreamDestroy (h->own);
+    delete h;
+    return 0;
+}
+
+int b200m_pw_process_device (b200m_pw* h, const float* d_in, size_t stride, uint32_t nfram, float db_thresh, int* fired, void* stream)
+{
+    if (int rc = check_block_args (h, d_in, stride, nfram)) return rc;
+    DeviceGuard g (h->device);
+    h->last_host = false;
+    return pw_process (h, d_in, stride, nfram, db_thresh, fired, (cudaStream_t)stream);
+}
+
+int b200m_pw_process_host (b200m_pw* h, const float* in, size_t stride, uint32_t nfram, float db_thresh, int* fired)
+{
+    if (int rc = check_block_args (h, in, stride, nfram)) return rc;
+    DeviceGuard g (h->device);
+    if (h->stage.ensure ((size_t)2 * h->n_inst, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
+    B200M_CUDA (cudaMemcpy2DAsync (h->stage.d, h->stage.cap * sizeof (float), in, stride * sizeof (float),
+                                   (size_t)nfram * sizeof (float), (size_t)2 * h->n_inst, cudaMemcpyHostToDevice, h->own));
+    h->last_host = true;
+    return pw_process (h, h->stage.d, h->stage.cap, nfram, db_thresh, fired, h->own);
+}
+
+int b200m_pw_results (b200m_pw* h, float* phase, float* level, float* peak, void* stream)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    DeviceGuard g (h->device);
+    cudaStream_t st = pw_stream (h, stream);
+    const size_t nb = (size_t)h->n_inst * h->bins * sizeof (float);
+    if (phase) B200M_CUDA (cudaMemcpyAsync (phase, h->d_phase, nb, cudaMemcpyDeviceToHost, st));
+    if (level) B200M_CUDA (cudaMemcpyAsync (level, h->d_level, nb, cudaMemcpyDeviceToHost, st));
+    if (peak)  B200M_CUDA (cudaMemcpyAsync (peak, h->d_peak, h->n_inst * sizeof (float), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_pw_raw (b200m_pw* h, uint32_t inst, float* powL, float* powR, float* phL, float* phR, void* stream)
+{
+    if (!h || inst >= h->n_inst) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    cudaStream_t st = pw_stream (h, stream);
+    float* dst[4] = {powL, powR, phL, phR};
+    for (int q = 0; q < 4; ++q)
+        if (dst[q]) B200M_CUDA (cudaMemcpyAsync (dst[q], h->d_raw + ((size_t)inst * 4 + q) * h->bins, h->bins * sizeof (float), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_pw_device_results (b200m_pw* h, const float** d_phase, const float** d_level, const float** d_peak)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    if (d_phase) *d_phase = h->d_phase;
+    if (d_level) *d_level = h->d_level;
+    if (d_peak) *d_peak = h->d_peak;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,506 @@
+// tpk.cu — true-peak (4x polyphase oversampler + PPM ballistics) and K-meter RMS bank.
+//
+// Replaces, for N mono channels at once, LV2M::TruePeakdsp (jmeters/truepeakdsp.cc:41-169) with its
+// zita-resampler core (zita-resampler/resampler.cc:171-262, table resampler-table.cc:52-75) and
+// LV2M::Kmeterdsp (jmeters/kmeterdsp.cc:47-162), as combined by dr14_run (src/dr14.c:391-394).
+//
+// B200 design (not the reference's ring-buffer walk): the resampler's steady state is a fixed
+// 48-tap x 4-phase FIR over the last 48 inputs, which is time-parallel, so a CTA
+// stages a [8 channels x 128 samples (+48 history)] tile in shared memory with cp.async and every
+// thread produces 4 consecutive input positions x 4 phases = 16 outputs from a 52-float register
+// window, coefficients read as constant-bank operands.  The non-linear ballistics
+// (truepeakdsp.cc:57-84) and the K-meter recurrences are serial in time, so one lane per channel
+// walks the |oversampled| tile in shared memory while the other CTAs resident on the SM run
+// their FIR phase.  The input is read from HBM exactly once for both meters.
+// All arithmetic keeps the reference's operation order without FMA contraction: outputs are
+// bit-identical to the reference build, not merely within tolerance.
+#include <math.h>
+#include "common.cuh"
+
+namespace b200m {
+
+constexpr int TPK_CH = 8;                   // channels per CTA
+constexpr int TPK_TC = 128;                 // input samples per chunk
+constexpr int TPK_XP = 48 + TPK_TC + 4;     // x row pitch (floats) = 180
+constexpr int TPK_OP = 4 * TPK_TC + 4;      // |out| row pitch (floats) = 516
+constexpr int TPK_THREADS = 128;
+
+__constant__ float c_tp_tab[120];           // zita table for hl=24, np=4, fr=1.0: [(np+1)][hl]
+
+struct TpkParams {
+    float w1, w2, w3, g;                    // TruePeakdsp::init (truepeakdsp.cc:153-157)
+    float omega, fall; int hold;            // Kmeterdsp::init (kmeterdsp.cc:47-54), _fall for this n (:65-70)
+};
+
+struct TpkState {                           // SoA, one entry per channel
+    float *hist;                            // [n_chan][48]: the 48 inputs preceding the next block
+    float *tp_z1, *tp_z2, *tp_m, *tp_p; int *tp_res;
+    float *km_z1, *km_z2, *km_rms, *km_peak, *km_fall; int *km_cnt, *km_fpp, *km_flag;
+};
+
+// 16 outputs (4 input positions x 4 phases) from a 52-sample window; w[j] = x[kb-48+j].
+// out[4k+ph] = (1e-20f + sum_i (x[k-47+i]*c1[i] + x[k-i]*c2[i])) - 1e-20f, pair-sum first, i ascending
+// (resampler.cc:213-230 with c1 = ctab + hl*ph, c2 = ctab + hl*(np-ph)).
+B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
+{
+    float acc[16];
+#pragma unroll
+    for (int a = 0; a < 16; ++a) acc[a] = 1e-20f;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) {
+#pragma unroll
+        for (int ph = 0; ph < 4; ++ph) {
+            const float c1 = c_tp_tab[24 * ph + i], c2 = c_tp_tab[24 * (4 - ph) + i];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                acc[4 * r + ph] = __fadd_rn (acc[4 * r + ph], __fadd_rn (__fmul_rn (w[r + i + 1], c1), __fmul_rn (w[r + 48 - i], c2)));
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 16; ++a) o[a] = __fsub_rn (acc[a], 1e-20f);
+}
+
+template <bool TP, bool TPMAX, bool KM>
+__global__ void __launch_bounds__ (TPK_THREADS)
+tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
+            float* __restrict__ dbg)
+{
+    __shared__ __align__ (16) float xs[2][TPK_CH][TPK_XP];
+    __shared__ __align__ (16) float ob[(TP && !TPMAX) ? TPK_CH : 1][(TP && !TPMAX) ? TPK_OP : 4];
+    __shared__ float smax[TPK_CH];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * TPK_CH;
+    const int nchunks = (nfram + TPK_TC - 1) / TPK_TC;
+
+    auto load_chunk = [&] (int c, int buf) {
+        if (c < nchunks) {
+            const int s0 = c * TPK_TC;
+            if (aligned) {
+                // 8 rows x 32 16-byte pieces = 256 copies over 128 threads
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int idx = tid + h * TPK_THREADS;
+                    const int r = idx >> 5, c4 = (idx & 31) * 4;
+                    const int ch = min (c0 + r, n_chan - 1);
+                    const int left = (nfram - (s0 + c4)) * 4;
+                    const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+                    cp_async16 (&xs[buf][r][48 + c4], nb ? in + (size_t)ch * stride + s0 + c4 : in, nb);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < TPK_CH; ++h) {
+                    const int ch = min (c0 + h, n_chan - 1);
+                    const bool ok = (s0 + tid) < nfram;
+                    cp_async4 (&xs[buf][h][48 + tid], ok ? in + (size_t)ch * stride + s0 + tid : in, ok ? 4 : 0);
+                }
+            }
+        }
+        cp_async_commit ();
+    };
+
+    // history -> xs[0][.][0..47]
+    for (int idx = tid; idx < TPK_CH * 48; idx += TPK_THREADS) {
+        const int r = idx / 48, j = idx % 48;
+        xs[0][r][j] = TP ? st.hist[(size_t)min (c0 + r, n_chan - 1) * 48 + j] : 0.0f;
+    }
+    load_chunk (0, 0);
+
+    // per-channel serial state: warp 0 lanes 0..7 = true-peak ballistics, warp 1 lanes 0..7 = K-meter
+    const bool is_tp = TP && warp == 0 && lane < TPK_CH;
+    const bool is_km = KM && warp == 1 && lane < TPK_CH;
+    const int chs = min (c0 + lane, n_chan - 1);
+    const bool live = (c0 + lane) < n_chan;
+    float z1 = 0, z2 = 0, m = 0, p = 0; int res = 0;
+    float kz1 = 0, kz2 = 0, kt = 0;
+    if (is_tp) {
+        res = st.tp_res[chs];
+        m = res ? 0.0f : st.tp_m[chs];                                  // truepeakdsp.cc:52-55
+        p = res ? 0.0f : st.tp_p[chs];
+        const float a = st.tp_z1[chs], b = st.tp_z2[chs];
+        z1 = a > 20 ? 20 : (a < 0 ? 0 : a);
+        z2 = b > 20 ? 20 : (b < 0 ? 0 : b);
+    }
+    if (is_km) {
+        const float a = st.km_z1[chs], b = st.km_z2[chs];               // kmeterdsp.cc:74-75
+        kz1 = a > 50 ? 50 : (a < 0 ? 0 : a);
+        kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
+    }
+    if (tid < TPK_CH) smax[tid] = 0.0f;                                   // process_max: plain max (:109-122)
+    const int km_n = (nfram / 4) * 4;                                     // "n /= 4" drops n mod 4 samples (:79)
+
+    for (int c = 0; c < nchunks; ++c) {
+        const int buf = c & 1;
+        const int s0 = c * TPK_TC;
+        const int len = min (TPK_TC, nfram - s0);
+        cp_async_wait<0> ();
+        __syncthreads ();                                   // chunk c (and its 48-sample prefix) is in xs[buf]
+        // prefix of the next chunk = last 48 samples of this one; start the next load
+        for (int idx = tid; idx < TPK_CH * 48; idx += TPK_THREADS) {
+            const int r = idx / 48, j = idx % 48;
+            xs[buf ^ 1][r][j] = xs[buf][r][len + j];
+        }
+        load_chunk (c + 1, buf ^ 1);
+
+        if (TP) {
+            // FIR phase: warp w handles channels w and w+4; lane q handles inputs 4q..4q+3 of the chunk
+#pragma unroll 1
+            for (int pass = 0; pass < TPK_CH / (TPK_THREADS / 32); ++pass) {
+                const int r = warp + pass * (TPK_THREADS / 32);
+                float vmax = 0.0f;
+                if (4 * lane < len) {
+                    float w[52];
+                    const float4* xr = reinterpret_cast<const float4*> (&xs[buf][r][4 * lane]);
+#pragma unroll
+                    for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+                    float o[16];
+                    fir16 (w, o);
+                    if (dbg && (c0 + r) < n_chan) {
+                        float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * lane));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d[i] = make_float4 (o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                    }
+                    if (TPMAX) {
+                        // positions beyond len inside the last group come from zero-filled input: exclude them
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            if (4 * lane + i < len) {
+#pragma unroll
+                                for (int ph = 0; ph < 4; ++ph) { const float v = fabsf (o[4 * i + ph]); if (v > vmax) vmax = v; }
+                            }
+                    } else {
+                        float4* d = reinterpret_cast<float4*> (&ob[(TP && !TPMAX) ? r : 0][(TP && !TPMAX) ? 16 * lane : 0]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            d[i] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
+                    }
+                }
+                if (TPMAX) {                                // channel r belongs to this warp alone: no race on smax[r]
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));
+                    if (lane == 0 && vmax > smax[r]) smax[r] = vmax;
+                }
+            }
+        }
+        if (TP && !TPMAX) __syncthreads ();                 // |out| tile complete
+
+        if (is_tp && !TPMAX) {
+            // PPM ballistics over the 4*len oversampled magnitudes (truepeakdsp.cc:57-84)
+            const float4* b4 = reinterpret_cast<const float4*> (&ob[(TP && !TPMAX) ? lane : 0][0]);
+            for (int j = 0; j < len; ++j) {
+                const float4 v4 = b4[j];
+                z1 = __fmul_rn (z1, prm.w3);
+                z2 = __fmul_rn (z2, prm.w3);
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = vv[i];
+                    if (v > z1) z1 = __fadd_rn (z1, __fmul_rn (prm.w1, __fsub_rn (v, z1)));
+                    if (v > z2) z2 = __fadd_rn (z2, __fmul_rn (prm.w2, __fsub_rn (v, z2)));
+                    if (v > p) p = v;
+                }
+                const float t = __fadd_rn (z1, z2);
+                if (t > m) m = t;
+            }
+        }
+        if (is_km) {
+            // kmeterdsp.cc:80-97: z1 every sample, z2 every 4th; the block's last n%4 samples are ignored
+            const int e = min (len, km_n - s0);
+            const float4* x4 = reinterpret_cast<const float4*> (&xs[buf][lane][48]);
+            const float om4 = __fmul_rn (4.0f, prm.omega);
+            for (int j = 0; j + 4 <= e; j += 4) {
+                const float4 v4 = x4[j >> 2];
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float s = __fmul_rn (vv[i], vv[i]);
+                    if (kt < s) kt = s;
+                    kz1 = __fadd_rn (kz1, __fmul_rn (prm.omega, __fsub_rn (s, kz1)));
+                }
+                kz2 = __fadd_rn (kz2, __fmul_rn (om4, __fsub_rn (kz1, kz2)));
+            }
+        }
+        __syncthreads ();                                   // ob / xs[buf] free for reuse
+    }
+    cp_async_wait<0> ();
+
+    // ---- end of block --------------------------------------------------------------------
+    if (TP) {
+        // new history = the 48 samples that precede the next block (left in xs[nchunks&1][.][0..47])
+        const int hb = nchunks & 1;
+        for (int idx = tid; idx < TPK_CH * 48; idx += TPK_THREADS) {
+            const int r = idx / 48, j = idx % 48;
+            if (c0 + r < n_chan) st.hist[(size_t)(c0 + r) * 48 + j] = xs[hb][r][j];
+        }
+    }
+    if (TP && TPMAX && tid < TPK_CH && (c0 + tid) < n_chan) {
+        // process_max (:108-123): m = _res ? 0 : _m; running max; _m = m.  _res, _p, _z1, _z2 untouched.
+        const int ch = c0 + tid;
+        float mm = st.tp_res[ch] ? 0.0f : st.tp_m[ch];
+        if (smax[tid] > mm) mm = smax[tid];
+        st.tp_m[ch] = mm;
+    }
+    if (is_tp && !TPMAX && live) {
+        st.tp_z1[chs] = __fadd_rn (z1, 1e-20f);             // :86-87
+        st.tp_z2[chs] = __fadd_rn (z2, 1e-20f);
+        m = __fmul_rn (m, prm.g);                           // :89
+        if (res) { st.tp_m[chs] = m; st.tp_p[chs] = p; st.tp_res[chs] = 0; }
+        else {
+            if (m > st.tp_m[chs]) st.tp_m[chs] = m;
+            if (p > st.tp_p[chs]) st.tp_p[chs] = p;
+        }
+    }
+    if (is_km && live) {
+        if (isnan (kz1)) kz1 = 0;                           // :101-103
+        if (isnan (kz2)) kz2 = 0;
+        if (!finitef_ (kt)) kt = 0;
+        st.km_z1[chs] = __fadd_rn (kz1, 1e-20f);
+        st.km_z2[chs] = __fadd_rn (kz2, 1e-20f);
+        const float s = __fsqrt_rn (__fmul_rn (2.0f, kz2));
+        const float t = __fsqrt_rn (kt);
+        if (st.km_flag[chs]) { st.km_rms[chs] = s; st.km_flag[chs] = 0; }
+        else if (s > st.km_rms[chs]) st.km_rms[chs] = s;
+        float pk = st.km_peak[chs]; int cnt = st.km_cnt[chs];
+        if (t >= pk) { pk = t; cnt = prm.hold; }            // :125-139
+        else if (cnt > 0) cnt -= nfram;
+        else { pk = __fmul_rn (pk, prm.fall); pk = __fadd_rn (pk, 1e-10f); }
+        st.km_peak[chs] = pk; st.km_cnt[chs] = cnt;
+        st.km_fall[chs] = prm.fall; st.km_fpp[chs] = nfram;
+    }
+}
+
+__global__ void tpk_read_kernel (int n_chan, uint32_t flags, TpkState st, b200m_tpk_result* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chan) return;
+    b200m_tpk_result r = out[i];
+    if (flags & B200M_TPK_TRUEPEAK) { r.tp_m = st.tp_m[i]; r.tp_p = st.tp_p[i]; st.tp_res[i] = 1; }     // read(m,p) :133-138
+    if (flags & B200M_TPK_KMETER)   { r.km_rms = st.km_rms[i]; r.km_peak = st.km_peak[i]; st.km_flag[i] = 1; }  // kmeterdsp.cc:150-155
+    out[i] = r;
+}
+
+__global__ void tpk_reset_kernel (int n_chan, int sel, uint32_t flags, TpkState st)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chan || (sel >= 0 && i != sel)) return;
+    if (flags & B200M_TPK_TRUEPEAK) { st.tp_res[i] = 1; st.tp_m[i] = 0; st.tp_p[i] = 0; }                 // :140-145
+    if (flags & B200M_TPK_KMETER) { st.km_z1[i] = st.km_z2[i] = st.km_rms[i] = st.km_peak[i] = 0; st.km_cnt[i] = 0; st.km_flag[i] = 0; }
+}
+
+}  // namespace b200m
+
+using namespace b200m;
+
+// ---------------------------------------------------------------------------- host side
+struct b200m_tpk {
+    int device; uint32_t n_chan, flags; float fsamp;
+    TpkParams prm; float ctab[120];
+    TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
+    cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
+};
+
+// zita-resampler table for (fr = 1.0, hl = 24, np = 4); restates Resampler_table's constructor
+// (zita-resampler/resampler-table.cc:29-44,52-75) in double precision with the host libm.
+static void zita_table (float* tab, unsigned hl, unsigned np, double fr)
+{
+    for (unsigned j = 0; j <= np; ++j) {
+        double t = (double)j / (double)np;
+        for (unsigned i = 0; i < hl; ++i) {
+            double xs = fabs (t * fr), sc = 1.0;
+            if (!(xs < 1e-6)) { xs *= M_PI; sc = sin (xs) / xs; }
+            double xw = fabs (t / hl), wn = 0.0;
+            if (!(xw >= 1.0)) { xw *= M_PI; wn = 0.384 + 0.500 * cos (xw) + 0.116 * cos (2 * xw); }
+            tab[j * hl + (hl - i - 1)] = (float)(fr * sc * wn);
+            t += 1;
+        }
+    }
+}
+
+static cudaStream_t tpk_stream (b200m_tpk* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
+
+static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st)
+{
+    const bool tp = h->flags & B200M_TPK_TRUEPEAK, km = h->flags & B200M_TPK_KMETER;
+    TpkParams prm = h->prm;
+    // Kmeterdsp::process (:65-70): per-period fallback multiplier, a pure function of n
+    prm.fall = powf (10.0f, -0.05f * 15.0f * ((float)(int)nfram / h->fsamp));
+    const int aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
+    dim3 grid ((h->n_chan + TPK_CH - 1) / TPK_CH), blk (TPK_THREADS);
+#define TPK_GO(TP, MX, KM) tpk_kernel<TP, MX, KM><<<grid, blk, 0, st>>> (d_in, stride, (int)h->n_chan, (int)nfram, aligned, prm, h->st, h->d_dbg)
+    if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (true, true, true); else TPK_GO (true, true, false); }
+    else if (tp) { if (km) TPK_GO (true, false, true); else TPK_GO (true, false, false); }
+    else TPK_GO (false, false, true);
+#undef TPK_GO
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+extern "C" {
+
+int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp, uint32_t flags)
+{
+    if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");
+    *out = nullptr;
+    if (n_chan == 0 || !(fsamp >= 1000.0f) || !(flags & 3u) || (flags & ~3u)) return set_err (B200M_E_INVAL, "bad n_chan/fsamp/flags");
+    if (b200m_device_count () <= 0) return set_err (B200M_E_NODEVICE, "no CUDA device: b200meters has no CPU path");
+    DeviceGuard g (device);
+    if (!g.ok) return set_err (B200M_E_NODEVICE, "cannot select CUDA device %d", device);
+    b200m_tpk* h = new (std::nothrow) b200m_tpk;
+    if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
+    h->device = device; h->n_chan = n_chan; h->flags = flags; h->fsamp = fsamp;
+    // TruePeakdsp::init (truepeakdsp.cc:148-157): float / float / double-literal, rounded to float
+    h->prm.w1 = 4000.0f / fsamp / 4.0;
+    h->prm.w2 = 17200.0f / fsamp / 4.0;
+    h->prm.w3 = 1.0f - 7.0f / fsamp / 4.0;
+    h->prm.g = 0.502f;
+    // Kmeterdsp::init (kmeterdsp.cc:47-54)
+    h->prm.hold = (int)(0.5f * fsamp + 0.5f);
+    h->prm.omega = 9.72f / fsamp;
+    h->prm.fall = 0.0f;
+    zita_table (h->ctab, 24, 4, 1.0);               // setup (fsamp, fsamp * 4.0, 1, 24, 1.0): np = 4, ratio-only
+    cudaError_t e = cudaMemcpyToSymbol (c_tp_tab, h->ctab, sizeof (h->ctab));
+    auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
+    const size_t n = n_chan;
+    A ((void**)&h->st.hist, n * 48 * sizeof (float));
+    A ((void**)&h->st.tp_z1, n * 4); A ((void**)&h->st.tp_z2, n * 4); A ((void**)&h->st.tp_m, n * 4); A ((void**)&h->st.tp_p, n * 4);
+    A ((void**)&h->st.tp_res, n * 4);
+    A ((void**)&h->st.km_z1, n * 4); A ((void**)&h->st.km_z2, n * 4); A ((void**)&h->st.km_rms, n * 4); A ((void**)&h->st.km_peak, n * 4);
+    A ((void**)&h->st.km_fall, n * 4); A ((void**)&h->st.km_cnt, n * 4); A ((void**)&h->st.km_fpp, n * 4); A ((void**)&h->st.km_flag, n * 4);
+    A ((void**)&h->d_res, n * sizeof (b200m_tpk_result));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        // constructors: TruePeakdsp _res(true) (:29); Kmeterdsp _flag(false), all zero (kmeterdsp.cc:30-40);
+        // the 8192-zero pre-roll (:159-168) leaves an all-zero history, which the memset above provides
+        tpk_reset_kernel<<<(n_chan + 127) / 128, 128>>> ((int)n_chan, -1, B200M_TPK_TRUEPEAK, h->st);
+        B200M_LAUNCHED (1);
+        e = cudaDeviceSynchronize ();
+    }
+    if (e != cudaSuccess) { int rc = cuda_fail (e, "tpk_create", __FILE__, __LINE__); b200m_tpk_destroy (h); return rc; }
+    *out = h;
+    return 0;
+}
+
+int b200m_tpk_destroy (b200m_tpk* h)
+{
+    if (!h) return 0;
+    DeviceGuard g (h->device);
+    cudaDeviceSynchronize ();
+    void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms,
+                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg};
+    for (void* p : ps) cudaFree (p);
+    h->stage.release ();
+    if (h->own) cudaStreamDestroy (h->own);
+    delete h;
+    return 0;
+}
+
+int b200m_tpk_process_device (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, void* stream)
+{
+    if (int rc = check_block_args (h, d_in, stride, nfram)) return rc;
+    if (tp_mode > 1) return set_err (B200M_E_INVAL, "bad tp_mode %u", tp_mode);
+    DeviceGuard g (h->device);
+    h->last_host = false;
+    return tpk_process (h, d_in, stride, nfram, tp_mode, (cudaStream_t)stream);
+}
+
+int b200m_tpk_process_host (b200m_tpk* h, const float* in, size_t stride, uint32_t nfram, uint32_t tp_mode)
+{
+    if (int rc = check_block_args (h, in, stride, nfram)) return rc;
+    if (tp_mode > 1) return set_err (B200M_E_INVAL, "bad tp_mode %u", tp_mode);
+    DeviceGuard g (h->device);
+    if (h->stage.ensure (h->n_chan, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
+    B200M_CUDA (cudaMemcpy2DAsync (h->stage.d, h->stage.cap * sizeof (float), in, stride * sizeof (float),
+                                   (size_t)nfram * sizeof (float), h->n_chan, cudaMemcpyHostToDevice, h->own));
+    h->last_host = true;
+    return tpk_process (h, h->stage.d, h->stage.cap, nfram, tp_mode, h->own);
+}
+
+int b200m_tpk_read_device (b200m_tpk* h, void* stream)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    DeviceGuard g (h->device);
+    tpk_read_kernel<<<(h->n_chan + 255) / 256, 256, 0, tpk_stream (h, stream)>>> ((int)h->n_chan, h->flags, h->st, h->d_res);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+int b200m_tpk_results (b200m_tpk* h, b200m_tpk_result* out, void* stream)
+{
+    if (!h || !out) return set_err (B200M_E_INVAL, "NULL argument");
+    DeviceGuard g (h->device);
+    cudaStream_t st = tpk_stream (h, stream);
+    B200M_CUDA (cudaMemcpyAsync (out, h->d_res, h->n_chan * sizeof (b200m_tpk_result), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_tpk_reset (b200m_tpk* h, int32_t chan, void* stream)
+{
+    if (!h || chan >= (int32_t)h->n_chan) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    tpk_reset_kernel<<<(h->n_chan + 127) / 128, 128, 0, tpk_stream (h, stream)>>> ((int)h->n_chan, chan, h->flags, h->st);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+int b200m_tpk_coeffs (const b200m_tpk* h, float w[4], float ctab[120], float km[2])
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    if (w) { w[0] = h->prm.w1; w[1] = h->prm.w2; w[2] = h->prm.w3; w[3] = h->prm.g; }
+    if (ctab) memcpy (ctab, h->ctab, sizeof (h->ctab));
+    if (km) { km[0] = h->prm.omega; km[1] = (float)h->prm.hold; }
+    return 0;
+}
+
+int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float* tp_z2, int32_t* tp_res, float* km8, void* stream)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    DeviceGuard g (h->device);
+    cudaStream_t st = tpk_stream (h, stream);
+    const size_t n = h->n_chan, b = n * 4;
+    if (tp_m)  B200M_CUDA (cudaMemcpyAsync (tp_m, h->st.tp_m, b, cudaMemcpyDeviceToHost, st));
+    if (tp_p)  B200M_CUDA (cudaMemcpyAsync (tp_p, h->st.tp_p, b, cudaMemcpyDeviceToHost, st));
+    if (tp_z1) B200M_CUDA (cudaMemcpyAsync (tp_z1, h->st.tp_z1, b, cudaMemcpyDeviceToHost, st));
+    if (tp_z2) B200M_CUDA (cudaMemcpyAsync (tp_z2, h->st.tp_z2, b, cudaMemcpyDeviceToHost, st));
+    if (tp_res) B200M_CUDA (cudaMemcpyAsync (tp_res, h->st.tp_res, b, cudaMemcpyDeviceToHost, st));
+    if (km8) {
+        float* tmp = (float*)malloc (8 * b);
+        if (!tmp) return set_err (B200M_E_NOMEM, "host allocation failed");
+        const void* src[8] = {h->st.km_z1, h->st.km_z2, h->st.km_rms, h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag};
+        cudaError_t e = cudaSuccess;
+        for (int q = 0; q < 8 && e == cudaSuccess; ++q) e = cudaMemcpyAsync (tmp + q * n, src[q], b, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize (st);
+        if (e != cudaSuccess) { free (tmp); return cuda_fail (e, "tpk_state", __FILE__, __LINE__); }
+        for (size_t i = 0; i < n; ++i)
+            for (int q = 0; q < 8; ++q)
+                km8[8 * i + q] = (q >= 5) ? (float)((const int*)(tmp + q * n))[i] : tmp[q * n + i];
+        free (tmp);
+    }
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_tpk_debug_capture (b200m_tpk* h, int enable)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    DeviceGuard g (h->device);
+    B200M_CUDA (cudaDeviceSynchronize ());
+    if (enable && !h->d_dbg) B200M_CUDA (cudaMalloc ((void**)&h->d_dbg, (size_t)h->n_chan * 4 * B200M_MAX_BLOCK * sizeof (float)));
+    if (!enable && h->d_dbg) { cudaFree (h->d_dbg); h->d_dbg = nullptr; }
+    return 0;
+}
+
+int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t n_out, void* stream)
+{
+    if (!h || !out || chan >= h->n_chan || n_out > 4 * B200M_MAX_BLOCK) return set_err (B200M_E_INVAL, "bad argument");
+    if (!h->d_dbg) return set_err (B200M_E_INVAL, "debug capture not enabled");
+    DeviceGuard g (h->device);
+    cudaStream_t st = tpk_stream (h, stream);
+    B200M_CUDA (cudaMemcpyAsync (out, h->d_dbg + (size_t)chan * 4 * B200M_MAX_BLOCK, (size_t)n_out * 4, cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,135 @@
+"""GPU parity: b200m_tpk_* (true peak 4x + K-meter) vs the CPU oracle; bit-exact on every output."""
+import numpy as np
+import pytest
+
+import _oracle as O
+import _signals as S
+
+pytestmark = pytest.mark.gpu
+
+
+def u32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def test_coeffs_bitwise():
+    import meters_lv2_b200 as B
+    for fs in (48000.0, 44100.0, 96000.0):
+        g = B.TruePeakKmeter(1, fs)
+        w, t, k = g.coeffs()
+        ow, ot = O.TruePeak(1, fs).coeffs()
+        om, oh = O.Kmeter(1, fs).coeffs()
+        assert np.array_equal(u32(w), u32(ow)) and np.array_equal(u32(t), u32(ot))
+        assert u32(k[:1])[0] == u32(np.float32(om))[()] and int(k[1]) == oh
+
+
+@pytest.mark.parametrize("n,block", [(4096, 1024), (3000, 1000), (777, 777), (8192, 8192), (130, 65)])
+def test_fir_stream_bit_exact(n, block):
+    """the raw 4x oversampled stream equals zita-resampler's output bit for bit."""
+    import torch
+    import meters_lv2_b200 as B
+    x = S.white(11, n, seed=5)
+    x[3] *= 1e-12; x[4] = 0; x[5, ::7] = 1e-40          # tiny / zero / denormal rows exercise the 1e-20f bias
+    g = B.TruePeakKmeter(11); g.debug_capture(True)
+    xd = torch.from_numpy(x).cuda()
+    for ch in (0, 3, 4, 5, 10):
+        pass
+    outs = {ch: [] for ch in (0, 3, 4, 5, 10)}
+    for o in range(0, n, block):
+        k = min(block, n - o)
+        g.process(xd[:, o:o + k])
+        for ch in outs:
+            outs[ch].append(g.debug_upsampled(ch, 4 * k))
+    for ch in outs:
+        ref = O.tp_upsample(x[ch], block=block)
+        got = np.concatenate(outs[ch])
+        assert np.array_equal(u32(got), u32(ref)), (ch, int((u32(got) != u32(ref)).sum()))
+
+
+def _drive(x, blocks, read_every=1, mode=0, flags=3, host=False):
+    import torch
+    import meters_lv2_b200 as B
+    C = x.shape[0]
+    g = B.TruePeakKmeter(C, flags=flags)
+    ot = O.TruePeak(C); ok = O.Kmeter(C)
+    xd = None if host else torch.from_numpy(x).cuda()
+    pos = 0
+    reads = []
+    for bi, n in enumerate(blocks):
+        blk = np.ascontiguousarray(x[:, pos:pos + n])
+        if flags & 1:
+            ot.process(blk, mode=mode, nthreads=8)
+        if flags & 2:
+            ok.process(blk, nthreads=8)
+        g.process(blk if host else xd[:, pos:pos + n], tp_mode=mode)
+        pos += n
+        if read_every and (bi + 1) % read_every == 0:
+            r = g.read()
+            if flags & 1:
+                m, p = ot.read()
+                assert np.array_equal(u32(r["tp_m"]), u32(m)), ("tp_m", bi)
+                assert np.array_equal(u32(r["tp_p"]), u32(p)), ("tp_p", bi)
+            if flags & 2:
+                rms, pk = ok.read()
+                assert np.array_equal(u32(r["km_rms"]), u32(rms)), ("km_rms", bi)
+                assert np.array_equal(u32(r["km_peak"]), u32(pk)), ("km_peak", bi)
+    s = g.state()
+    if flags & 1:
+        m, p, z1, z2, res = ot.peek()
+        for k, v in (("m", m), ("p", p), ("z1", z1), ("z2", z2)):
+            assert np.array_equal(u32(s[k]), u32(v)), k
+        assert np.array_equal(s["res"], res)
+    if flags & 2:
+        km = ok.peek()
+        assert np.array_equal(u32(s["km"]), u32(km)), "kmeter state"
+    return g
+
+
+@pytest.mark.parametrize("C,blocks,read_every", [
+    (70, [1024] * 50, 1),                 # TPnRMS cadence: read after every run()
+    (19, [1024] * 30, 0),                 # never read: max-merge branch, m *= g quirk
+    (9, [64] * 20 + [480] * 10 + [8192] * 2 + [1, 2, 3, 5, 1023, 4097], 3),   # ragged blocks, n % 4 != 0
+])
+def test_process_bit_exact(C, blocks, read_every):
+    x = S.white(C, sum(blocks), seed=11)
+    _drive(x, blocks, read_every)
+
+
+def test_process_max_mode():
+    x = S.white(21, 1024 * 12, seed=3)
+    _drive(x, [1024] * 12, read_every=1, mode=1, flags=1)
+    _drive(x, [1024] * 12, read_every=0, mode=1, flags=1)
+
+
+def test_single_meter_banks_and_host_path():
+    x = S.white(10, 1000 * 8 + 1, seed=9)[:, 1:]           # unaligned rows
+    _drive(x, [1000] * 8, flags=1, host=True)
+    _drive(x, [1000] * 8, flags=2, host=True)
+
+
+def test_nan_inf_denormal():
+    x = S.nasty(16, 1024 * 6)
+    _drive(x, [1024] * 6, read_every=2)
+
+
+def test_true_peak_of_fs4_sine():
+    # fs/4 sine at 45 deg: sample peaks 0.7071, true peak 1.0 (+3 dB) -- SURVEY App. C: p -> 1.0000032
+    n = 1024 * 47
+    x = np.ascontiguousarray(S.sine(n, 12000.0, phase=np.pi / 4)[None, :])
+    g = _drive(x, [1024] * 47, read_every=0, flags=1)
+    s = g.state()
+    assert abs(s["p"][0] - 1.0) < 0.02 and s["p"][0] > 0.99
+
+
+def test_reset():
+    import torch
+    import meters_lv2_b200 as B
+    x = S.white(6, 2048, seed=2)
+    g = B.TruePeakKmeter(6); ot = O.TruePeak(6); ok = O.Kmeter(6)
+    xd = torch.from_numpy(x).cuda()
+    g.process(xd[:, :1024]); ot.process(np.ascontiguousarray(x[:, :1024])); ok.process(np.ascontiguousarray(x[:, :1024]))
+    g.reset(2); ot.reset(2); ok.reset(2)
+    g.process(xd[:, 1024:]); ot.process(np.ascontiguousarray(x[:, 1024:])); ok.process(np.ascontiguousarray(x[:, 1024:]))
+    s = g.state(); m, p, z1, z2, res = ot.peek()
+    assert np.array_equal(u32(s["m"]), u32(m)) and np.array_equal(u32(s["p"]), u32(p))
+    assert np.array_equal(u32(s["km"]), u32(ok.peek()))
