@@ -56,6 +56,19 @@ int         b200m_host_free (void* p);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t    b200m_launch_count (void);
 
+/* Host-side coefficient design, callable without a GPU (pure functions of the sample rate, computed with
+ * the host libm in the reference's expression types so that every value is bitwise the reference's):
+ *   ebu : detect_init (ebumeter/ebu_r128_proc.cc:263-293)           -> a0 a1 a2 b1 b2 c3 c4
+ *   tpk : TruePeakdsp::init (jmeters/truepeakdsp.cc:148-157), zita table (zita-resampler/resampler-table.cc:
+ *         52-75; hl=24 np=4 fr=1), Kmeterdsp::init (jmeters/kmeterdsp.cc:47-54) -> w1 w2 w3 g | ctab | omega hold
+ *   cor : Stcorrdsp::init (jmeters/stcorrdsp.cc:85-93)              -> w1 w2
+ *   spec: spectrum_instantiate band table + bandpass_setup (src/spectrumlv2.c:100-118, src/spectr.c:89-206)
+ *         -> W[30][6][6] = a0 a1 a2 b0 b1 b2 per section */
+int b200m_design_ebu (float fsamp, float out7[7]);
+int b200m_design_tpk (float fsamp, float w[4], float ctab[120], float km[2]);
+int b200m_design_cor (int fsamp, float flp, float tcf, float w[2]);
+int b200m_design_spec (double rate, double* W1080);
+
 /* ======================================================================================
  * EBU R128 loudness bank — replaces LV2M::Ebu_r128_proc (ebumeter/ebu_r128_proc.h:66-125)
  * as driven by ebur128_run (src/ebulv2.cc:341-358).

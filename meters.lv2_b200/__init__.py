@@ -42,6 +42,10 @@ _PROTOS = {
     "b200m_host_alloc": (C.c_int, [C.POINTER(_v), C.c_size_t]),
     "b200m_host_free": (C.c_int, [_v]),
     "b200m_launch_count": (C.c_uint64, []),
+    "b200m_design_ebu": (C.c_int, [C.c_float, _v]),
+    "b200m_design_tpk": (C.c_int, [C.c_float, _v, _v, _v]),
+    "b200m_design_cor": (C.c_int, [C.c_int, C.c_float, C.c_float, _v]),
+    "b200m_design_spec": (C.c_int, [C.c_double, _v]),
     # EBU
     "b200m_ebu_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_float]),
     "b200m_ebu_destroy": (C.c_int, [_v]),
@@ -159,6 +163,30 @@ def _host_planar(x):
         return _np_ptr(x), x.strides[0] // 4, x.shape[0], x.shape[1]
     assert (not x.is_cuda) and x.dim() == 2 and x.stride(1) == 1
     return C.c_void_p(x.data_ptr()), x.stride(0), x.shape[0], x.shape[1]
+
+
+def design_ebu(fsamp):
+    o = np.empty(7, np.float32)
+    _ck(lib().b200m_design_ebu(fsamp, _np_ptr(o)))
+    return o
+
+
+def design_tpk(fsamp):
+    w = np.empty(4, np.float32); t = np.empty(120, np.float32); k = np.empty(2, np.float32)
+    _ck(lib().b200m_design_tpk(fsamp, _np_ptr(w), _np_ptr(t), _np_ptr(k)))
+    return w, t, k
+
+
+def design_cor(fsamp, flp=2e3, tcf=0.3):
+    w = np.empty(2, np.float32)
+    _ck(lib().b200m_design_cor(int(fsamp), flp, tcf, _np_ptr(w)))
+    return w
+
+
+def design_spec(rate):
+    W = np.empty((30, 6, 6), np.float64)
+    _ck(lib().b200m_design_spec(rate, _np_ptr(W)))
+    return W
 
 
 def launch_count():

@@ -115,6 +115,14 @@ static int cor_process (b200m_cor* h, const float* d_in, size_t stride, uint32_t
 
 extern "C" {
 
+int b200m_design_cor (int fsamp, float flp, float tcf, float w[2])
+{
+    if (!w || fsamp < 1000) return set_err (B200M_E_INVAL, "bad argument");
+    w[0] = 6.28f * flp / fsamp;                    // Stcorrdsp::init (stcorrdsp.cc:85-93), int fsamp
+    w[1] = 1 / (tcf * fsamp);
+    return 0;
+}
+
 int b200m_cor_create (b200m_cor** out, int device, uint32_t n_inst, int fsamp, float flp, float tcf)
 {
     if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");
@@ -126,8 +134,7 @@ int b200m_cor_create (b200m_cor** out, int device, uint32_t n_inst, int fsamp, f
     b200m_cor* h = new (std::nothrow) b200m_cor;
     if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
     h->device = device; h->n_inst = n_inst;
-    h->w1 = 6.28f * flp / fsamp;                   // Stcorrdsp::init (stcorrdsp.cc:85-93), int fsamp
-    h->w2 = 1 / (tcf * fsamp);
+    { float w[2]; b200m_design_cor (fsamp, flp, tcf, w); h->w1 = w[0]; h->w2 = w[1]; }
     cudaError_t e = cudaMalloc ((void**)&h->d_st, (size_t)5 * n_inst * sizeof (float));
     if (e == cudaSuccess) e = cudaMemset (h->d_st, 0, (size_t)5 * n_inst * sizeof (float));
     if (e == cudaSuccess) e = cudaMalloc ((void**)&h->d_res, n_inst * sizeof (float));

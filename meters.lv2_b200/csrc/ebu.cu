@@ -431,6 +431,14 @@ static int ebu_ctl (b200m_ebu* h, int32_t inst, int cmd, void* stream)
 
 extern "C" {
 
+int b200m_design_ebu (float fsamp, float o[7])
+{
+    if (!o || !(fsamp >= 1000.0f)) return set_err (B200M_E_INVAL, "bad argument");
+    EbuCoef k; ebu_design (fsamp, k);
+    o[0] = k.a0; o[1] = k.a1; o[2] = k.a2; o[3] = k.b1; o[4] = k.b2; o[5] = k.c3; o[6] = k.c4;
+    return 0;
+}
+
 int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nchan, float fsamp)
 {
     if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");

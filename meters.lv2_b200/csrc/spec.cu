@@ -151,6 +151,10 @@ typedef std::complex<double> cplx;
 // band-pass via the (c_a, c_b) bilinear substitution -> per-section a1 = -2 Re(P), a2 = |P|^2, numerator
 // (1, +-2, 1) -> unity gain at the geometric centre folded into section 0.  Same operation order and the
 // same std::complex<double> operators as the reference, hence bitwise-equal coefficients on the same libm.
+// noinline/noclone keeps `order` a run-time value: a clone specialised for order = 6 would let GCC fold the
+// pole angles' cos/sin at compile time (MPFR, correctly rounded), which differs from glibc's run-time cos/sin
+// in the last ulp for some angles — the reference build evaluates them at run time.
+__attribute__ ((noinline, noclone))
 static void design_band (double W[6][6], double rate, double freq, double band, int order)
 {
     const double wc = 2. * M_PI * freq / rate, ww = 2. * M_PI * band / rate;
@@ -194,6 +198,19 @@ static void design_band (double W[6][6], double rate, double freq, double band, 
     W[0][3] *= std::real (scale); W[0][4] *= std::real (scale); W[0][5] *= std::real (scale);
 }
 
+static void design_bank (double W[30][6][6], double rate)
+{
+    // band table (src/spectrumlv2.c:100-118): f_m = 1000 * 2^((i-16)/3), band edges at 2^(+-1/6), order 6
+    const double f_r = 1000, b = 3;
+    const double lo = pow (2, -1. / (2. * b)), hi = pow (2, 1. / (2. * b));
+    for (int i = 0; i < SPEC_BANDS; ++i) {
+        const int x = i - 16;
+        const double f_m = pow (2, x / b) * f_r;
+        const double f_1 = f_m * lo, f_2 = f_m * hi;
+        design_band (W[i], rate, f_m, f_2 - f_1, 6);
+    }
+}
+
 static float spec_omega (float speed, double rate)
 {
     // 1.0 - e^(-2 pi v / rate), float result of a double argument (src/spectrumlv2.c:98,176)
@@ -231,6 +248,13 @@ static int spec_process (b200m_spec* h, const float* d_in, size_t stride, uint32
 
 extern "C" {
 
+int b200m_design_spec (double rate, double* W1080)
+{
+    if (!W1080 || !(rate >= 1000.0)) return set_err (B200M_E_INVAL, "bad argument");
+    design_bank (reinterpret_cast<double (*)[6][6]> (W1080), rate);
+    return 0;
+}
+
 int b200m_spec_create (b200m_spec** out, int device, uint32_t n_inst, uint32_t nchan, double rate)
 {
     if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");
@@ -244,16 +268,10 @@ int b200m_spec_create (b200m_spec** out, int device, uint32_t n_inst, uint32_t n
     h->device = device; h->n_inst = n_inst; h->nchan = nchan; h->rate = rate;
     h->rst_h = -4; h->spd_h = 1.0; h->frames = 0;       // :95-98
     h->omega = spec_omega (h->spd_h, rate);
-    // band table (:100-118): f_m = 1000 * 2^((i-16)/3), band edges at 2^(+-1/6)
-    const double f_r = 1000, b = 3;
-    const double lo = pow (2, -1. / (2. * b)), hi = pow (2, 1. / (2. * b));
     double coef[SPEC_BANDS][16];
     memset (coef, 0, sizeof (coef));
+    design_bank (h->W, rate);
     for (int i = 0; i < SPEC_BANDS; ++i) {
-        const int x = i - 16;
-        const double f_m = pow (2, x / b) * f_r;
-        const double bw = f_m * hi - f_m * lo;
-        design_band (h->W[i], rate, f_m, bw, 6);
         coef[i][0] = h->W[i][0][3]; coef[i][1] = h->W[i][0][4]; coef[i][2] = h->W[i][0][5];
         for (int s = 0; s < 6; ++s) { coef[i][3 + 2 * s] = h->W[i][s][1]; coef[i][4 + 2 * s] = h->W[i][s][2]; }
     }

@@ -315,6 +315,20 @@ static void zita_table (float* tab, unsigned hl, unsigned np, double fr)
     }
 }
 
+static void tpk_design (float fsamp, TpkParams& prm, float* ctab)
+{
+    // TruePeakdsp::init (truepeakdsp.cc:148-157): float / float / double-literal, rounded to float
+    prm.w1 = 4000.0f / fsamp / 4.0;
+    prm.w2 = 17200.0f / fsamp / 4.0;
+    prm.w3 = 1.0f - 7.0f / fsamp / 4.0;
+    prm.g = 0.502f;
+    // Kmeterdsp::init (kmeterdsp.cc:47-54)
+    prm.hold = (int)(0.5f * fsamp + 0.5f);
+    prm.omega = 9.72f / fsamp;
+    prm.fall = 0.0f;
+    zita_table (ctab, 24, 4, 1.0);                  // setup (fsamp, fsamp * 4.0, 1, 24, 1.0): np = 4, ratio-only
+}
+
 static cudaStream_t tpk_stream (b200m_tpk* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
 
 static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st)
@@ -337,6 +351,16 @@ static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
 
 extern "C" {
 
+int b200m_design_tpk (float fsamp, float w[4], float ctab[120], float km[2])
+{
+    if (!(fsamp >= 1000.0f)) return set_err (B200M_E_INVAL, "bad argument");
+    TpkParams p; float t[120]; tpk_design (fsamp, p, t);
+    if (w) { w[0] = p.w1; w[1] = p.w2; w[2] = p.w3; w[3] = p.g; }
+    if (ctab) memcpy (ctab, t, sizeof (t));
+    if (km) { km[0] = p.omega; km[1] = (float)p.hold; }
+    return 0;
+}
+
 int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp, uint32_t flags)
 {
     if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");
@@ -348,16 +372,7 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     b200m_tpk* h = new (std::nothrow) b200m_tpk;
     if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
     h->device = device; h->n_chan = n_chan; h->flags = flags; h->fsamp = fsamp;
-    // TruePeakdsp::init (truepeakdsp.cc:148-157): float / float / double-literal, rounded to float
-    h->prm.w1 = 4000.0f / fsamp / 4.0;
-    h->prm.w2 = 17200.0f / fsamp / 4.0;
-    h->prm.w3 = 1.0f - 7.0f / fsamp / 4.0;
-    h->prm.g = 0.502f;
-    // Kmeterdsp::init (kmeterdsp.cc:47-54)
-    h->prm.hold = (int)(0.5f * fsamp + 0.5f);
-    h->prm.omega = 9.72f / fsamp;
-    h->prm.fall = 0.0f;
-    zita_table (h->ctab, 24, 4, 1.0);               // setup (fsamp, fsamp * 4.0, 1, 24, 1.0): np = 4, ratio-only
+    tpk_design (fsamp, h->prm, h->ctab);
     cudaError_t e = cudaMemcpyToSymbol (c_tp_tab, h->ctab, sizeof (h->ctab));
     auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
     const size_t n = n_chan;

@@ -1,0 +1,70 @@
+"""Generates tests/golden/golden_v1.npz from the REFERENCE build (oracle/_ref, i.e. the unmodified
+x42/meters.lv2 sources compiled by oracle/Makefile) on small seeded streams.
+
+    python tests/golden/make_golden.py            # rewrite the fixture (needs /root/reference -> oracle/_ref)
+
+The reference ships no golden vectors or tests, so these fixtures — outputs of the
+reference itself, run here — are the pin for the oracle port on machines where /root/reference is absent.
+`compute(kind)` is also what tests/test_oracle_port.py::test_golden_vectors replays.
+The phasewheel entries come from the port (FFTW3 is absent: that path has no reference build).
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+import _oracle as O          # noqa: E402
+import _signals as S         # noqa: E402
+
+BLOCKS = [1024] * 130 + [480, 64, 8192, 1, 3, 1023]
+
+
+def compute(kind):
+    out = {}
+    x = S.white(8, sum(BLOCKS), seed=0xC0FFEE)
+    x[6, 5000:5010] = [np.nan, np.inf, -np.inf, 1e-42, 0, 1, -1, 1e-30, 3e38, -3e38]
+    e = O.Ebu(4, 2, kind=kind); e.integr("start")
+    tp = O.TruePeak(8, kind=kind); km = O.Kmeter(8, kind=kind); co = O.Stcorr(4, kind=kind)
+    sp = O.Spectr30(2, 2, kind=kind)
+    tpm, kmr, cor = [], [], []
+    pos = 0
+    for i, n in enumerate(BLOCKS):
+        blk = np.ascontiguousarray(x[:, pos:pos + n]); pos += n
+        e.process(blk); tp.process(blk); km.process(blk); co.process(blk)
+        if i < 24:
+            sp.process(np.ascontiguousarray(blk[:4]))
+        m, p = tp.read(); r, pk = km.read()
+        tpm.append(np.stack([m, p])); kmr.append(np.stack([r, pk])); cor.append(co.read())
+    out["ebu_results"] = e.read()
+    for i in range(4):
+        hm, hs, c = e.hist(i)
+        out["ebu_histM_%d" % i], out["ebu_histS_%d" % i], out["ebu_counts_%d" % i] = hm, hs, c
+    out["ebu_coeffs"] = e.coeffs()
+    out["tp_reads"] = np.stack(tpm); out["km_reads"] = np.stack(kmr); out["cor_reads"] = np.stack(cor)
+    w, t = tp.coeffs(); out["tp_w"], out["tp_ctab"] = w, t
+    out["tp_upsampled"] = O.tp_upsample(x[0, :2048], kind=kind)
+    ports = sp.read()
+    out["spec_ports"] = ports[:, :30].copy(); out["spec_maxports"] = ports[:, 30:].copy()
+    out["spec_coeffs"] = sp.coeffs()
+    # 997 Hz / -23 dBFS tone (EBU Tech 3341 case 1)
+    s = S.sine(1024 * 300, 997.0, amp=10 ** (-23 / 20)); y = np.ascontiguousarray(np.stack([s, s]))
+    e2 = O.Ebu(1, 2, kind=kind); e2.integr("start")
+    for b in range(300):
+        e2.process(np.ascontiguousarray(y[:, b * 1024:(b + 1) * 1024]))
+    out["ebu_tone_results"] = e2.read()
+    # phasewheel (port only)
+    pw = O.Phasewheel(2, 1024, kind="port")
+    for b in range(4):
+        pw.process(np.ascontiguousarray(x[:4, b * 1024:(b + 1) * 1024]))
+    ph, lv, pk = pw.read()
+    out["pw_phase"], out["pw_level"], out["pw_peak"] = ph, lv, pk
+    return out
+
+
+if __name__ == "__main__":
+    assert O.available("reference"), "build oracle/_ref first (make -C oracle ref)"
+    d = compute("reference")
+    np.savez_compressed(os.path.join(HERE, "golden_v1.npz"), **d)
+    print("wrote golden_v1.npz:", {k: v.shape for k, v in d.items()})

@@ -105,10 +105,10 @@ def test_nan_inf_denormal_scrub():
 
 def test_ebu_tech3341_tone():
     # 997 Hz, -23 dBFS, L = R  =>  -23.0 LUFS (EBU Tech 3341 case 1); oracle gives M = -23.007
-    n = 1024 * 200
+    n = 1024 * 300                                       # 6.4 s: > 50 momentary points, so I is live
     s = S.sine(n, 997.0, amp=10 ** (-23 / 20))
     x = np.ascontiguousarray(np.stack([s, s]))
-    g, o, gr, orr = _run_both(x, [1024] * 200)
+    g, o, gr, orr = _run_both(x, [1024] * 300)
     _assert_equal(g, o, gr, orr, 1)
     assert abs(gr["loudness_M"][0] + 23.0) < 0.02 and abs(gr["integrated"][0] + 23.0) < 0.05
 

@@ -1,0 +1,155 @@
+"""CPU: pins the oracle.  (1) the port (oracle/oracle_port.cc, this repo's restatement) must equal the
+reference build (oracle/_ref, the unmodified reference sources) bit for bit on seeded streams;
+(2) both must reproduce the committed golden vectors (tests/golden/*.npz, generated from oracle/_ref by
+tests/golden/make_golden.py) and the survey's known-answer values."""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import _signals as S
+
+HAVE_REF = O.available("reference")
+HAVE_PORT = O.available("port")
+needs_both = pytest.mark.skipif(not (HAVE_REF and HAVE_PORT), reason="needs oracle/_ref and oracle/liboracle_port.so")
+needs_port = pytest.mark.skipif(not HAVE_PORT, reason="run `make -C oracle port`")
+BLOCKS = [1024] * 30 + [64] * 8 + [480] * 4 + [8192, 1, 3, 1023, 2401, 4799]
+
+
+def u32(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _blocks(x, blocks):
+    pos = 0
+    for n in blocks:
+        yield np.ascontiguousarray(x[:, pos:pos + n])
+        pos += n
+
+
+@needs_both
+@pytest.mark.parametrize("nchan", [1, 2])
+def test_ebu_port_equals_reference(nchan):
+    x = S.white(6 * nchan, sum(BLOCKS) + 1024 * 280, seed=101)
+    a, b = O.Ebu(6, nchan, kind="reference"), O.Ebu(6, nchan, kind="port")
+    assert np.array_equal(u32(a.coeffs()), u32(b.coeffs()))
+    a.integr("start"); b.integr("start")
+    for blk in _blocks(x, BLOCKS + [1024] * 280):
+        a.process(blk); b.process(blk)
+    assert np.array_equal(u32(a.read()), u32(b.read()))
+    for i in range(6):
+        ha, hb = a.hist(i), b.hist(i)
+        assert all(np.array_equal(p, q) for p, q in zip(ha, hb))
+        sa, sb = a.state(i), b.state(i)
+        assert np.array_equal(u32(sa[0]), u32(sb[0])) and np.array_equal(u32(sa[1]), u32(sb[1])) and list(sa[3]) == list(sb[3])
+
+
+@needs_both
+def test_truepeak_kmeter_port_equals_reference():
+    x = S.nasty(7, sum(BLOCKS), seed=102)
+    wa, ta = O.TruePeak(1, kind="reference").coeffs(); wb, tb = O.TruePeak(1, kind="port").coeffs()
+    assert np.array_equal(u32(wa), u32(wb)) and np.array_equal(u32(ta), u32(tb))
+    for mode in (0, 1):
+        a, b = O.TruePeak(7, kind="reference"), O.TruePeak(7, kind="port")
+        ka, kb = O.Kmeter(7, kind="reference"), O.Kmeter(7, kind="port")
+        for i, blk in enumerate(_blocks(x, BLOCKS)):
+            a.process(blk, mode); b.process(blk, mode); ka.process(blk); kb.process(blk)
+            if i % 3 == 0:
+                ra, rb = a.read(), b.read()
+                assert np.array_equal(u32(ra[0]), u32(rb[0])) and np.array_equal(u32(ra[1]), u32(rb[1]))
+                qa, qb = ka.read(), kb.read()
+                assert np.array_equal(u32(qa[0]), u32(qb[0])) and np.array_equal(u32(qa[1]), u32(qb[1]))
+        assert all(np.array_equal(u32(p), u32(q)) for p, q in zip(a.peek()[:4], b.peek()[:4]))
+        assert np.array_equal(u32(ka.peek()), u32(kb.peek()))
+    y = S.white(1, 5000, seed=3)[0]
+    assert np.array_equal(u32(O.tp_upsample(y, kind="reference")), u32(O.tp_upsample(y, kind="port")))
+
+
+@needs_both
+def test_stcorr_port_equals_reference():
+    x = S.nasty(10, sum(BLOCKS), seed=103)
+    a, b = O.Stcorr(5, kind="reference"), O.Stcorr(5, kind="port")
+    assert np.array_equal(u32(a.coeffs()), u32(b.coeffs()))
+    for blk in _blocks(x, BLOCKS):
+        a.process(blk); b.process(blk)
+        assert np.array_equal(u32(a.read()), u32(b.read()))
+    assert np.array_equal(u32(a.peek()), u32(b.peek()))
+
+
+@needs_both
+@pytest.mark.parametrize("nchan,rate", [(2, 48000.0), (1, 44100.0)])
+def test_spectr_port_equals_reference(nchan, rate):
+    x = S.white(2 * nchan, 1024 * 6 + 777, seed=104)
+    a, b = O.Spectr30(2, nchan, rate, kind="reference"), O.Spectr30(2, nchan, rate, kind="port")
+    assert np.array_equal(a.coeffs().view(np.uint64), b.coeffs().view(np.uint64))
+    for i, blk in enumerate(_blocks(x, [1024] * 6 + [777])):
+        spd = 1.0 if i < 3 else 4.0
+        a.process(blk, spd, -4.0); b.process(blk, spd, -4.0)
+        pa, pb = a.read(), b.read()
+        assert np.array_equal(u32(pa[:, :30]), u32(pb[:, :30]))
+        ok = pa[:, 30:] > -500
+        assert np.array_equal(u32(pa[:, 30:][ok]), u32(pb[:, 30:][ok]))
+    za, zb = a.state(1), b.state(1)
+    assert np.array_equal(za[0].view(np.uint64), zb[0].view(np.uint64)) and np.array_equal(u32(za[1]), u32(zb[1]))
+
+
+@needs_port
+def test_port_phasewheel_against_numpy_fft():
+    """the FFT restatement (FFTW absent => parity unpinned) is at least a correct DFT of the windowed ring."""
+    x = S.white(2, 4096, seed=105)
+    p = O.Phasewheel(1, 1024, kind="port")
+    fired = [p.process(np.ascontiguousarray(x[:, i * 1024:(i + 1) * 1024])) for i in range(4)]
+    assert fired == [0, 1, 0, 1]                          # sps = 1920: every second 1024-block
+    N = 2048
+    i = np.arange(N)
+    w = (0.5 - 0.5 * np.cos(2 * np.pi * i / (N - 1))).astype(np.float32)
+    w = (w * (2.0 / w.astype(np.float64).sum())).astype(np.float32)
+    X = np.fft.rfft((x[0, 2048:4096] * w).astype(np.float64))
+    powL, powR, phL, phR = p.raw(0)
+    ref = (X.real.astype(np.float32) ** 2 + X.imag.astype(np.float32) ** 2)[1:1023]
+    assert np.allclose(powL[1:1023], ref, rtol=1e-5, atol=1e-12)
+
+
+@needs_port
+def test_known_answers_survey_appendix_c():
+    """values the survey generated from the reference build (LCG noise, 4688 x 1024)."""
+    nb = 4688
+    x = S.lcg_stereo(1024 * nb)
+    for kind in (["port", "reference"] if HAVE_REF else ["port"]):
+        k = O.Kmeter(1, kind=kind); c = O.Stcorr(1, kind=kind); t = O.TruePeak(1, kind=kind)
+        e = O.Ebu(1, kind=kind); e.integr("start")
+        pmax = 0.0
+        for blk in _blocks(x, [1024] * nb):
+            e.process(blk); k.process(blk[:1]); c.process(blk); t.process(blk[:1])
+            rms, pk = k.read(); m, p = t.read(); pmax = max(pmax, float(p[0]))
+        r = e.read()[0]
+        want = np.array([-10.673171, -10.666748, -10.689788, -20.689789], np.float32)
+        assert np.allclose(r[[0, 2, 4, 5]], want, atol=2e-6, rtol=0), r
+        hm, hs, cnt = e.hist(0)
+        assert cnt[0] == 1000 and cnt[1] == 200
+        assert np.float32(rms[0]) == np.float32(0.20495217) and np.float32(pk[0]) == np.float32(0.24985489)
+        assert abs(float(c.read()[0]) - (-0.02344654)) < 1e-8
+        assert abs(pmax - 0.50329632) < 1e-8
+
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz")
+
+
+@needs_port
+@pytest.mark.skipif(not os.path.exists(GOLD), reason="golden vectors not generated")
+@pytest.mark.parametrize("kind", ["port"] + (["reference"] if HAVE_REF else []))
+def test_golden_vectors(kind):
+    import golden.make_golden as G
+    got = G.compute(kind)
+    ref = np.load(GOLD)
+    assert set(got) == set(ref.files)
+    for k in ref.files:
+        a, b = got[k], ref[k]
+        if k.startswith("pw_"):                               # FFT path: double DFT, still deterministic on one libm
+            assert np.allclose(a, b, rtol=1e-5, atol=1e-7), k
+        elif k.startswith("spec_maxports"):
+            ok = b > -500
+            assert np.array_equal(a[ok].view(np.uint32), b[ok].view(np.uint32)), k
+        else:
+            assert a.dtype == b.dtype and np.array_equal(a.view(np.uint8), b.view(np.uint8)), k
