@@ -56,6 +56,10 @@ int         b200m_host_free (void* p);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t    b200m_launch_count (void);
 
+/* ALU ceilings measured on the device (the driver's MEASURED_PEAKS.json has only HBM and bf16 GEMM):
+ * kind 0 = fp32 unfused FMUL+FADD issue rate, kind 1 = fp64 DMUL+DADD; result in 1e9 lane-operations/s. */
+int         b200m_peak_probe (int device, int kind, double* gops);
+
 /* Host-side coefficient design, callable without a GPU (pure functions of the sample rate, computed with
  * the host libm in the reference's expression types so that every value is bitwise the reference's):
  *   ebu : detect_init (ebumeter/ebu_r128_proc.cc:263-293)           -> a0 a1 a2 b1 b2 c3 c4
@@ -153,6 +157,24 @@ int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float
  * only kept when enabled with b200m_tpk_debug_capture(h,1): FIR bit-exactness tests */
 int b200m_tpk_debug_capture (b200m_tpk* h, int enable);
 int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t n_out, void* stream);
+
+/* ======================================================================================
+ * EBUr128 plugin cycle — the audio part of ebur128_run (src/ebulv2.cc:341-367) for N stereo
+ * instances: Ebu_r128_proc::process + (if dbtp_enable) TruePeakdsp::process_max on both channels,
+ * the getters, and the dBTP hold  tp_max = max (tp_max, coef_to_db (max (tp0, tp1)))  (:227-230,360-367).
+ * One host->device copy per block feeds both meters.  Atom/radar/GUI messaging is out of scope.
+ * ====================================================================================== */
+typedef struct b200m_r128 b200m_r128;
+enum { B200M_R128_START = 1, B200M_R128_PAUSE = 2, B200M_R128_RESET = 3 };   /* CTL_START/PAUSE/RESET, src/uris.h:187-203 */
+int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsamp, int dbtp_enable);
+int b200m_r128_destroy (b200m_r128* h);
+int b200m_r128_control (b200m_r128* h, int32_t inst, int cmd, void* stream);      /* inst = -1: all */
+int b200m_r128_run_device (b200m_r128* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
+int b200m_r128_run_host (b200m_r128* h, const float* in, size_t stride, uint32_t nfram);
+/* ebu_out: n_inst getter blocks (may be NULL); tp_max_db: n_inst floats, -inf when dBTP is disabled (may be NULL) */
+int b200m_r128_results (b200m_r128* h, b200m_ebu_result* ebu_out, float* tp_max_db, void* stream);
+b200m_ebu* b200m_r128_ebu (b200m_r128* h);     /* the underlying banks (histograms, state, coefficients) */
+b200m_tpk* b200m_r128_tpk (b200m_r128* h);
 
 /* ======================================================================================
  * Stereo correlation bank — replaces LV2M::Stcorrdsp (jmeters/stcorrdsp.h:27-55) as driven by

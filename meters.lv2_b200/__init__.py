@@ -42,6 +42,7 @@ _PROTOS = {
     "b200m_host_alloc": (C.c_int, [C.POINTER(_v), C.c_size_t]),
     "b200m_host_free": (C.c_int, [_v]),
     "b200m_launch_count": (C.c_uint64, []),
+    "b200m_peak_probe": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_double)]),
     "b200m_design_ebu": (C.c_int, [C.c_float, _v]),
     "b200m_design_tpk": (C.c_int, [C.c_float, _v, _v, _v]),
     "b200m_design_cor": (C.c_int, [C.c_int, C.c_float, C.c_float, _v]),
@@ -73,6 +74,15 @@ _PROTOS = {
     "b200m_tpk_state": (C.c_int, [_v, _v, _v, _v, _v, _v, _v, _v]),
     "b200m_tpk_debug_capture": (C.c_int, [_v, C.c_int]),
     "b200m_tpk_debug_upsampled": (C.c_int, [_v, C.c_uint32, _v, C.c_uint32, _v]),
+    # EBUr128 plugin cycle
+    "b200m_r128_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_float, C.c_int]),
+    "b200m_r128_destroy": (C.c_int, [_v]),
+    "b200m_r128_control": (C.c_int, [_v, C.c_int32, C.c_int, _v]),
+    "b200m_r128_run_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
+    "b200m_r128_run_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
+    "b200m_r128_results": (C.c_int, [_v, _v, _v, _v]),
+    "b200m_r128_ebu": (_v, [_v]),
+    "b200m_r128_tpk": (_v, [_v]),
     # Stcorr
     "b200m_cor_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_int, C.c_float, C.c_float]),
     "b200m_cor_destroy": (C.c_int, [_v]),
@@ -189,6 +199,13 @@ def design_spec(rate):
     return W
 
 
+def peak_probe(kind, device=0):
+    """kind 0: fp32 unfused mul+add, kind 1: fp64; returns 1e9 lane-ops/s measured on the device."""
+    v = C.c_double(0)
+    _ck(lib().b200m_peak_probe(device, kind, C.byref(v)))
+    return v.value
+
+
 def launch_count():
     return int(lib().b200m_launch_count())
 
@@ -201,7 +218,8 @@ class _Bank:
 
     def close(self):
         if getattr(self, "h", None) and self.h.value:
-            getattr(lib(), self._destroy)(self.h)
+            if self._destroy:
+                getattr(lib(), self._destroy)(self.h)
             self.h = _v()
 
     def __del__(self):
@@ -456,3 +474,47 @@ class Phasewheel(_Bank):
         a = [np.empty(self.bins, np.float32) for _ in range(4)]
         _ck(lib().b200m_pw_raw(self.h, inst, *[_np_ptr(v) for v in a], _stream_ptr(stream)))
         return a
+
+
+class EBUr128(_Bank):
+    """N x the EBUr128 plugin's audio cycle (ebur128_run, src/ebulv2.cc:341-367): EBU R128 + optional dBTP."""
+    _destroy = "b200m_r128_destroy"
+    START, PAUSE, RESET = 1, 2, 3
+
+    def __init__(self, n_inst, fsamp=48000.0, dbtp_enable=True, device=0):
+        super().__init__()
+        self.n_inst = n_inst
+        _ck(lib().b200m_r128_create(C.byref(self.h), device, n_inst, fsamp, int(dbtp_enable)))
+        self.ebu = Ebu_r128_proc.__new__(Ebu_r128_proc)
+        self.ebu.h = _v(lib().b200m_r128_ebu(self.h)); self.ebu.n_inst = n_inst; self.ebu.nchan = 2
+        self.ebu._destroy = None
+
+    def close(self):
+        if getattr(self, "ebu", None) is not None:
+            self.ebu.h = _v()
+        super().close()
+
+    def control(self, cmd, inst=-1, stream=None):
+        _ck(lib().b200m_r128_control(self.h, inst, cmd, _stream_ptr(stream)))
+
+    def run(self, x, stream=None):
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == 2 * self.n_inst
+            _ck(lib().b200m_r128_run_host(self.h, p, s, n))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == 2 * self.n_inst
+            _ck(lib().b200m_r128_run_device(self.h, p, s, n, _stream_ptr(stream)))
+
+    def run_ptr(self, ptr, stride, nfram, stream=None, host=False):
+        if host:
+            _ck(lib().b200m_r128_run_host(self.h, C.c_void_p(ptr), stride, nfram))
+        else:
+            _ck(lib().b200m_r128_run_device(self.h, C.c_void_p(ptr), stride, nfram, _stream_ptr(stream)))
+
+    def results(self, stream=None, out=None, tp=None):
+        out = np.empty(self.n_inst, EBU_RESULT_DTYPE) if out is None else out
+        tp = np.empty(self.n_inst, np.float32) if tp is None else tp
+        _ck(lib().b200m_r128_results(self.h, _np_ptr(out), _np_ptr(tp), _stream_ptr(stream)))
+        return out, tp

@@ -329,6 +329,10 @@ static void tpk_design (float fsamp, TpkParams& prm, float* ctab)
     zita_table (ctab, 24, 4, 1.0);                  // setup (fsamp, fsamp * 4.0, 1, 24, 1.0): np = 4, ratio-only
 }
 
+namespace b200m {
+void tpk_raw_pointers (b200m_tpk* h, float** tp_m, int** tp_res) { *tp_m = h->st.tp_m; *tp_res = h->st.tp_res; }
+}
+
 static cudaStream_t tpk_stream (b200m_tpk* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
 
 static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st)

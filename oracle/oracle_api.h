@@ -53,6 +53,11 @@ void  orc_tp_coeffs   (void* h, float* w4, float* ctab120); /* w1 w2 w3 g ; resa
 /* raw 4x stream of a fresh meter (after init's pre-roll): out has 4*n floats */
 void  orc_tp_upsample (float fsamp, const float* in, int n, int block, float* out);
 
+/* one ebur128_run audio cycle (src/ebulv2.cc:341-347) per stereo instance i: ebu[i].process (L,R) and, if
+ * tp != NULL, process_max on tp[2i] (L) and tp[2i+1] (R), followed by read(); all inside ONE thread fan-out
+ * and repeated for `nblocks` consecutive blocks (block b starts at in + b*nfram): the CPU baseline of bench.py */
+void  orc_r128_cycle  (void* ebu, void* tp, const float* in, size_t stride, int nfram, int nblocks, int nthreads);
+
 /* ---- K-meter (jmeters/kmeterdsp.h:27-62) ---- */
 void* orc_km_create   (int n, float fsamp);
 void  orc_km_destroy  (void* h);

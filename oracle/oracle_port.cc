@@ -563,6 +563,20 @@ void orc_tp_reset (void* h, int inst) { auto* b = (Bank<TruePeak>*)h; for (int i
 void orc_tp_coeffs (void* h, float* w4, float* ctab) { const TruePeak& t = ((Bank<TruePeak>*)h)->v[0]; w4[0] = t.w1; w4[1] = t.w2; w4[2] = t.w3; w4[3] = t.g; memcpy (ctab, zita_tab ().c, 120 * sizeof (float)); }
 void orc_tp_upsample (float, const float* in, int n, int, float* out) { Up4 u; for (int k = 0; k < n; ++k) u.push (in[k], out + 4 * k); }
 
+void orc_r128_cycle (void* eh, void* th, const float* in, size_t stride, int nfram, int nblocks, int nthreads) {
+    auto* e = (Bank<Ebu>*)eh; auto* t = (Bank<TruePeak>*)th;
+    par_for (e->n, nthreads, [=] (int a, int b) {
+        for (int i = a; i < b; ++i)
+            for (int blk = 0; blk < nblocks; ++blk) {
+                const float* l = in + (size_t)(2 * i) * stride + (size_t)blk * nfram;
+                const float* r = in + (size_t)(2 * i + 1) * stride + (size_t)blk * nfram;
+                const float* ip[2] = {l, r};
+                e->v[i].process (nfram, ip);
+                if (t) { t->v[2 * i].process_max (l, nfram); t->v[2 * i + 1].process_max (r, nfram); t->v[2 * i].res = true; t->v[2 * i + 1].res = true; }
+            }
+    });
+}
+
 void* orc_km_create (int n, float fs) { auto* b = new Bank<Kmeter>; b->n = n; b->v.resize (n); Kmeter::init (fs); return b; }
 void orc_km_destroy (void* h) { delete (Bank<Kmeter>*)h; }
 void orc_km_process (void* h, const float* in, size_t stride, int nfram, int nthreads) {

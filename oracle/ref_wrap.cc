@@ -163,6 +163,21 @@ void orc_tp_upsample (float fsamp, const float* in, int n, int block, float* out
     }
 }
 
+void orc_r128_cycle (void* eh, void* th, const float* in, size_t stride, int nfram, int nblocks, int nthreads)
+{
+    EbuB* e = (EbuB*)eh; TpB* t = (TpB*)th;
+    par_for (e->n, nthreads, [=] (int a, int b) {
+        for (int i = a; i < b; ++i)
+            for (int blk = 0; blk < nblocks; ++blk) {
+                float* l = const_cast<float*> (in + (size_t)(2 * i) * stride + (size_t)blk * nfram);
+                float* r = const_cast<float*> (in + (size_t)(2 * i + 1) * stride + (size_t)blk * nfram);
+                float* ip[2] = {l, r};
+                e->p[i]->process (nfram, ip);
+                if (t) { t->p[2 * i]->process_max (l, nfram); t->p[2 * i + 1]->process_max (r, nfram); t->p[2 * i]->read (); t->p[2 * i + 1]->read (); }
+            }
+    });
+}
+
 /* ------------------------------------------------------------------ K-meter */
 struct KmB { int n; std::vector<Kmeterdsp*> p; };
 void* orc_km_create (int n, float fsamp)

@@ -36,6 +36,7 @@ def _proto(lib):
         "orc_ebu_hist": (None, [_v, C.c_int, _v, _v, _v]),
         "orc_ebu_coeffs": (None, [_v, _v]),
         "orc_ebu_state": (None, [_v, C.c_int, _v, _v, _v, _v]),
+        "orc_r128_cycle": (None, [_v, _v, _v, C.c_size_t, C.c_int, C.c_int, C.c_int]),
         "orc_tp_create": (_v, [C.c_int, C.c_float]),
         "orc_tp_destroy": (None, [_v]),
         "orc_tp_process": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int, C.c_int]),
@@ -140,6 +141,13 @@ class Ebu:
         fr = np.empty(1, np.float32); c = np.empty(4, np.int32)
         self.L.orc_ebu_state(self.h, inst, ptr(z), ptr(pw), ptr(fr), ptr(c))
         return z, pw, fr[0], c
+
+
+def r128_cycle(ebu, tp, x, nfram, nblocks, nthreads):
+    """x: [2*n_inst, >= nfram*nblocks]; runs nblocks ebur128_run audio cycles on every instance (tp may be None)."""
+    p, s = planar(x)
+    assert x.shape[1] >= nfram * nblocks
+    ebu.L.orc_r128_cycle(ebu.h, tp.h if tp is not None else None, p, s, nfram, nblocks, nthreads)
 
 
 class TruePeak:
