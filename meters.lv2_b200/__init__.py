@@ -149,7 +149,8 @@ def _dev_ptr(x):
     if isinstance(x, int):
         raise TypeError("pass (ptr, stride, nfram) explicitly via process_ptr()")
     assert x.is_cuda and x.dim() == 2 and x.stride(1) == 1, "need a [channels, nfram] float32 CUDA tensor"
-    return C.c_void_p(x.data_ptr()), x.stride(0), x.shape[0], x.shape[1]
+    stride = x.stride(0) if x.shape[0] > 1 else max(x.stride(0), x.shape[1])   # 1-row tensors may report stride 0/1
+    return C.c_void_p(x.data_ptr()), stride, x.shape[0], x.shape[1]
 
 
 def _stream_ptr(stream):
@@ -170,7 +171,8 @@ def _host_planar(x):
     """numpy [channels, nfram] float32 (row-contiguous) or a pinned torch CPU tensor."""
     if isinstance(x, np.ndarray):
         assert x.dtype == np.float32 and x.ndim == 2 and x.strides[1] == 4
-        return _np_ptr(x), x.strides[0] // 4, x.shape[0], x.shape[1]
+        stride = x.strides[0] // 4 if x.shape[0] > 1 else max(x.strides[0] // 4, x.shape[1])
+        return _np_ptr(x), stride, x.shape[0], x.shape[1]
     assert (not x.is_cuda) and x.dim() == 2 and x.stride(1) == 1
     return C.c_void_p(x.data_ptr()), x.stride(0), x.shape[0], x.shape[1]
 

@@ -18,7 +18,10 @@ namespace b200m {
 
 constexpr int EBU_TILE   = 64;            // samples per smem tile
 constexpr int EBU_ROWP   = EBU_TILE + 4;  // padded row pitch (floats): 68 = 4 mod 32 -> LDS.128 conflict free
-constexpr int EBU_STAGES = 4;             // cp.async pipeline depth
+constexpr int EBU_STAGES = 3;             // cp.async pipeline depth (2 tiles = 128 samples in flight per channel)
+constexpr int EBU_WARPS  = 4;             // warps per CTA: one per SM sub-partition, each an independent 32-channel pipeline
+constexpr int EBU_WARP_FLOATS = EBU_STAGES * 32 * EBU_ROWP;
+constexpr int EBU_SMEM_BYTES = EBU_WARPS * EBU_WARP_FLOATS * 4;
 constexpr int EBU_MAXCHUNK = 32;          // chunks (block/fragment edges) handled per K1 launch
 constexpr int HIST_PITCH = 752;           // 751 bins padded to a 16-byte multiple
 
@@ -32,7 +35,11 @@ struct EbuChunks {                        // bit31: chunk ends a 50 ms fragment
 // ---- K1: K-weighting recurrence + per-chunk power sums ------------------------------------
 // One warp = 32 consecutive mono channels (lane = channel).  Tiles of [32 ch x 64 samples] are
 // copied global->shared with cp.async (each row of the planar input is contiguous, so every
-// 16-byte copy is fully coalesced), four tiles in flight; lane l then walks row l with LDS.128.
+// 16-byte copy is fully coalesced), two tiles in flight behind the one being consumed; lane l
+// walks row l with LDS.128, the next float4 always loaded one group ahead (the recurrence is a
+// pure dependent chain: an exposed LDS latency costs as much as two samples).
+// The kernel is bound by per-warp instruction issue, not HBM: a CTA therefore
+// carries exactly one warp per SM sub-partition.
 B200M_DEV void kw_step (float p, const EbuCoef& c, float& z1, float& z2, float& z3, float& z4, float& sj)
 {
     // x = p - b1*z1 - b2*z2 + 1e-15f;  y = a0*x + a1*z1 + a2*z2 - c3*z3 - c4*z4   (:321-322)
@@ -50,20 +57,22 @@ B200M_DEV void kw_step (float p, const EbuCoef& c, float& z1, float& z2, float& 
 }
 
 template <int NCHAN, bool ALIGNED>
-__global__ void __launch_bounds__ (32)
+__global__ void __launch_bounds__ (EBU_WARPS * 32)
 ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int nfram, EbuCoef cf, EbuChunks ck,
                   float fragm_f, float* __restrict__ zst, float* __restrict__ frpwr, float* __restrict__ fragpw, int n_inst)
 {
-    __shared__ __align__ (16) float tile[EBU_STAGES][32 * EBU_ROWP];
-    const int lane = threadIdx.x;
-    const int k0 = blockIdx.x * 32;
+    extern __shared__ __align__ (16) float ebu_smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int k0 = (blockIdx.x * EBU_WARPS + warp) * 32;
+    if (k0 >= nchans) return;                          // warp-uniform; warps never synchronise with each other
+    float* tile = ebu_smem + warp * EBU_WARP_FLOATS;
     const int k = min (k0 + lane, nchans - 1);       // tail lanes shadow the last channel (no stores)
     const bool live = (k0 + lane) < nchans;
     const int ntiles = (nfram + EBU_TILE - 1) / EBU_TILE;
 
     auto issue = [&] (int t) {
         if (t < ntiles) {
-            float* dst = tile[t % EBU_STAGES];
+            float* dst = tile + (t % EBU_STAGES) * (32 * EBU_ROWP);
             const int s0 = t * EBU_TILE;
             if (ALIGNED) {
                 const int c4 = (lane & 15) * 4;                  // column of this lane's 16-byte piece
@@ -101,45 +110,64 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int n
     int cend = (int)(ck.v[0] & 0x7fffffffu);           // end position (exclusive) of the current chunk
     bool cfrag = (ck.v[0] >> 31) != 0;
 
+    // end of one detect_process() call (:324-335): state scrub, channel sum, _frpwr +=, fragment hand-over (:217-221)
+    auto chunk_end = [&] () {
+        z1 = scrub (z1); z2 = scrub (z2); z3 = scrub (z3); z4 = scrub (z4);
+        float si;
+        if (NCHAN == 1) si = __fmul_rn (2.0f, sj);
+        else si = __fadd_rn (sj, __shfl_xor_sync (0xffffffffu, sj, 1));   // 1.0f*sjL + 1.0f*sjR
+        fp = __fadd_rn (fp, si);
+        if (cfrag) {
+            if (live && (k % NCHAN) == 0) fragpw[(size_t)nfr * n_inst + inst] = __fdiv_rn (fp, fragm_f);
+            fp = 1e-30f;
+            ++nfr;
+        }
+        sj = 0.0f;
+        ++ci;
+        if (ci < ck.n) { cend = (int)(ck.v[ci] & 0x7fffffffu); cfrag = (ck.v[ci] >> 31) != 0; }
+        else cend = 0x7fffffff;
+    };
+
 #pragma unroll
     for (int t = 0; t < EBU_STAGES - 1; ++t) issue (t);
 
     for (int t = 0; t < ntiles; ++t) {
         cp_async_wait<EBU_STAGES - 2> ();
         __syncwarp ();
-        const float* row = tile[t % EBU_STAGES] + lane * EBU_ROWP;
+        const float* row = tile + (t % EBU_STAGES) * (32 * EBU_ROWP) + lane * EBU_ROWP;
         int a = t * EBU_TILE;
         const int b = min (a + EBU_TILE, nfram);
-        while (a < b) {
-            const int e = min (b, cend);
-            int j = a;
-            // scalar head up to a 4-aligned position, vector body, scalar tail
-            for (; j < e && (j & 3); ++j) kw_step (row[j - t * EBU_TILE], cf, z1, z2, z3, z4, sj);
-            for (; j + 4 <= e; j += 4) {
-                const float4 v = *reinterpret_cast<const float4*> (row + (j - t * EBU_TILE));
-                kw_step (v.x, cf, z1, z2, z3, z4, sj);
-                kw_step (v.y, cf, z1, z2, z3, z4, sj);
-                kw_step (v.z, cf, z1, z2, z3, z4, sj);
-                kw_step (v.w, cf, z1, z2, z3, z4, sj);
+        if (b - a == EBU_TILE && cend >= b) {
+            // fast path: a whole tile inside one chunk; float4 groups with a one-group register prefetch
+            const float4* r4 = reinterpret_cast<const float4*> (row);
+            float4 cur = r4[0];
+#pragma unroll 4
+            for (int q = 0; q < EBU_TILE / 4; ++q) {
+                const float4 nxt = r4[(q + 1) & (EBU_TILE / 4 - 1)];
+                kw_step (cur.x, cf, z1, z2, z3, z4, sj);
+                kw_step (cur.y, cf, z1, z2, z3, z4, sj);
+                kw_step (cur.z, cf, z1, z2, z3, z4, sj);
+                kw_step (cur.w, cf, z1, z2, z3, z4, sj);
+                cur = nxt;
             }
-            for (; j < e; ++j) kw_step (row[j - t * EBU_TILE], cf, z1, z2, z3, z4, sj);
-            a = e;
-            if (a == cend) {
-                // end of one detect_process() call (:324-335): state scrub, channel sum, _frpwr +=
-                z1 = scrub (z1); z2 = scrub (z2); z3 = scrub (z3); z4 = scrub (z4);
-                float si;
-                if (NCHAN == 1) si = __fmul_rn (2.0f, sj);
-                else si = __fadd_rn (sj, __shfl_xor_sync (0xffffffffu, sj, 1));   // 1.0f*sjL + 1.0f*sjR
-                fp = __fadd_rn (fp, si);
-                if (cfrag) {                                                  // :217-221
-                    if (live && (k % NCHAN) == 0) fragpw[(size_t)nfr * n_inst + inst] = __fdiv_rn (fp, fragm_f);
-                    fp = 1e-30f;
-                    ++nfr;
+            a = b;
+            if (a == cend) chunk_end ();
+        } else {
+            while (a < b) {
+                const int e = min (b, cend);
+                int j = a;
+                // scalar head up to a 4-aligned position, vector body, scalar tail
+                for (; j < e && (j & 3); ++j) kw_step (row[j - t * EBU_TILE], cf, z1, z2, z3, z4, sj);
+                for (; j + 4 <= e; j += 4) {
+                    const float4 v = *reinterpret_cast<const float4*> (row + (j - t * EBU_TILE));
+                    kw_step (v.x, cf, z1, z2, z3, z4, sj);
+                    kw_step (v.y, cf, z1, z2, z3, z4, sj);
+                    kw_step (v.z, cf, z1, z2, z3, z4, sj);
+                    kw_step (v.w, cf, z1, z2, z3, z4, sj);
                 }
-                sj = 0.0f;
-                ++ci;
-                if (ci < ck.n) { cend = (int)(ck.v[ci] & 0x7fffffffu); cfrag = (ck.v[ci] >> 31) != 0; }
-                else cend = 0x7fffffff;
+                for (; j < e; ++j) kw_step (row[j - t * EBU_TILE], cf, z1, z2, z3, z4, sj);
+                a = e;
+                if (a == cend) chunk_end ();
             }
         }
         __syncwarp ();
@@ -154,7 +182,7 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int n
 }
 
 // ---- K2: per-fragment loudness, histograms, gated integration ------------------------------
-struct EbuCtl { int div1, div2, integr, pad; };
+struct EbuCtl { int div1, div2, integr, calc; };
 
 // Ebu_r128_hist::integrate (:82-102).  `c[t]` holds bin t*32+lane.  Only non-zero bins change the
 // running float sum, so the warp walks them in bin order (ballot) and applies the "/= 10 after
@@ -245,83 +273,91 @@ B200M_DEV void hist_calc_range (const int* row, int count, const float* bp, int 
     v1 = __fdiv_rn ((float)(j - 699), 10.0f);
 }
 
-// Ebu_r128_hist::addpoint (:66-79); lane 0 performs the update
-B200M_DEV void hist_addpoint (int* row, int* cnt, int* err, float v, int lane)
-{
-    int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, v), 700.5f));
-    if (k < 0) return;
-    if (lane == 0) {
-        if (k > 750) { k = 750; (*err)++; }
-        row[k]++; (*cnt)++;
-    }
-}
+// K2a: one THREAD per instance, one completed 50 ms fragment (process :217-243 minus the gated statistics).
+// ring layout [64][n_inst] so that lane = instance accesses coalesce; each thread parks its 64-slot ring column
+// in shared memory (column private to the thread: no barrier needed) for the two ordered sums.
+constexpr int K2A_THREADS = 128;
 
-constexpr int K2_WARPS = 4;
-
-__global__ void __launch_bounds__ (K2_WARPS * 32)
-ebu_loudness_hist (int n_inst, int nfrag, int wrind0, const float* __restrict__ fragpw, float* __restrict__ ring,
-                   EbuCtl* __restrict__ ctl, b200m_ebu_result* __restrict__ res, int* __restrict__ histM,
-                   int* __restrict__ histS, int* __restrict__ cnt, const float* __restrict__ bin_power)
+__global__ void __launch_bounds__ (K2A_THREADS)
+ebu_fragment_kernel (int n_inst, int frag, int wrind, const float* __restrict__ fragpw, float* __restrict__ ring,
+                     EbuCtl* __restrict__ ctl, b200m_ebu_result* __restrict__ res, int* __restrict__ histM,
+                     int* __restrict__ histS, int* __restrict__ cnt)
 {
-    __shared__ float sring[K2_WARPS][64];
-    __shared__ float sbp[100];
-    for (int i = threadIdx.x; i < 100; i += blockDim.x) sbp[i] = bin_power[i];
-    __syncthreads ();
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int inst = blockIdx.x * K2_WARPS + w;
-    if (inst >= n_inst) return;
-    float* rg = sring[w];
-    rg[lane] = ring[(size_t)inst * 64 + lane];
-    rg[lane + 32] = ring[(size_t)inst * 64 + lane + 32];
-    EbuCtl c = ctl[inst];
-    b200m_ebu_result r = res[inst];
-    int* hM = histM + (size_t)inst * HIST_PITCH;
-    int* hS = histS + (size_t)inst * HIST_PITCH;
-    int* ct = cnt + (size_t)inst * 4;
-    int cntM = ct[0], cntS = ct[1];
-    int wr = wrind0;
-    __syncwarp ();
-    for (int f = 0; f < nfrag; ++f) {
-        const float p = fragpw[(size_t)f * n_inst + inst];
-        if (lane == 0) rg[wr] = p;                         // _power[_wrind++] = _frpwr / _fragm (:218)
-        wr = (wr + 1) & 63;
-        __syncwarp ();
-        r.frag_power = p;
-        // addfrags (8), addfrags (60) (:251-260): sequential sums, oldest fragment first
-        float s8 = 0.0f, s60 = 0.0f;
-        { const int k = (wr - 8) & 63;  for (int i = 0; i < 8; ++i)  s8  = __fadd_rn (s8,  rg[(i + k) & 63]); }
-        { const int k = (wr - 60) & 63; for (int i = 0; i < 60; ++i) s60 = __fadd_rn (s60, rg[(i + k) & 63]); }
-        float lm = __fadd_rn (-0.6976f, __fmul_rn (10.0f, log10f_glibc (__fdiv_rn (s8, 8.0f))));
-        float ls = __fadd_rn (-0.6976f, __fmul_rn (10.0f, log10f_glibc (__fdiv_rn (s60, 60.0f))));
-        if (!finitef_ (lm) || lm < -200.0f) lm = -200.0f;  // :224-225
-        if (!finitef_ (ls) || ls < -200.0f) ls = -200.0f;
-        r.loudness_M = lm; r.loudness_S = ls;
-        if (lm > r.maxloudn_M) r.maxloudn_M = lm;
-        if (ls > r.maxloudn_S) r.maxloudn_S = ls;
-        if (c.integr) {                                     // :228-242
-            if (++c.div1 == 2) {
-                const int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, lm), 700.5f));
-                hist_addpoint (hM, ct + 0, ct + 2, lm, lane);
-                if (k >= 0) ++cntM;
-                c.div1 = 0;
-            }
-            if (++c.div2 == 10) {
-                const int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, ls), 700.5f));
-                hist_addpoint (hS, ct + 1, ct + 3, ls, lane);
-                if (k >= 0) ++cntS;
-                c.div2 = 0;
-                __syncwarp ();                              // lane 0's bin updates -> visible to the warp
-                hist_calc_integ (hM, cntM, sbp, lane, r.integrated, r.integ_thr);
-                hist_calc_range (hS, cntS, sbp, lane, r.range_min, r.range_max, r.range_thr);
+    __shared__ float sring[64][K2A_THREADS];
+    const int tid = threadIdx.x;
+    const int i = blockIdx.x * K2A_THREADS + tid;
+    if (i >= n_inst) return;
+#pragma unroll 8
+    for (int w = 0; w < 64; ++w) sring[w][tid] = ring[(size_t)w * n_inst + i];
+    EbuCtl c = ctl[i];
+    b200m_ebu_result r = res[i];
+    const float p = fragpw[(size_t)frag * n_inst + i];
+    sring[wrind][tid] = p;                                 // _power[_wrind++] = _frpwr / _fragm (:218)
+    ring[(size_t)wrind * n_inst + i] = p;
+    const int wr = (wrind + 1) & 63;
+    r.frag_power = p;
+    // addfrags (8), addfrags (60) (:251-260): sequential sums, oldest fragment first
+    float s8 = 0.0f, s60 = 0.0f;
+    { const int k = (wr - 8) & 63;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)  s8  = __fadd_rn (s8,  sring[(q + k) & 63][tid]); }
+    { const int k = (wr - 60) & 63;
+#pragma unroll 10
+      for (int q = 0; q < 60; ++q) s60 = __fadd_rn (s60, sring[(q + k) & 63][tid]); }
+    float lm = __fadd_rn (-0.6976f, __fmul_rn (10.0f, log10f_glibc (__fdiv_rn (s8, 8.0f))));
+    float ls = __fadd_rn (-0.6976f, __fmul_rn (10.0f, log10f_glibc (__fdiv_rn (s60, 60.0f))));
+    if (!finitef_ (lm) || lm < -200.0f) lm = -200.0f;      // :224-225
+    if (!finitef_ (ls) || ls < -200.0f) ls = -200.0f;
+    r.loudness_M = lm; r.loudness_S = ls;
+    if (lm > r.maxloudn_M) r.maxloudn_M = lm;
+    if (ls > r.maxloudn_S) r.maxloudn_S = ls;
+    if (c.integr) {                                         // :228-242
+        if (++c.div1 == 2) {                                // Ebu_r128_hist::addpoint (:66-79)
+            c.div1 = 0;
+            int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, lm), 700.5f));
+            if (k >= 0) {
+                if (k > 750) { k = 750; cnt[(size_t)i * 4 + 2]++; }
+                histM[(size_t)i * HIST_PITCH + k]++;
+                r.hist_M_count = ++cnt[(size_t)i * 4 + 0];
             }
         }
+        if (++c.div2 == 10) {
+            c.div2 = 0;
+            int k = (int)floorf (__fadd_rn (__fmul_rn (10.0f, ls), 700.5f));
+            if (k >= 0) {
+                if (k > 750) { k = 750; cnt[(size_t)i * 4 + 3]++; }
+                histS[(size_t)i * HIST_PITCH + k]++;
+                r.hist_S_count = ++cnt[(size_t)i * 4 + 1];
+            }
+            c.calc = 1;                                     // calc_integ + calc_range follow in K2b
+        }
     }
-    __syncwarp ();
-    ring[(size_t)inst * 64 + lane] = rg[lane];
-    ring[(size_t)inst * 64 + lane + 32] = rg[lane + 32];
+    ctl[i] = c; res[i] = r;
+}
+
+// K2b: one WARP per instance, only launched when the host's phase book-keeping says that some instance
+// completed its 10th fragment: calc_integ on hist_M, calc_range on hist_S (:240-241).
+constexpr int K2B_WARPS = 4;
+
+__global__ void __launch_bounds__ (K2B_WARPS * 32)
+ebu_gate_kernel (int n_inst, EbuCtl* __restrict__ ctl, b200m_ebu_result* __restrict__ res, const int* histM,
+                 const int* histS, const int* __restrict__ cnt, const float* __restrict__ bin_power)
+{
+    __shared__ float sbp[100];
+    for (int q = threadIdx.x; q < 100; q += blockDim.x) sbp[q] = bin_power[q];
+    __syncthreads ();
+    const int lane = threadIdx.x & 31;
+    const int inst = blockIdx.x * K2B_WARPS + (threadIdx.x >> 5);
+    if (inst >= n_inst) return;
+    if (!ctl[inst].calc) return;
+    float vi = res[inst].integrated, th = res[inst].integ_thr;
+    float v0 = res[inst].range_min, v1 = res[inst].range_max, rt = res[inst].range_thr;
+    hist_calc_integ (histM + (size_t)inst * HIST_PITCH, cnt[(size_t)inst * 4 + 0], sbp, lane, vi, th);
+    hist_calc_range (histS + (size_t)inst * HIST_PITCH, cnt[(size_t)inst * 4 + 1], sbp, lane, v0, v1, rt);
     if (lane == 0) {
-        r.hist_M_count = cntM; r.hist_S_count = cntS;
-        ctl[inst] = c; res[inst] = r;
+        res[inst].integrated = vi; res[inst].integ_thr = th;
+        res[inst].range_min = v0; res[inst].range_max = v1; res[inst].range_thr = rt;
+        ctl[inst].calc = 0;
     }
 }
 
@@ -340,12 +376,12 @@ __global__ void ebu_ctl_kernel (int n_inst, int inst_sel, int cmd, int nchan, fl
     r.maxloudn_M = r.maxloudn_S = r.integrated = r.integ_thr = -200.0f;
     r.range_min = r.range_max = r.range_thr = -200.0f;
     r.hist_M_count = r.hist_S_count = 0;
-    ctl[i].div1 = ctl[i].div2 = 0;
+    ctl[i].div1 = ctl[i].div2 = 0; ctl[i].calc = 0;
     if (cmd == 3) {
         ctl[i].integr = 0;
         frpwr[i] = 1e-30f;
         r.loudness_M = r.loudness_S = -200.0f; r.frag_power = 0.0f;
-        for (int b = 0; b < 64; ++b) ring[(size_t)i * 64 + b] = 0.0f;
+        for (int b = 0; b < 64; ++b) ring[(size_t)b * n_inst + i] = 0.0f;
         const size_t nch = (size_t)n_inst * nchan;
         for (int c = 0; c < nchan; ++c) for (int z = 0; z < 4; ++z) zst[z * nch + (size_t)i * nchan + c] = 0.0f;
     }
@@ -391,6 +427,21 @@ struct b200m_ebu {
     EbuCtl* d_ctl = nullptr; b200m_ebu_result* d_res = nullptr;
     int *d_histM = nullptr, *d_histS = nullptr, *d_cnt = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
+    // Host mirror of every instance's S-histogram period (_div2, :234-241), kept in O(1) per fragment: an
+    // integrating instance has div2 = (G - base) mod 10 where G counts fragments; cnt10[r] = number of integrating
+    // instances with base = r.  The gated-statistics kernel (K2b) is launched only for fragments where some
+    // instance wraps, i.e. cnt10[G] > 0.
+    std::vector<uint8_t> integ, base, frozen; int cnt10[10]; int G = 0;
+    void phase_reset () { integ.assign (n_inst, 0); base.assign (n_inst, 0); frozen.assign (n_inst, 0); for (int& c : cnt10) c = 0; G = 0; }
+    void phase_ctl (int32_t inst, int cmd) {
+        for (uint32_t i = 0; i < n_inst; ++i) {
+            if (inst >= 0 && (uint32_t)inst != i) continue;
+            if (cmd == 0 && integ[i]) { frozen[i] = (uint8_t)((G - base[i] + 10) % 10); cnt10[base[i]]--; integ[i] = 0; }
+            else if (cmd == 1 && !integ[i]) { base[i] = (uint8_t)((G - frozen[i] + 10) % 10); cnt10[base[i]]++; integ[i] = 1; }
+            else if (cmd == 2) { if (integ[i]) { cnt10[base[i]]--; base[i] = (uint8_t)G; cnt10[base[i]]++; } else frozen[i] = 0; }
+        }
+    }
+    bool phase_tick () { G = (G + 1) % 10; return cnt10[G] > 0; }     // one fragment completed: does anyone wrap?
 };
 
 // Host-side coefficient design; restates Ebu_r128_proc::detect_init (ebu_r128_proc.cc:263-293).
@@ -422,6 +473,7 @@ static int ebu_ctl (b200m_ebu* h, int32_t inst, int cmd, void* stream)
     if (!h) return set_err (B200M_E_INVAL, "NULL handle");
     if (inst >= (int32_t)h->n_inst) return set_err (B200M_E_INVAL, "instance %d out of range", inst);
     DeviceGuard g (h->device);
+    if (cmd == 3) h->phase_reset (); else h->phase_ctl (inst, cmd);
     ebu_ctl_kernel<<<(h->n_inst + 127) / 128, 128, 0, (cudaStream_t)stream>>> (
         (int)h->n_inst, inst, cmd, (int)h->nchan, h->d_z, h->d_frpwr, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt);
     B200M_LAUNCHED (1);
@@ -473,7 +525,14 @@ int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nch
     A ((void**)&h->d_cnt, (size_t)4 * n_inst * sizeof (int));
     if (e == cudaSuccess) e = cudaMemcpy (h->d_binpow, bp, sizeof (bp), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
+    for (int al = 0; al < 2 && e == cudaSuccess; ++al) {      // K1 carries 102 KB of dynamic shared memory per CTA
+        if (nchan == 1) e = al ? cudaFuncSetAttribute (ebu_kweight_frag<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SMEM_BYTES)
+                               : cudaFuncSetAttribute (ebu_kweight_frag<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SMEM_BYTES);
+        else            e = al ? cudaFuncSetAttribute (ebu_kweight_frag<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SMEM_BYTES)
+                               : cudaFuncSetAttribute (ebu_kweight_frag<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SMEM_BYTES);
+    }
     if (e != cudaSuccess) { int rc = cuda_fail (e, "ebu_create allocations", __FILE__, __LINE__); b200m_ebu_destroy (h); return rc; }
+    h->phase_reset ();
     int rc = b200m_ebu_reset (h, -1, nullptr);       // constructor + init() end in reset() (:153-173)
     if (rc == 0 && cudaDeviceSynchronize () != cudaSuccess) rc = set_err (B200M_E_CUDA, "reset kernel failed");
     if (rc) { b200m_ebu_destroy (h); return rc; }
@@ -524,17 +583,23 @@ static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
         }
         const float* src = d_in + done;
         const bool al = aligned && (done % 4 == 0);
-        dim3 grid ((nch + 31) / 32), blk (32);
-#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, 0, st>>> (src, stride, nch, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
+        const int nwarps = (nch + 31) / 32;
+        dim3 grid ((nwarps + EBU_WARPS - 1) / EBU_WARPS), blk (EBU_WARPS * 32);
+#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, EBU_SMEM_BYTES, st>>> (src, stride, nch, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
         if (h->nchan == 1) { if (al) EBU_K1 (1, true); else EBU_K1 (1, false); }
         else               { if (al) EBU_K1 (2, true); else EBU_K1 (2, false); }
 #undef EBU_K1
         B200M_LAUNCHED (1);
-        if (nfrag) {
-            ebu_loudness_hist<<<(h->n_inst + K2_WARPS - 1) / K2_WARPS, K2_WARPS * 32, 0, st>>> (
-                (int)h->n_inst, nfrag, h->wrind, h->d_fragpw, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt, h->d_binpow);
+        for (int f = 0; f < nfrag; ++f) {                    // fragments complete in order; each may trigger gating
+            ebu_fragment_kernel<<<(h->n_inst + K2A_THREADS - 1) / K2A_THREADS, K2A_THREADS, 0, st>>> (
+                (int)h->n_inst, f, h->wrind, h->d_fragpw, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt);
             B200M_LAUNCHED (1);
-            h->wrind = (h->wrind + nfrag) & 63;
+            h->wrind = (h->wrind + 1) & 63;
+            if (h->phase_tick ()) {
+                ebu_gate_kernel<<<(h->n_inst + K2B_WARPS - 1) / K2B_WARPS, K2B_WARPS * 32, 0, st>>> (
+                    (int)h->n_inst, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt, h->d_binpow);
+                B200M_LAUNCHED (1);
+            }
         }
         done += pos;
     }
@@ -601,7 +666,7 @@ int b200m_ebu_state (b200m_ebu* h, uint32_t inst, float* z, float* power64, floa
     for (uint32_t c = 0; c < h->nchan; ++c)
         for (int q = 0; q < 4; ++q)
             B200M_CUDA (cudaMemcpyAsync (z + 4 * c + q, h->d_z + q * nch + (size_t)inst * h->nchan + c, sizeof (float), cudaMemcpyDeviceToHost, st));
-    B200M_CUDA (cudaMemcpyAsync (power64, h->d_ring + (size_t)inst * 64, 64 * sizeof (float), cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaMemcpy2DAsync (power64, sizeof (float), h->d_ring + inst, (size_t)h->n_inst * sizeof (float), sizeof (float), 64, cudaMemcpyDeviceToHost, st));
     B200M_CUDA (cudaMemcpyAsync (frpwr, h->d_frpwr + inst, sizeof (float), cudaMemcpyDeviceToHost, st));
     EbuCtl c;
     B200M_CUDA (cudaMemcpyAsync (&c, h->d_ctl + inst, sizeof (c), cudaMemcpyDeviceToHost, st));

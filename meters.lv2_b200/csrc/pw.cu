@@ -140,9 +140,17 @@ static cudaStream_t pw_stream (b200m_pw* h, void* stream) { return h->last_host 
 
 static int pw_process (b200m_pw* h, const float* d_in, size_t stride, uint32_t nfram, float db_thresh, int* fired, cudaStream_t st)
 {
-    int any = 0;
-    uint32_t done = 0;
-    while (done < nfram) {                                  // fftx_run: steps of at most window_size (gui/fft.c:346-360)
+    // fftx_run walks the block in steps of at most window_size (gui/fft.c:346-360) and process_audio runs ONCE
+    // after both channels' fftx_run (gui/phasewheel.c:1310-1313): when several analyses fire inside one call only
+    // the last one's spectra survive, so only that one is launched (its ring state is the one at its firing time
+    // because launches execute in stream order).
+    int any = 0, last_fire = -1;
+    {
+        uint32_t sm = h->smps, d = 0; int step = 0;
+        while (d < nfram) { const uint32_t n = (nfram - d) < h->N ? (nfram - d) : h->N; sm += n; if (sm >= h->sps) { sm = 0; last_fire = step; } d += n; ++step; }
+    }
+    uint32_t done = 0; int step = 0;
+    while (done < nfram) {
         const uint32_t n = (nfram - done) < h->N ? (nfram - done) : h->N;
         const size_t total = (size_t)h->n_inst * 2 * n;
         pw_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>> (d_in + done, stride, (int)(h->n_inst * 2), (int)n, (int)h->N, (int)h->rboff, h->d_ring);
@@ -151,12 +159,14 @@ static int pw_process (b200m_pw* h, const float* d_in, size_t stride, uint32_t n
         h->smps += n;
         if (h->smps >= h->sps) {                            // :308-313
             h->step = h->smps; h->smps = 0;
-            pw_analyze_kernel<<<h->n_inst, PW_THREADS, (size_t)2 * h->N * sizeof (float2), st>>> (
-                h->d_ring, (int)h->N, h->log2n, (int)h->rboff, h->d_win, h->d_tw, db_thresh, h->d_raw, h->d_phase, h->d_level, h->d_peak);
-            B200M_LAUNCHED (1);
+            if (step == last_fire) {
+                pw_analyze_kernel<<<h->n_inst, PW_THREADS, (size_t)2 * h->N * sizeof (float2), st>>> (
+                    h->d_ring, (int)h->N, h->log2n, (int)h->rboff, h->d_win, h->d_tw, db_thresh, h->d_raw, h->d_phase, h->d_level, h->d_peak);
+                B200M_LAUNCHED (1);
+            }
             any = 1;
         }
-        done += n;
+        done += n; ++step;
     }
     if (fired) *fired = any;
     B200M_CUDA (cudaGetLastError ());

@@ -19,10 +19,6 @@
 
 namespace b200m {
 
-constexpr int TPK_CH = 8;                   // channels per CTA
-constexpr int TPK_TC = 128;                 // input samples per chunk
-constexpr int TPK_XP = 48 + TPK_TC + 4;     // x row pitch (floats) = 180
-constexpr int TPK_OP = 4 * TPK_TC + 4;      // |out| row pitch (floats) = 516
 constexpr int TPK_THREADS = 128;
 
 __constant__ float c_tp_tab[120];           // zita table for hl=24, np=4, fr=1.0: [(np+1)][hl]
@@ -60,38 +56,47 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
     for (int a = 0; a < 16; ++a) o[a] = __fsub_rn (acc[a], 1e-20f);
 }
 
-template <bool TP, bool TPMAX, bool KM>
+// Tile geometry: CH channels x TC input samples per chunk.  process_max (no serial true-peak lane) uses
+// <8,128>: smallest tiles, best balance over 148 SMs.  process() uses <16,64>: the ballistics warp then runs
+// 16 channels x {z1 filter, z2 filter} = 32 busy lanes (the two one-pole attack filters are independent until
+// the per-sample m = max (m, z1 + z2), which costs one shuffle), so the serial part issues ~1/4 of the
+// instructions it would with one channel per lane.
+template <int CH, int TC, bool TP, bool TPMAX, bool KM>
 __global__ void __launch_bounds__ (TPK_THREADS)
 tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
             float* __restrict__ dbg)
 {
-    __shared__ __align__ (16) float xs[2][TPK_CH][TPK_XP];
-    __shared__ __align__ (16) float ob[(TP && !TPMAX) ? TPK_CH : 1][(TP && !TPMAX) ? TPK_OP : 4];
-    __shared__ float smax[TPK_CH];
+    constexpr int XP = 48 + TC + 4;               // x row pitch (floats): 16-byte multiple
+    constexpr int OP = 4 * TC + 4;                // |out| row pitch
+    constexpr int GPC = TC / 4;                   // 4-sample groups per channel per chunk
+    constexpr bool BAL = TP && !TPMAX;
+    static_assert (!BAL || CH == 16, "split ballistics lanes assume 16 channels per CTA");
+    static_assert (CH <= 32 && (CH * GPC) % TPK_THREADS == 0, "tile geometry");
+    __shared__ __align__ (16) float xs[2][CH][XP];
+    __shared__ __align__ (16) float ob[BAL ? CH : 1][BAL ? OP : 4];
+    __shared__ float smax[CH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = blockIdx.x * TPK_CH;
-    const int nchunks = (nfram + TPK_TC - 1) / TPK_TC;
+    const int c0 = blockIdx.x * CH;
+    const int nchunks = (nfram + TC - 1) / TC;
 
     auto load_chunk = [&] (int c, int buf) {
         if (c < nchunks) {
-            const int s0 = c * TPK_TC;
+            const int s0 = c * TC;
             if (aligned) {
-                // 8 rows x 32 16-byte pieces = 256 copies over 128 threads
 #pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const int idx = tid + h * TPK_THREADS;
-                    const int r = idx >> 5, c4 = (idx & 31) * 4;
+                for (int idx = tid; idx < CH * GPC; idx += TPK_THREADS) {      // CH rows x GPC 16-byte pieces
+                    const int r = idx / GPC, c4 = (idx % GPC) * 4;
                     const int ch = min (c0 + r, n_chan - 1);
                     const int left = (nfram - (s0 + c4)) * 4;
                     const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
                     cp_async16 (&xs[buf][r][48 + c4], nb ? in + (size_t)ch * stride + s0 + c4 : in, nb);
                 }
             } else {
-#pragma unroll
-                for (int h = 0; h < TPK_CH; ++h) {
-                    const int ch = min (c0 + h, n_chan - 1);
-                    const bool ok = (s0 + tid) < nfram;
-                    cp_async4 (&xs[buf][h][48 + tid], ok ? in + (size_t)ch * stride + s0 + tid : in, ok ? 4 : 0);
+                for (int idx = tid; idx < CH * TC; idx += TPK_THREADS) {
+                    const int r = idx / TC, cc = idx % TC;
+                    const int ch = min (c0 + r, n_chan - 1);
+                    const bool ok = (s0 + cc) < nfram;
+                    cp_async4 (&xs[buf][r][48 + cc], ok ? in + (size_t)ch * stride + s0 + cc : in, ok ? 4 : 0);
                 }
             }
         }
@@ -99,63 +104,64 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, 
     };
 
     // history -> xs[0][.][0..47]
-    for (int idx = tid; idx < TPK_CH * 48; idx += TPK_THREADS) {
+    for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
         const int r = idx / 48, j = idx % 48;
         xs[0][r][j] = TP ? st.hist[(size_t)min (c0 + r, n_chan - 1) * 48 + j] : 0.0f;
     }
     load_chunk (0, 0);
 
-    // per-channel serial state: warp 0 lanes 0..7 = true-peak ballistics, warp 1 lanes 0..7 = K-meter
-    const bool is_tp = TP && warp == 0 && lane < TPK_CH;
-    const bool is_km = KM && warp == 1 && lane < TPK_CH;
-    const int chs = min (c0 + lane, n_chan - 1);
-    const bool live = (c0 + lane) < n_chan;
-    float z1 = 0, z2 = 0, m = 0, p = 0; int res = 0;
+    // serial lanes.  warp 0: true-peak ballistics, lane = filter * 16 + channel.  warp 1: K-meter, lane = channel.
+    const bool is_tp = BAL && warp == 0;
+    const int tch = lane & 15, filt = lane >> 4;
+    const bool is_km = KM && warp == 1 && lane < CH;
+    const int chs = min (c0 + (is_tp ? tch : lane), n_chan - 1);
+    const bool live = (c0 + (is_tp ? tch : lane)) < n_chan;
+    float z = 0, m = 0, p = 0, wf = 0; int res = 0;
     float kz1 = 0, kz2 = 0, kt = 0;
     if (is_tp) {
         res = st.tp_res[chs];
         m = res ? 0.0f : st.tp_m[chs];                                  // truepeakdsp.cc:52-55
         p = res ? 0.0f : st.tp_p[chs];
-        const float a = st.tp_z1[chs], b = st.tp_z2[chs];
-        z1 = a > 20 ? 20 : (a < 0 ? 0 : a);
-        z2 = b > 20 ? 20 : (b < 0 ? 0 : b);
+        const float a = filt ? st.tp_z2[chs] : st.tp_z1[chs];
+        z = a > 20 ? 20 : (a < 0 ? 0 : a);
+        wf = filt ? prm.w2 : prm.w1;
     }
     if (is_km) {
         const float a = st.km_z1[chs], b = st.km_z2[chs];               // kmeterdsp.cc:74-75
         kz1 = a > 50 ? 50 : (a < 0 ? 0 : a);
         kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
     }
-    if (tid < TPK_CH) smax[tid] = 0.0f;                                   // process_max: plain max (:109-122)
+    if (tid < CH) smax[tid] = 0.0f;                                       // process_max: plain max (:109-122)
     const int km_n = (nfram / 4) * 4;                                     // "n /= 4" drops n mod 4 samples (:79)
 
     for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1;
-        const int s0 = c * TPK_TC;
-        const int len = min (TPK_TC, nfram - s0);
+        const int s0 = c * TC;
+        const int len = min (TC, nfram - s0);
         cp_async_wait<0> ();
         __syncthreads ();                                   // chunk c (and its 48-sample prefix) is in xs[buf]
         // prefix of the next chunk = last 48 samples of this one; start the next load
-        for (int idx = tid; idx < TPK_CH * 48; idx += TPK_THREADS) {
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
             const int r = idx / 48, j = idx % 48;
             xs[buf ^ 1][r][j] = xs[buf][r][len + j];
         }
         load_chunk (c + 1, buf ^ 1);
 
         if (TP) {
-            // FIR phase: warp w handles channels w and w+4; lane q handles inputs 4q..4q+3 of the chunk
+            // FIR phase: item = (channel r, group q of 4 consecutive inputs); consecutive lanes take consecutive groups
 #pragma unroll 1
-            for (int pass = 0; pass < TPK_CH / (TPK_THREADS / 32); ++pass) {
-                const int r = warp + pass * (TPK_THREADS / 32);
+            for (int item = tid; item < CH * GPC; item += TPK_THREADS) {
+                const int r = item / GPC, q = item % GPC;
                 float vmax = 0.0f;
-                if (4 * lane < len) {
+                if (4 * q < len) {
                     float w[52];
-                    const float4* xr = reinterpret_cast<const float4*> (&xs[buf][r][4 * lane]);
+                    const float4* xr = reinterpret_cast<const float4*> (&xs[buf][r][4 * q]);
 #pragma unroll
                     for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
                     float o[16];
                     fir16 (w, o);
                     if (dbg && (c0 + r) < n_chan) {
-                        float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * lane));
+                        float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
 #pragma unroll
                         for (int i = 0; i < 4; ++i) d[i] = make_float4 (o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     }
@@ -163,42 +169,44 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, 
                         // positions beyond len inside the last group come from zero-filled input: exclude them
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (4 * lane + i < len) {
+                            if (4 * q + i < len) {
 #pragma unroll
                                 for (int ph = 0; ph < 4; ++ph) { const float v = fabsf (o[4 * i + ph]); if (v > vmax) vmax = v; }
                             }
                     } else {
-                        float4* d = reinterpret_cast<float4*> (&ob[(TP && !TPMAX) ? r : 0][(TP && !TPMAX) ? 16 * lane : 0]);
+                        float4* d = reinterpret_cast<float4*> (&ob[BAL ? r : 0][BAL ? 16 * q : 0]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
                             d[i] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
                     }
                 }
-                if (TPMAX) {                                // channel r belongs to this warp alone: no race on smax[r]
+                if (TPMAX) {
+                    // the lanes that share channel r are GPC consecutive lanes of this warp: segmented max, one atomic-free
+                    // writer per (warp, channel) because a channel's groups never straddle two warps (GPC divides 32 or 32 | GPC)
+                    constexpr int SEG = GPC < 32 ? GPC : 32;
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));
-                    if (lane == 0 && vmax > smax[r]) smax[r] = vmax;
+                    for (int o = SEG / 2; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));
+                    if ((lane & (SEG - 1)) == 0) atomicMax (reinterpret_cast<int*> (&smax[r]), __float_as_int (vmax));   // vmax >= +0: int order == float order
                 }
             }
         }
-        if (TP && !TPMAX) __syncthreads ();                 // |out| tile complete
+        if (BAL) __syncthreads ();                          // |out| tile complete
 
-        if (is_tp && !TPMAX) {
-            // PPM ballistics over the 4*len oversampled magnitudes (truepeakdsp.cc:57-84)
-            const float4* b4 = reinterpret_cast<const float4*> (&ob[(TP && !TPMAX) ? lane : 0][0]);
+        if (is_tp) {
+            // PPM ballistics over the 4*len oversampled magnitudes (truepeakdsp.cc:57-84); this lane owns one of the
+            // two attack filters of channel tch
+            const float4* b4 = reinterpret_cast<const float4*> (&ob[BAL ? tch : 0][0]);
             for (int j = 0; j < len; ++j) {
                 const float4 v4 = b4[j];
-                z1 = __fmul_rn (z1, prm.w3);
-                z2 = __fmul_rn (z2, prm.w3);
+                z = __fmul_rn (z, prm.w3);
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const float v = vv[i];
-                    if (v > z1) z1 = __fadd_rn (z1, __fmul_rn (prm.w1, __fsub_rn (v, z1)));
-                    if (v > z2) z2 = __fadd_rn (z2, __fmul_rn (prm.w2, __fsub_rn (v, z2)));
+                    if (v > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v, z)));
                     if (v > p) p = v;
                 }
-                const float t = __fadd_rn (z1, z2);
+                const float t = __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16));    // z1 + z2
                 if (t > m) m = t;
             }
         }
@@ -227,26 +235,28 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, 
     if (TP) {
         // new history = the 48 samples that precede the next block (left in xs[nchunks&1][.][0..47])
         const int hb = nchunks & 1;
-        for (int idx = tid; idx < TPK_CH * 48; idx += TPK_THREADS) {
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
             const int r = idx / 48, j = idx % 48;
             if (c0 + r < n_chan) st.hist[(size_t)(c0 + r) * 48 + j] = xs[hb][r][j];
         }
     }
-    if (TP && TPMAX && tid < TPK_CH && (c0 + tid) < n_chan) {
+    if (TP && TPMAX && tid < CH && (c0 + tid) < n_chan) {
         // process_max (:108-123): m = _res ? 0 : _m; running max; _m = m.  _res, _p, _z1, _z2 untouched.
         const int ch = c0 + tid;
         float mm = st.tp_res[ch] ? 0.0f : st.tp_m[ch];
         if (smax[tid] > mm) mm = smax[tid];
         st.tp_m[ch] = mm;
     }
-    if (is_tp && !TPMAX && live) {
-        st.tp_z1[chs] = __fadd_rn (z1, 1e-20f);             // :86-87
-        st.tp_z2[chs] = __fadd_rn (z2, 1e-20f);
-        m = __fmul_rn (m, prm.g);                           // :89
-        if (res) { st.tp_m[chs] = m; st.tp_p[chs] = p; st.tp_res[chs] = 0; }
+    if (is_tp && live) {
+        if (filt) st.tp_z2[chs] = __fadd_rn (z, 1e-20f);    // :86-87
         else {
-            if (m > st.tp_m[chs]) st.tp_m[chs] = m;
-            if (p > st.tp_p[chs]) st.tp_p[chs] = p;
+            st.tp_z1[chs] = __fadd_rn (z, 1e-20f);
+            m = __fmul_rn (m, prm.g);                       // :89
+            if (res) { st.tp_m[chs] = m; st.tp_p[chs] = p; st.tp_res[chs] = 0; }
+            else {
+                if (m > st.tp_m[chs]) st.tp_m[chs] = m;
+                if (p > st.tp_p[chs]) st.tp_p[chs] = p;
+            }
         }
     }
     if (is_km && live) {
@@ -342,11 +352,11 @@ static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
     // Kmeterdsp::process (:65-70): per-period fallback multiplier, a pure function of n
     prm.fall = powf (10.0f, -0.05f * 15.0f * ((float)(int)nfram / h->fsamp));
     const int aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
-    dim3 grid ((h->n_chan + TPK_CH - 1) / TPK_CH), blk (TPK_THREADS);
-#define TPK_GO(TP, MX, KM) tpk_kernel<TP, MX, KM><<<grid, blk, 0, st>>> (d_in, stride, (int)h->n_chan, (int)nfram, aligned, prm, h->st, h->d_dbg)
-    if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (true, true, true); else TPK_GO (true, true, false); }
-    else if (tp) { if (km) TPK_GO (true, false, true); else TPK_GO (true, false, false); }
-    else TPK_GO (false, false, true);
+    dim3 blk (TPK_THREADS);
+#define TPK_GO(CH, TC, TP, MX, KM) tpk_kernel<CH, TC, TP, MX, KM><<<(h->n_chan + CH - 1) / CH, blk, 0, st>>> (d_in, stride, (int)h->n_chan, (int)nfram, aligned, prm, h->st, h->d_dbg)
+    if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 128, true, true, true); else TPK_GO (8, 128, true, true, false); }
+    else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
+    else TPK_GO (16, 64, false, false, true);
 #undef TPK_GO
     B200M_LAUNCHED (1);
     B200M_CUDA (cudaGetLastError ());

@@ -147,3 +147,62 @@ def test_whole_mix_histogram_extension():
     assert np.array_equal(m[:751], hm) and np.array_equal(m[752:752 + 751], hs) and m[1504] == cm and m[1505] == cs
     out = g.mix_finish(mix)
     assert np.isfinite(out).all() and -40 < out[0] < 0
+
+
+def test_sharded_banks_equal_single_bank():
+    """multi-GPU = replicas over disjoint instance ranges: two half banks (as two ranks would own them) must equal
+    one full bank bit for bit, and their all-reduced mix vector must equal the full bank's."""
+    import torch
+    import meters_lv2_b200 as B
+    from meters_lv2_b200 import shard
+    n = 22
+    x = S.white(2 * n, 1024 * 140, seed=66)
+    xd = torch.from_numpy(x).cuda()
+    full = B.Ebu_r128_proc(n, 2); full.integr_start()
+    parts = []
+    for r in range(2):
+        lo, cnt = shard.shard_range(n, r, 2)
+        b = B.Ebu_r128_proc(cnt, 2); b.integr_start(); parts.append((lo, cnt, b))
+    for blk in range(140):
+        v = xd[:, blk * 1024:(blk + 1) * 1024]
+        full.process(v)
+        for lo, cnt, b in parts:
+            b.process(v[2 * lo:2 * (lo + cnt)])
+    fr = full.results()
+    cat = np.concatenate([b.results() for _, _, b in parts])
+    assert np.array_equal(fr.view(np.uint8), cat.view(np.uint8))
+    mf = torch.zeros(B.MIX_WORDS, dtype=torch.int32, device="cuda"); full.mix_reduce(mf)
+    acc = torch.zeros_like(mf)
+    for _, _, b in parts:
+        m = torch.zeros_like(mf); b.mix_reduce(m); acc += m
+    assert torch.equal(mf, acc)
+    assert np.array_equal(full.mix_finish(mf).view(np.uint32), parts[0][2].mix_finish(acc).view(np.uint32))
+
+
+def test_ebur128_plugin_cycle_with_dbtp():
+    """b200m_r128_*: ebur128_run's audio cycle (src/ebulv2.cc:341-367), device and host paths."""
+    import torch
+    import meters_lv2_b200 as B
+    n = 12
+    x = S.white(2 * n, 1024 * 130, seed=67)
+    xd = torch.from_numpy(x).cuda()
+    for host in (False, True):
+        g = B.EBUr128(n, 48000.0, True); g.control(B.EBUr128.START)
+        oe = O.Ebu(n, 2); ot = O.TruePeak(2 * n); oe.integr("start")
+        tpmax = np.full(n, -np.inf, np.float32)
+        for b in range(130):
+            blk = np.ascontiguousarray(x[:, b * 1024:(b + 1) * 1024])
+            g.run(blk if host else xd[:, b * 1024:(b + 1) * 1024])
+            oe.process(blk); ot.process(blk, mode=1)
+            m, _ = ot.read()
+            v = np.maximum(m[0::2], m[1::2])
+            tp = np.float32(20.0) * np.log10(v)            # compared with 1e-4 dB tolerance below, exact on device
+            tpmax = np.maximum(tpmax, tp.astype(np.float32))
+        res, tp = g.results()
+        orr = o_read = oe.read()
+        for i, name in enumerate(RES):
+            assert np.array_equal(res[name].view(np.uint32), orr[:, i].view(np.uint32)), name
+        assert np.abs(tp - tpmax).max() < 1e-4
+    g2 = B.EBUr128(3, 48000.0, False)
+    g2.run(xd[:6, :1024])
+    assert np.isneginf(g2.results()[1]).all()              # dBTP disabled: tp_max = -inf (:365-366)
