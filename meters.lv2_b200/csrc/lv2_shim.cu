@@ -1,0 +1,207 @@
+// lv2_shim.cu — per-instance LV2 façade over the batched engine: `lv2_descriptor()` with the reference's URIs,
+// port indices and run() semantics, so that an LV2 host can load this library where it loaded meters.so.
+//
+// Covers the control-port plugins of the hot path (src/meters.cc:745-792 lists all 38 descriptors):
+//   COR (cor_run :511-536), dBTPmono/stereo (dbtp_run :438-508), K12/K14/K20 mono/stereo (kmeter_run :333-418),
+//   spectr30mono/stereo (spectrum_run, src/spectrumlv2.c:159-257).
+// EBUr128, TPnRMS/DR14, phasewheel, stereoscope, goniometer, bitmeter and SigDistHist publish their results only
+// through LV2 atom messages (src/uris.h:279-318), which is out of scope: use the batch API.
+// Each LV2 instance owns a bank of one instance; run() is synchronous (host buffers in, ports out), exactly the
+// reference's calling convention (robtk/jackwrap.c:531-544).  LV2 core types are restated from the LV2
+// specification (the SDK is not installed); the struct layout is the stable public C ABI.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+
+extern "C" {
+typedef void* LV2_Handle;
+typedef struct { const char* URI; void* data; } LV2_Feature;
+typedef struct LV2_Descriptor_s {
+    const char* URI;
+    LV2_Handle (*instantiate) (const struct LV2_Descriptor_s*, double, const char*, const LV2_Feature* const*);
+    void (*connect_port) (LV2_Handle, uint32_t, void*);
+    void (*activate) (LV2_Handle);
+    void (*run) (LV2_Handle, uint32_t);
+    void (*deactivate) (LV2_Handle);
+    void (*cleanup) (LV2_Handle);
+    const void* (*extension_data) (const char*);
+} LV2_Descriptor;
+}
+
+#define MTR_URI "http://gareus.org/oss/lv2/meters#"      /* src/uris.h:37 */
+
+namespace {
+
+enum Kind { K_COR, K_DBTP, K_KMETER, K_SPEC };
+
+struct Shim {
+    Kind kind; uint32_t chn;
+    b200m_cor* cor = nullptr; b200m_tpk* tpk = nullptr; b200m_spec* spec = nullptr;
+    float* port[68] = {nullptr};          // raw port pointers, indexed as in the reference's enums
+    float* stage = nullptr; size_t stage_cap = 0;   // pinned [chn][cap] planar staging
+    float p_refl = -9999, peak_max[2] = {0, 0}, peak_hold = 0;   // src/meters.cc:245-251
+};
+
+// port enums: src/meters.cc:59-70 (MTR_*), src/spectrumlv2.c:35-44 (SA_*)
+enum { MTR_REFLEVEL = 0, MTR_INPUT0, MTR_OUTPUT0, MTR_LEVEL0, MTR_INPUT1, MTR_OUTPUT1, MTR_LEVEL1, MTR_PEAK0, MTR_PEAK1, MTR_HOLD };
+enum { SA_SPEED = 60, SA_RESET = 61, SA_AMP = 62, SA_STATE = 63, SA_INPUT0 = 64, SA_OUTPUT0 = 65, SA_INPUT1 = 66, SA_OUTPUT1 = 67 };
+
+bool stage_in (Shim* s, const float* const* in, uint32_t n)
+{
+    if (n > s->stage_cap) {
+        if (s->stage) b200m_host_free (s->stage);
+        s->stage = nullptr; s->stage_cap = 0;
+        const size_t cap = n < 1024 ? 1024 : B200M_MAX_BLOCK;
+        if (b200m_host_alloc ((void**)&s->stage, (size_t)s->chn * cap * sizeof (float))) return false;
+        s->stage_cap = cap;
+    }
+    for (uint32_t c = 0; c < s->chn; ++c) memcpy (s->stage + (size_t)c * s->stage_cap, in[c], n * sizeof (float));
+    return true;
+}
+
+void pass_through (float* const* in, float* const* out, uint32_t chn, uint32_t n)
+{
+    for (uint32_t c = 0; c < chn; ++c) if (in[c] != out[c] && in[c] && out[c]) memcpy (out[c], in[c], sizeof (float) * n);
+}
+
+LV2_Handle shim_instantiate (const LV2_Descriptor* d, double rate, const char*, const LV2_Feature* const*)
+{
+    Shim* s = new (std::nothrow) Shim;
+    if (!s) return nullptr;
+    const char* u = d->URI + strlen (MTR_URI);
+    int rc = -1;
+    if (!strcmp (u, "COR")) { s->kind = K_COR; s->chn = 2; rc = b200m_cor_create (&s->cor, 0, 1, (int)rate, 2e3f, 0.3f); }          // :204-207
+    else if (!strncmp (u, "dBTP", 4)) { s->kind = K_DBTP; s->chn = strstr (u, "stereo") ? 2 : 1; rc = b200m_tpk_create (&s->tpk, 0, s->chn, (float)rate, B200M_TPK_TRUEPEAK); }
+    else if (u[0] == 'K') { s->kind = K_KMETER; s->chn = strstr (u, "stereo") ? 2 : 1; rc = b200m_tpk_create (&s->tpk, 0, s->chn, (float)rate, B200M_TPK_KMETER); }
+    else if (!strncmp (u, "spectr30", 8)) { s->kind = K_SPEC; s->chn = strstr (u, "stereo") ? 2 : 1; rc = b200m_spec_create (&s->spec, 0, 1, s->chn, rate); }
+    if (rc) { delete s; return nullptr; }                  // instantiate() -> NULL, as the reference does on failure
+    return s;
+}
+
+void shim_connect (LV2_Handle h, uint32_t port, void* data)
+{
+    Shim* s = (Shim*)h;
+    if (port < 68) s->port[port] = (float*)data;
+}
+
+void shim_cleanup (LV2_Handle h)
+{
+    Shim* s = (Shim*)h;
+    b200m_cor_destroy (s->cor); b200m_tpk_destroy (s->tpk); b200m_spec_destroy (s->spec);
+    if (s->stage) b200m_host_free (s->stage);
+    delete s;
+}
+
+const void* shim_extension_data (const char*) { return nullptr; }
+
+void run_cor (Shim* s, uint32_t n)
+{
+    float* in[2] = {s->port[MTR_INPUT0], s->port[MTR_INPUT1]}; float* out[2] = {s->port[MTR_OUTPUT0], s->port[MTR_OUTPUT1]};
+    if (!stage_in (s, in, n)) return;
+    float v = 0;
+    if (b200m_cor_process_host (s->cor, s->stage, s->stage_cap, n) == 0 && b200m_cor_results (s->cor, &v, nullptr) == 0)
+        *s->port[MTR_LEVEL0] = v;                          // *level[0] = cor->read() (:516-517)
+    pass_through (in, out, 2, n);
+}
+
+// the "re-use port 0 to request/notify UI" handshake shared by dbtp_run (:444-463) and kmeter_run (:339-357)
+bool refl_handshake (Shim* s, bool kmeter)
+{
+    bool reinit = false;
+    const float r = *s->port[MTR_REFLEVEL];
+    if (s->p_refl != r) {
+        if (fabsf (r) < 3) {
+            reinit = true;
+            if (kmeter) s->peak_hold = 0; else { s->peak_max[0] = 0; s->peak_max[1] = 0; }
+            b200m_tpk_reset (s->tpk, -1, nullptr);
+        }
+        if (kmeter) { if (fabsf (r) == 3) reinit = true; else s->p_refl = r; }
+        else if (fabsf (r) != 3) s->p_refl = r;
+    }
+    if (!kmeter && fabsf (r) == 3) reinit = true;
+    return reinit;
+}
+
+void run_tpk (Shim* s, uint32_t n)
+{
+    const bool km = s->kind == K_KMETER;
+    const bool reinit = refl_handshake (s, km);
+    float* in[2] = {s->port[MTR_INPUT0], s->port[MTR_INPUT1]}; float* out[2] = {s->port[MTR_OUTPUT0], s->port[MTR_OUTPUT1]};
+    if (!stage_in (s, in, n)) return;
+    if (b200m_tpk_process_host (s->tpk, s->stage, s->stage_cap, n, B200M_TP_MODE_PROCESS)) return;
+    pass_through (in, out, s->chn, n);
+    if (reinit) {                                          // force parameter change (:381-389, :476-489)
+        if (km) { if (s->chn == 1) *s->port[MTR_OUTPUT1] = -1 - (rand () & 0xffff); else *s->port[MTR_HOLD] = -1 - (rand () & 0xffff); }
+        else if (s->chn == 1) { *s->port[MTR_LEVEL0] = -500 - (rand () & 0xffff); *s->port[MTR_INPUT1] = -500 - (rand () & 0xffff); }
+        else { for (int p : {MTR_LEVEL0, MTR_LEVEL1, MTR_PEAK0, MTR_PEAK1}) *s->port[p] = -500 - (rand () & 0xffff); }
+        return;
+    }
+    b200m_tpk_result r[2];
+    if (b200m_tpk_read_device (s->tpk, nullptr) || b200m_tpk_results (s->tpk, r, nullptr)) return;
+    const float rlgain = 1.0f;                             // :243
+    if (km) {                                              // :391-407
+        if (s->chn == 1) {
+            *s->port[MTR_LEVEL0] = rlgain * r[0].km_rms;
+            *s->port[MTR_INPUT1] = rlgain * r[0].km_peak;
+            if (*s->port[MTR_INPUT1] > s->peak_hold) s->peak_hold = *s->port[MTR_INPUT1];
+            *s->port[MTR_OUTPUT1] = s->peak_hold;
+        } else {
+            for (int c = 0; c < 2; ++c) {
+                *s->port[c ? MTR_LEVEL1 : MTR_LEVEL0] = rlgain * r[c].km_rms;
+                float* pk = s->port[c ? MTR_PEAK1 : MTR_PEAK0];
+                *pk = rlgain * r[c].km_peak;
+                if (*pk > s->peak_hold) s->peak_hold = *pk;
+            }
+            *s->port[MTR_HOLD] = s->peak_hold;
+        }
+    } else {                                               // :491-507
+        for (uint32_t c = 0; c < s->chn; ++c) {
+            if (s->peak_max[c] < rlgain * r[c].tp_p) s->peak_max[c] = rlgain * r[c].tp_p;
+            *s->port[c ? MTR_LEVEL1 : MTR_LEVEL0] = rlgain * r[c].tp_m;
+        }
+        if (s->chn == 1) *s->port[MTR_INPUT1] = s->peak_max[0];
+        else { *s->port[MTR_PEAK0] = s->peak_max[0]; *s->port[MTR_PEAK1] = s->peak_max[1]; }
+    }
+}
+
+void run_spec (Shim* s, uint32_t n)
+{
+    float* in[2] = {s->port[SA_INPUT0], s->port[SA_INPUT1]}; float* out[2] = {s->port[SA_OUTPUT0], s->port[SA_OUTPUT1]};
+    if (!stage_in (s, in, n)) return;
+    float ports[60];
+    if (b200m_spec_process_host (s->spec, s->stage, s->stage_cap, n, *s->port[SA_SPEED], *s->port[SA_RESET])) return;
+    if (b200m_spec_results (s->spec, ports, nullptr)) return;
+    for (int i = 0; i < 30; ++i) {
+        if (s->port[i]) *s->port[i] = ports[i];
+        if (s->port[30 + i]) *s->port[30 + i] = ports[30 + i] <= -500.0f ? -500.0f - (rand () & 0xffff) : ports[30 + i];   // :243-246
+    }
+    pass_through (in, out, s->chn, n);
+}
+
+void shim_run (LV2_Handle h, uint32_t n)
+{
+    Shim* s = (Shim*)h;
+    if (n == 0 || n > B200M_MAX_BLOCK) return;             // run() never fails
+    switch (s->kind) {
+    case K_COR: run_cor (s, n); break;
+    case K_DBTP: case K_KMETER: run_tpk (s, n); break;
+    case K_SPEC: run_spec (s, n); break;
+    }
+}
+
+#define DESC(NAME) {MTR_URI NAME, shim_instantiate, shim_connect, nullptr, shim_run, nullptr, shim_cleanup, shim_extension_data}
+const LV2_Descriptor g_desc[] = {
+    DESC ("COR"), DESC ("spectr30mono"), DESC ("dBTPmono"), DESC ("dBTPstereo"),
+    DESC ("K12mono"), DESC ("K14mono"), DESC ("K20mono"), DESC ("K12stereo"), DESC ("K14stereo"), DESC ("K20stereo"),
+    DESC ("spectr30stereo"),
+};
+
+}  // namespace
+
+// The one symbol meters.so exports (src/meters.cc:739-792).  Hosts look plugins up by URI; the indices here are
+// the covered subset in the reference's order.
+extern "C" __attribute__ ((visibility ("default"))) const LV2_Descriptor* lv2_descriptor (uint32_t index)
+{
+    return index < sizeof (g_desc) / sizeof (g_desc[0]) ? &g_desc[index] : nullptr;
+}
