@@ -58,16 +58,17 @@ B200M_DEV void kw_step (float p, const EbuCoef& c, float& z1, float& z2, float& 
 
 template <int NCHAN, bool ALIGNED>
 __global__ void __launch_bounds__ (EBU_WARPS * 32)
-ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int nfram, EbuCoef cf, EbuChunks ck,
+ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k_first, int k_end, int nfram, EbuCoef cf, EbuChunks ck,
                   float fragm_f, float* __restrict__ zst, float* __restrict__ frpwr, float* __restrict__ fragpw, int n_inst)
 {
+    // channels [k_first, k_end) of the bank's nchans (a slice: *_run_host overlaps the copy of slice s+1 with slice s)
     extern __shared__ __align__ (16) float ebu_smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k0 = (blockIdx.x * EBU_WARPS + warp) * 32;
-    if (k0 >= nchans) return;                          // warp-uniform; warps never synchronise with each other
+    const int k0 = k_first + (blockIdx.x * EBU_WARPS + warp) * 32;
+    if (k0 >= k_end) return;                           // warp-uniform; warps never synchronise with each other
     float* tile = ebu_smem + warp * EBU_WARP_FLOATS;
-    const int k = min (k0 + lane, nchans - 1);       // tail lanes shadow the last channel (no stores)
-    const bool live = (k0 + lane) < nchans;
+    const int k = min (k0 + lane, k_end - 1);        // tail lanes shadow the last channel (no stores)
+    const bool live = (k0 + lane) < k_end;
     const int ntiles = (nfram + EBU_TILE - 1) / EBU_TILE;
 
     auto issue = [&] (int t) {
@@ -81,14 +82,14 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int n
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const int r = 2 * i + (lane >> 4);
-                    const int kr = min (k0 + r, nchans - 1);
+                    const int kr = min (k0 + r, k_end - 1);
                     const float* src = in + (size_t)kr * stride + s0 + c4;
                     cp_async16 (dst + r * EBU_ROWP + c4, nb ? src : in, nb);
                 }
             } else {
 #pragma unroll 4
                 for (int r = 0; r < 32; ++r) {
-                    const int kr = min (k0 + r, nchans - 1);
+                    const int kr = min (k0 + r, k_end - 1);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int c = lane + 32 * h;
@@ -564,7 +565,11 @@ int b200m_ebu_integr_start (b200m_ebu* h, int32_t inst, void* stream) { return e
 int b200m_ebu_integr_pause (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 0, stream); }
 int b200m_ebu_integr_reset (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 2, stream); }
 
-static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
+// One Ebu_r128_proc::process call for every instance.  `nsl` instance slices [bounds[s], bounds[s+1]) are launched
+// separately, slice s after event ready[s] (the host->device copy of its rows) when `ready` is given; the
+// fragment/gating kernels run once, after the last slice.
+int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st,
+                        int nsl, const uint32_t* bounds, cudaEvent_t* ready)
 {
     const int nch = (int)(h->n_inst * h->nchan);
     const bool aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
@@ -583,13 +588,18 @@ static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
         }
         const float* src = d_in + done;
         const bool al = aligned && (done % 4 == 0);
-        const int nwarps = (nch + 31) / 32;
-        dim3 grid ((nwarps + EBU_WARPS - 1) / EBU_WARPS), blk (EBU_WARPS * 32);
-#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, EBU_SMEM_BYTES, st>>> (src, stride, nch, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
-        if (h->nchan == 1) { if (al) EBU_K1 (1, true); else EBU_K1 (1, false); }
-        else               { if (al) EBU_K1 (2, true); else EBU_K1 (2, false); }
+        for (int sl = 0; sl < nsl; ++sl) {
+            const int kf = (int)(bounds[sl] * h->nchan), ke = (int)(bounds[sl + 1] * h->nchan);
+            if (ke <= kf) continue;
+            if (ready && done == 0) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
+            const int nwarps = (ke - kf + 31) / 32;
+            dim3 grid ((nwarps + EBU_WARPS - 1) / EBU_WARPS), blk (EBU_WARPS * 32);
+#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, EBU_SMEM_BYTES, st>>> (src, stride, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
+            if (h->nchan == 1) { if (al) EBU_K1 (1, true); else EBU_K1 (1, false); }
+            else               { if (al) EBU_K1 (2, true); else EBU_K1 (2, false); }
 #undef EBU_K1
-        B200M_LAUNCHED (1);
+            B200M_LAUNCHED (1);
+        }
         for (int f = 0; f < nfrag; ++f) {                    // fragments complete in order; each may trigger gating
             ebu_fragment_kernel<<<(h->n_inst + K2A_THREADS - 1) / K2A_THREADS, K2A_THREADS, 0, st>>> (
                 (int)h->n_inst, f, h->wrind, h->d_fragpw, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt);
@@ -605,6 +615,12 @@ static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
     }
     B200M_CUDA (cudaGetLastError ());
     return 0;
+}
+
+static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
+{
+    const uint32_t bounds[2] = {0, h->n_inst};
+    return ebu_process_sliced (h, d_in, stride, nfram, st, 1, bounds, nullptr);
 }
 
 int b200m_ebu_process_device (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, void* stream)

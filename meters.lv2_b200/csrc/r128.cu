@@ -27,20 +27,37 @@ void tpk_raw_pointers (b200m_tpk* h, float** tp_m, int** tp_res);
 
 }  // namespace b200m
 
+// sliced process entry points of the two banks (ebu.cu, tpk.cu)
+extern "C" int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready);
+int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready);
+
 using namespace b200m;
+
+constexpr int R128_SLICES = 4;
 
 struct b200m_r128 {
     int device; uint32_t n_inst; int dbtp;
     b200m_ebu* ebu = nullptr; b200m_tpk* tpk = nullptr;
     float* d_tpmax = nullptr;
-    cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
+    // own: EBU kernels + joins (host path);  side: true-peak kernels (run concurrently with the latency-bound EBU
+    // kernel);  copy: host->device slices, so that the copy of slice s+1 overlaps the kernels of slice s
+    cudaStream_t own = nullptr, side = nullptr, copy = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_tp = nullptr, ev_done = nullptr, ev_ready[R128_SLICES] = {nullptr};
+    HostStage stage; bool last_host = false;
 };
 
-static int r128_run (b200m_r128* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
+static int r128_run (b200m_r128* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, cudaEvent_t* ready)
 {
-    if (int rc = b200m_ebu_process_device (h->ebu, d_in, stride, nfram, st)) return rc;
+    uint32_t bi[R128_SLICES + 1], bc[R128_SLICES + 1];
+    for (int s = 0; s <= nsl; ++s) { bi[s] = (uint32_t)((uint64_t)h->n_inst * s / nsl); bc[s] = 2 * bi[s]; }
     if (h->dbtp) {
-        if (int rc = b200m_tpk_process_device (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, st)) return rc;
+        if (!ready) { B200M_CUDA (cudaEventRecord (h->ev_in, st)); B200M_CUDA (cudaStreamWaitEvent (h->side, h->ev_in, 0)); }
+        if (int rc = tpk_process_sliced (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, h->side, nsl, bc, ready)) return rc;
+        B200M_CUDA (cudaEventRecord (h->ev_tp, h->side));
+    }
+    if (int rc = ebu_process_sliced (h->ebu, d_in, stride, nfram, st, nsl, bi, ready)) return rc;
+    if (h->dbtp) {
+        B200M_CUDA (cudaStreamWaitEvent (st, h->ev_tp, 0));
         float* tp_m; int* tp_res;
         tpk_raw_pointers (h->tpk, &tp_m, &tp_res);
         r128_tp_kernel<<<(h->n_inst + 255) / 256, 256, 0, st>>> ((int)h->n_inst, tp_m, tp_res, h->d_tpmax);
@@ -67,7 +84,9 @@ int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsam
     if (!rc) {
         DeviceGuard g (device);
         cudaError_t e = cudaMalloc ((void**)&h->d_tpmax, n_inst * sizeof (float));
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
+        for (cudaStream_t* sp : {&h->own, &h->side, &h->copy}) if (e == cudaSuccess) e = cudaStreamCreateWithFlags (sp, cudaStreamNonBlocking);
+        for (cudaEvent_t* ep : {&h->ev_in, &h->ev_tp, &h->ev_done}) if (e == cudaSuccess) e = cudaEventCreateWithFlags (ep, cudaEventDisableTiming);
+        for (int s = 0; s < R128_SLICES; ++s) if (e == cudaSuccess) e = cudaEventCreateWithFlags (&h->ev_ready[s], cudaEventDisableTiming);
         if (e == cudaSuccess) {
             r128_fill_kernel<<<(n_inst + 255) / 256, 256>>> ((int)n_inst, h->d_tpmax, -INFINITY);
             B200M_LAUNCHED (1);
@@ -85,8 +104,11 @@ int b200m_r128_destroy (b200m_r128* h)
     if (!h) return 0;
     b200m_ebu_destroy (h->ebu); b200m_tpk_destroy (h->tpk);
     DeviceGuard g (h->device);
+    cudaDeviceSynchronize ();
     cudaFree (h->d_tpmax); h->stage.release ();
-    if (h->own) cudaStreamDestroy (h->own);
+    for (cudaStream_t sp : {h->own, h->side, h->copy}) if (sp) cudaStreamDestroy (sp);
+    for (cudaEvent_t ep : {h->ev_in, h->ev_tp, h->ev_done}) if (ep) cudaEventDestroy (ep);
+    for (int s = 0; s < R128_SLICES; ++s) if (h->ev_ready[s]) cudaEventDestroy (h->ev_ready[s]);
     delete h;
     return 0;
 }
@@ -108,7 +130,7 @@ int b200m_r128_run_device (b200m_r128* h, const float* d_in, size_t stride, uint
     if (int rc = check_block_args (h, d_in, stride, nfram)) return rc;
     DeviceGuard g (h->device);
     h->last_host = false;
-    return r128_run (h, d_in, stride, nfram, (cudaStream_t)stream);
+    return r128_run (h, d_in, stride, nfram, (cudaStream_t)stream, 1, nullptr);
 }
 
 int b200m_r128_run_host (b200m_r128* h, const float* in, size_t stride, uint32_t nfram)
@@ -117,10 +139,19 @@ int b200m_r128_run_host (b200m_r128* h, const float* in, size_t stride, uint32_t
     DeviceGuard g (h->device);
     const size_t nch = (size_t)2 * h->n_inst;
     if (h->stage.ensure (nch, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
-    B200M_CUDA (cudaMemcpy2DAsync (h->stage.d, h->stage.cap * sizeof (float), in, stride * sizeof (float),
-                                   (size_t)nfram * sizeof (float), nch, cudaMemcpyHostToDevice, h->own));
+    // the staging buffer is single: the next copy may only start when the previous cycle's kernels have read it
+    if (h->last_host) B200M_CUDA (cudaStreamWaitEvent (h->copy, h->ev_done, 0));
+    const int nsl = h->n_inst >= 64 ? R128_SLICES : 1;
+    for (int s = 0; s < nsl; ++s) {
+        const size_t r0 = 2 * ((uint64_t)h->n_inst * s / nsl), r1 = 2 * ((uint64_t)h->n_inst * (s + 1) / nsl);
+        B200M_CUDA (cudaMemcpy2DAsync (h->stage.d + r0 * h->stage.cap, h->stage.cap * sizeof (float), in + r0 * stride, stride * sizeof (float),
+                                       (size_t)nfram * sizeof (float), r1 - r0, cudaMemcpyHostToDevice, h->copy));
+        B200M_CUDA (cudaEventRecord (h->ev_ready[s], h->copy));
+    }
     h->last_host = true;
-    return r128_run (h, h->stage.d, h->stage.cap, nfram, h->own);
+    if (int rc = r128_run (h, h->stage.d, h->stage.cap, nfram, h->own, nsl, h->ev_ready)) return rc;
+    B200M_CUDA (cudaEventRecord (h->ev_done, h->own));
+    return 0;
 }
 
 int b200m_r128_results (b200m_r128* h, b200m_ebu_result* ebu_out, float* tp_max_db, void* stream)

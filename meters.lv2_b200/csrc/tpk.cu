@@ -63,9 +63,10 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
 // instructions it would with one channel per lane.
 template <int CH, int TC, bool TP, bool TPMAX, bool KM>
 __global__ void __launch_bounds__ (TPK_THREADS)
-tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
+tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
             float* __restrict__ dbg)
 {
+    // processes channels [c_first, n_chan): `n_chan` is the END of the slice (absolute channel index)
     constexpr int XP = 48 + TC + 4;               // x row pitch (floats): 16-byte multiple
     constexpr int OP = 4 * TC + 4;                // |out| row pitch
     constexpr int GPC = TC / 4;                   // 4-sample groups per channel per chunk
@@ -76,7 +77,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, 
     __shared__ __align__ (16) float ob[BAL ? CH : 1][BAL ? OP : 4];
     __shared__ float smax[CH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = blockIdx.x * CH;
+    const int c0 = c_first + blockIdx.x * CH;
     const int nchunks = (nfram + TC - 1) / TC;
 
     auto load_chunk = [&] (int c, int buf) {
@@ -174,10 +175,12 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, 
                                 for (int ph = 0; ph < 4; ++ph) { const float v = fabsf (o[4 * i + ph]); if (v > vmax) vmax = v; }
                             }
                     } else {
-                        float4* d = reinterpret_cast<float4*> (&ob[BAL ? r : 0][BAL ? 16 * q : 0]);
+                        // the 4 outputs of input sample 4q+i live at float4 slot i*GPC + q: consecutive lanes (q) store
+                        // consecutive float4 -> conflict-free STS.128; the ballistics lane un-swizzles when it reads
+                        float4* d = reinterpret_cast<float4*> (&ob[BAL ? r : 0][0]);
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            d[i] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
+                            d[BAL ? i * GPC + q : 0] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
                     }
                 }
                 if (TPMAX) {
@@ -197,7 +200,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, 
             // two attack filters of channel tch
             const float4* b4 = reinterpret_cast<const float4*> (&ob[BAL ? tch : 0][0]);
             for (int j = 0; j < len; ++j) {
-                const float4 v4 = b4[j];
+                const float4 v4 = b4[(j & 3) * GPC + (j >> 2)];
                 z = __fmul_rn (z, prm.w3);
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
@@ -345,7 +348,10 @@ void tpk_raw_pointers (b200m_tpk* h, float** tp_m, int** tp_res) { *tp_m = h->st
 
 static cudaStream_t tpk_stream (b200m_tpk* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
 
-static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st)
+// process()/process_max() of every meter; channel slices [bounds[s], bounds[s+1]) are launched separately, slice s
+// after event ready[s] when `ready` is given (see ebu_process_sliced).
+int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st,
+                        int nsl, const uint32_t* bounds, cudaEvent_t* ready)
 {
     const bool tp = h->flags & B200M_TPK_TRUEPEAK, km = h->flags & B200M_TPK_KMETER;
     TpkParams prm = h->prm;
@@ -353,14 +359,25 @@ static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
     prm.fall = powf (10.0f, -0.05f * 15.0f * ((float)(int)nfram / h->fsamp));
     const int aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
     dim3 blk (TPK_THREADS);
-#define TPK_GO(CH, TC, TP, MX, KM) tpk_kernel<CH, TC, TP, MX, KM><<<(h->n_chan + CH - 1) / CH, blk, 0, st>>> (d_in, stride, (int)h->n_chan, (int)nfram, aligned, prm, h->st, h->d_dbg)
-    if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 128, true, true, true); else TPK_GO (8, 128, true, true, false); }
-    else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
-    else TPK_GO (16, 64, false, false, true);
+    for (int sl = 0; sl < nsl; ++sl) {
+        const int cf = (int)bounds[sl], ce = (int)bounds[sl + 1];
+        if (ce <= cf) continue;
+        if (ready) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
+#define TPK_GO(CH, TC, TP, MX, KM) tpk_kernel<CH, TC, TP, MX, KM><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg)
+        if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 128, true, true, true); else TPK_GO (8, 128, true, true, false); }
+        else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
+        else TPK_GO (16, 64, false, false, true);
 #undef TPK_GO
-    B200M_LAUNCHED (1);
+        B200M_LAUNCHED (1);
+    }
     B200M_CUDA (cudaGetLastError ());
     return 0;
+}
+
+static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st)
+{
+    const uint32_t bounds[2] = {0, h->n_chan};
+    return tpk_process_sliced (h, d_in, stride, nfram, tp_mode, st, 1, bounds, nullptr);
 }
 
 extern "C" {
