@@ -57,7 +57,8 @@ int         b200m_host_free (void* p);
 uint64_t    b200m_launch_count (void);
 
 /* ALU ceilings measured on the device (the driver's MEASURED_PEAKS.json has only HBM and bf16 GEMM):
- * kind 0 = fp32 unfused FMUL+FADD issue rate, kind 1 = fp64 DMUL+DADD; result in 1e9 lane-operations/s. */
+ * kind 0 = fp32 unfused FMUL+FADD issue rate, kind 1 = fp64 DMUL+DADD, kind 2 = packed fp32x2 FMUL2+FADD2;
+ * result in 1e9 lane-operations/s. */
 int         b200m_peak_probe (int device, int kind, double* gops);
 
 /* Host-side coefficient design, callable without a GPU (pure functions of the sample rate, computed with
@@ -156,6 +157,8 @@ int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float
 /* the raw 4x oversampled stream of the LAST processed block of one channel (4*nfram floats),
  * only kept when enabled with b200m_tpk_debug_capture(h,1): FIR bit-exactness tests */
 int b200m_tpk_debug_capture (b200m_tpk* h, int enable);
+/* FIR instruction selection: 0 = scalar FMUL/FADD, 1 = packed fp32x2 FMUL2/FADD2 (same roundings, fewer issue slots) */
+int b200m_tpk_set_packed (b200m_tpk* h, int enable);
 int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t n_out, void* stream);
 
 /* ======================================================================================

@@ -5,6 +5,7 @@
 //   lm/mm/ls/ms/il/rn/rx getters;  tp = coef_to_db (max (mtr[0]->read (), mtr[1]->read ()));  tp_max = max (tp_max, tp)
 // It composes the EBU bank (ebu.cu) and the true-peak bank (tpk.cu) over ONE host->device copy of the block.
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200m {
@@ -43,21 +44,24 @@ struct b200m_r128 {
     // kernel);  copy: host->device slices, so that the copy of slice s+1 overlaps the kernels of slice s
     cudaStream_t own = nullptr, side = nullptr, copy = nullptr;
     cudaEvent_t ev_in = nullptr, ev_tp = nullptr, ev_done = nullptr, ev_ready[R128_SLICES] = {nullptr};
-    HostStage stage; bool last_host = false;
+    HostStage stage; bool last_host = false; int concurrent = 1, slices = R128_SLICES;
 };
+
+static int env_int (const char* name, int dflt) { const char* v = getenv (name); return v ? atoi (v) : dflt; }
 
 static int r128_run (b200m_r128* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, cudaEvent_t* ready)
 {
     uint32_t bi[R128_SLICES + 1], bc[R128_SLICES + 1];
     for (int s = 0; s <= nsl; ++s) { bi[s] = (uint32_t)((uint64_t)h->n_inst * s / nsl); bc[s] = 2 * bi[s]; }
-    if (h->dbtp) {
-        if (!ready) { B200M_CUDA (cudaEventRecord (h->ev_in, st)); B200M_CUDA (cudaStreamWaitEvent (h->side, h->ev_in, 0)); }
-        if (int rc = tpk_process_sliced (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, h->side, nsl, bc, ready)) return rc;
-        B200M_CUDA (cudaEventRecord (h->ev_tp, h->side));
-    }
+    // The EBU kernel is latency bound on 4 warps per SM; launched FIRST it leaves most of every SM to the true-peak
+    // kernel, which then runs concurrently on the side stream (tuning knob: B200M_R128_CONCURRENT=0 serialises them).
+    const bool conc = h->dbtp && h->concurrent;
+    cudaStream_t tps = conc ? h->side : st;
+    if (conc && !ready) { B200M_CUDA (cudaEventRecord (h->ev_in, st)); B200M_CUDA (cudaStreamWaitEvent (h->side, h->ev_in, 0)); }
     if (int rc = ebu_process_sliced (h->ebu, d_in, stride, nfram, st, nsl, bi, ready)) return rc;
     if (h->dbtp) {
-        B200M_CUDA (cudaStreamWaitEvent (st, h->ev_tp, 0));
+        if (int rc = tpk_process_sliced (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, tps, nsl, bc, conc ? ready : nullptr)) return rc;
+        if (conc) { B200M_CUDA (cudaEventRecord (h->ev_tp, h->side)); B200M_CUDA (cudaStreamWaitEvent (st, h->ev_tp, 0)); }
         float* tp_m; int* tp_res;
         tpk_raw_pointers (h->tpk, &tp_m, &tp_res);
         r128_tp_kernel<<<(h->n_inst + 255) / 256, 256, 0, st>>> ((int)h->n_inst, tp_m, tp_res, h->d_tpmax);
@@ -79,6 +83,10 @@ int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsam
     b200m_r128* h = new (std::nothrow) b200m_r128;
     if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
     h->device = device; h->n_inst = n_inst; h->dbtp = dbtp_enable ? 1 : 0;
+    h->concurrent = env_int ("B200M_R128_CONCURRENT", 1);
+    h->slices = env_int ("B200M_R128_SLICES", R128_SLICES);
+    if (h->slices < 1) h->slices = 1;
+    if (h->slices > R128_SLICES) h->slices = R128_SLICES;
     int rc = b200m_ebu_create (&h->ebu, device, n_inst, 2, fsamp);                 // ebu->init (2, rate), src/ebulv2.cc:190
     if (!rc) rc = b200m_tpk_create (&h->tpk, device, 2 * n_inst, fsamp, B200M_TPK_TRUEPEAK);   // 2 x TruePeakdsp, :192-196
     if (!rc) {
@@ -141,7 +149,7 @@ int b200m_r128_run_host (b200m_r128* h, const float* in, size_t stride, uint32_t
     if (h->stage.ensure (nch, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
     // the staging buffer is single: the next copy may only start when the previous cycle's kernels have read it
     if (h->last_host) B200M_CUDA (cudaStreamWaitEvent (h->copy, h->ev_done, 0));
-    const int nsl = h->n_inst >= 64 ? R128_SLICES : 1;
+    const int nsl = h->n_inst >= 64 ? h->slices : 1;
     for (int s = 0; s < nsl; ++s) {
         const size_t r0 = 2 * ((uint64_t)h->n_inst * s / nsl), r1 = 2 * ((uint64_t)h->n_inst * (s + 1) / nsl);
         B200M_CUDA (cudaMemcpy2DAsync (h->stage.d + r0 * h->stage.cap, h->stage.cap * sizeof (float), in + r0 * stride, stride * sizeof (float),
