@@ -157,8 +157,6 @@ int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float
 /* the raw 4x oversampled stream of the LAST processed block of one channel (4*nfram floats),
  * only kept when enabled with b200m_tpk_debug_capture(h,1): FIR bit-exactness tests */
 int b200m_tpk_debug_capture (b200m_tpk* h, int enable);
-/* FIR instruction selection: 0 = scalar FMUL/FADD, 1 = packed fp32x2 FMUL2/FADD2 (same roundings, fewer issue slots) */
-int b200m_tpk_set_packed (b200m_tpk* h, int enable);
 int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t n_out, void* stream);
 
 /* ======================================================================================

@@ -73,7 +73,6 @@ _PROTOS = {
     "b200m_tpk_coeffs": (C.c_int, [_v, _v, _v, _v]),
     "b200m_tpk_state": (C.c_int, [_v, _v, _v, _v, _v, _v, _v, _v]),
     "b200m_tpk_debug_capture": (C.c_int, [_v, C.c_int]),
-    "b200m_tpk_set_packed": (C.c_int, [_v, C.c_int]),
     "b200m_tpk_debug_upsampled": (C.c_int, [_v, C.c_uint32, _v, C.c_uint32, _v]),
     # EBUr128 plugin cycle
     "b200m_r128_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_float, C.c_int]),
@@ -355,9 +354,6 @@ class TruePeakKmeter(_Bank):
         res = np.empty(n, np.int32); km = np.empty((n, 8), np.float32)
         _ck(lib().b200m_tpk_state(self.h, _np_ptr(m), _np_ptr(p), _np_ptr(z1), _np_ptr(z2), _np_ptr(res), _np_ptr(km), _stream_ptr(stream)))
         return dict(m=m, p=p, z1=z1, z2=z2, res=res, km=km)
-
-    def set_packed(self, enable=True):
-        _ck(lib().b200m_tpk_set_packed(self.h, int(enable)))
 
     def debug_capture(self, enable=True):
         _ck(lib().b200m_tpk_debug_capture(self.h, int(enable)))

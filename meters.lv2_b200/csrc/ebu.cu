@@ -288,11 +288,14 @@ ebu_fragment_kernel (int n_inst, int frag, int wrind, const float* __restrict__ 
     const int tid = threadIdx.x;
     const int i = blockIdx.x * K2A_THREADS + tid;
     if (i >= n_inst) return;
-#pragma unroll 8
-    for (int w = 0; w < 64; ++w) sring[w][tid] = ring[(size_t)w * n_inst + i];
+    // all 64 ring slots in flight at once (one round of memory latency, not 64): cp.async straight into the column
+#pragma unroll
+    for (int w = 0; w < 64; ++w) cp_async4 (&sring[w][tid], ring + (size_t)w * n_inst + i, 4);
+    cp_async_commit ();
     EbuCtl c = ctl[i];
     b200m_ebu_result r = res[i];
     const float p = fragpw[(size_t)frag * n_inst + i];
+    cp_async_wait<0> ();
     sring[wrind][tid] = p;                                 // _power[_wrind++] = _frpwr / _fragm (:218)
     ring[(size_t)wrind * n_inst + i] = p;
     const int wr = (wrind + 1) & 63;

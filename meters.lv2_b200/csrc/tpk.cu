@@ -56,57 +56,18 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
     for (int a = 0; a < 16; ++a) o[a] = __fsub_rn (acc[a], 1e-20f);
 }
 
-// ---- packed variant: Blackwell FMUL2 / FADD2 (fp32x2) -------------------------------------------------------
-// The FIR is bound by instruction ISSUE (ncu: 96 % of issue slots busy, fma pipe 85 %), so the same 384 roundings per
-// sample are issued as fewer instructions: products two phases at a time with mul.rn.f32x2 on a duplicated sample
-// (w, w) x (c[ph], c[ph+1]), the pair-sum as scalar add.rn.f32 (ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into
-// FFMA2 although it never contracts the scalar .rn forms, so the add that consumes a product must stay scalar), and
-// the accumulation two phases at a time with add.rn.f32x2 (safe: its operands are sums, not products).  Every
-// operation rounds exactly as in fir16; tests compare both variants bit for bit with zita-resampler.
-__constant__ float2 c_tp_tab2[24][4];       // [i] -> {c1[0],c1[1]}, {c1[2],c1[3]}, {c2[0],c2[1]}, {c2[2],c2[3]}
-
-B200M_DEV unsigned long long pk2 (float lo, float hi) { unsigned long long r; asm ("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-B200M_DEV void upk2 (unsigned long long v, float& lo, float& hi) { asm ("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-B200M_DEV unsigned long long mul2 (unsigned long long a, unsigned long long b) { unsigned long long r; asm ("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-B200M_DEV unsigned long long add2 (unsigned long long a, unsigned long long b) { unsigned long long r; asm ("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-
-B200M_DEV void fir16_packed (const float (&w)[52], float (&o)[16])
-{
-    unsigned long long acc[8];                      // [r][phase pair]
-    const unsigned long long bias = pk2 (1e-20f, 1e-20f);
-#pragma unroll
-    for (int a = 0; a < 8; ++a) acc[a] = bias;
-#pragma unroll
-    for (int i = 0; i < 24; ++i) {
-        const unsigned long long cA01 = *reinterpret_cast<const unsigned long long*> (&c_tp_tab2[i][0]);
-        const unsigned long long cA23 = *reinterpret_cast<const unsigned long long*> (&c_tp_tab2[i][1]);
-        const unsigned long long cB01 = *reinterpret_cast<const unsigned long long*> (&c_tp_tab2[i][2]);
-        const unsigned long long cB23 = *reinterpret_cast<const unsigned long long*> (&c_tp_tab2[i][3]);
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const unsigned long long wa = pk2 (w[r + i + 1], w[r + i + 1]), wb = pk2 (w[r + 48 - i], w[r + 48 - i]);
-            float a0, a1, a2, a3, b0, b1, b2, b3;
-            upk2 (mul2 (wa, cA01), a0, a1); upk2 (mul2 (wa, cA23), a2, a3);
-            upk2 (mul2 (wb, cB01), b0, b1); upk2 (mul2 (wb, cB23), b2, b3);
-            acc[2 * r]     = add2 (acc[2 * r],     pk2 (__fadd_rn (a0, b0), __fadd_rn (a1, b1)));
-            acc[2 * r + 1] = add2 (acc[2 * r + 1], pk2 (__fadd_rn (a2, b2), __fadd_rn (a3, b3)));
-        }
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r) {
-        float v0, v1, v2, v3;
-        upk2 (acc[2 * r], v0, v1); upk2 (acc[2 * r + 1], v2, v3);
-        o[4 * r] = __fsub_rn (v0, 1e-20f); o[4 * r + 1] = __fsub_rn (v1, 1e-20f);
-        o[4 * r + 2] = __fsub_rn (v2, 1e-20f); o[4 * r + 3] = __fsub_rn (v3, 1e-20f);
-    }
-}
+// Note on Blackwell's packed fp32x2 instructions (FMUL2 / FADD2): tried and dropped.  b200m_peak_probe(2) measures
+// 37.1 T lane-ops/s against 36.2 T for scalar FMUL+FADD, i.e. a packed instruction occupies the fma pipe for two
+// issue cycles, so halving the instruction count buys nothing for this pipe-bound loop (measured 224 us vs 212 us);
+// and ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (it never contracts the scalar .rn forms), which
+// breaks the reference's rounding sequence.
 
 // Tile geometry: CH channels x TC input samples per chunk.  process_max (no serial true-peak lane) uses
 // <8,128>: smallest tiles, best balance over 148 SMs.  process() uses <16,64>: the ballistics warp then runs
 // 16 channels x {z1 filter, z2 filter} = 32 busy lanes (the two one-pole attack filters are independent until
 // the per-sample m = max (m, z1 + z2), which costs one shuffle), so the serial part issues ~1/4 of the
 // instructions it would with one channel per lane.
-template <int CH, int TC, bool TP, bool TPMAX, bool KM, bool PACKED>
+template <int CH, int TC, bool TP, bool TPMAX, bool KM>
 __global__ void __launch_bounds__ (TPK_THREADS)
 tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
             float* __restrict__ dbg)
@@ -205,7 +166,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
 #pragma unroll
                     for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
                     float o[16];
-                    if (PACKED) fir16_packed (w, o); else fir16 (w, o);
+                    fir16 (w, o);
                     if (dbg && (c0 + r) < n_chan) {
                         float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
 #pragma unroll
@@ -352,7 +313,7 @@ using namespace b200m;
 struct b200m_tpk {
     int device; uint32_t n_chan, flags; float fsamp;
     TpkParams prm; float ctab[120];
-    TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr; int packed = 0;
+    TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 
@@ -408,11 +369,10 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
         const int cf = (int)bounds[sl], ce = (int)bounds[sl + 1];
         if (ce <= cf) continue;
         if (ready) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
-#define TPK_GO(CH, TC, TP, MX, KM) do { if (h->packed) tpk_kernel<CH, TC, TP, MX, KM, true><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg); \
-                                        else tpk_kernel<CH, TC, TP, MX, KM, false><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg); } while (0)
+#define TPK_GO(CH, TC, TP, MX, KM) tpk_kernel<CH, TC, TP, MX, KM><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg)
         if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 128, true, true, true); else TPK_GO (8, 128, true, true, false); }
         else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
-        else tpk_kernel<16, 64, false, false, true, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg);
+        else TPK_GO (16, 64, false, false, true);
 #undef TPK_GO
         B200M_LAUNCHED (1);
     }
@@ -451,16 +411,6 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     h->device = device; h->n_chan = n_chan; h->flags = flags; h->fsamp = fsamp;
     tpk_design (fsamp, h->prm, h->ctab);
     cudaError_t e = cudaMemcpyToSymbol (c_tp_tab, h->ctab, sizeof (h->ctab));
-    {
-        float2 t2[24][4];
-        for (int i = 0; i < 24; ++i) {
-            t2[i][0] = make_float2 (h->ctab[i], h->ctab[24 + i]);            // c1[ph] = ctab + 24 ph
-            t2[i][1] = make_float2 (h->ctab[48 + i], h->ctab[72 + i]);
-            t2[i][2] = make_float2 (h->ctab[96 + i], h->ctab[72 + i]);       // c2[ph] = ctab + 24 (4 - ph)
-            t2[i][3] = make_float2 (h->ctab[48 + i], h->ctab[24 + i]);
-        }
-        if (e == cudaSuccess) e = cudaMemcpyToSymbol (c_tp_tab2, t2, sizeof (t2));
-    }
     auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
     const size_t n = n_chan;
     A ((void**)&h->st.hist, n * 48 * sizeof (float));
@@ -581,13 +531,6 @@ int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float
         free (tmp);
     }
     B200M_CUDA (cudaStreamSynchronize (st));
-    return 0;
-}
-
-int b200m_tpk_set_packed (b200m_tpk* h, int enable)
-{
-    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
-    h->packed = enable ? 1 : 0;
     return 0;
 }
 

@@ -41,7 +41,7 @@ def host_ms(bank, k=30):
 
 
 for conc in (0, 1):
-    for sl in (1, 2, 4):
+    for sl in (1, 2, 4, 8):
         os.environ["B200M_R128_CONCURRENT"] = str(conc); os.environ["B200M_R128_SLICES"] = str(sl)
         b = B.EBUr128(N, 48000.0, True); b.control(B.EBUr128.START)
         d = dev_ms(b) if sl == 1 else float("nan")
@@ -63,23 +63,3 @@ for _ in range(20):
 torch.cuda.synchronize()
 print("torch pinned H2D contiguous 64 MiB: %.3f ms per block" % ((time.perf_counter() - t0) / 20 * 1e3))
 
-# scalar vs packed FIR
-for packed in (0, 1):
-    t = B.TruePeakKmeter(2 * N, flags=B.TPK_TRUEPEAK); t.set_packed(packed)
-    for s in range(5):
-        t.process_ptr(base + 4 * NF * (s % RING), stride, NF, B.TP_MODE_MAX)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(40):
-        t.process_ptr(base + 4 * NF * (s % RING), stride, NF, B.TP_MODE_MAX)
-    e1.record(); torch.cuda.synchronize()
-    print("FIR process_max packed=%d : %.4f ms/block" % (packed, e0.elapsed_time(e1) / 40))
-    t2 = B.TruePeakKmeter(2 * N); t2.set_packed(packed)
-    for s in range(5):
-        t2.process_ptr(base + 4 * NF * (s % RING), stride, NF)
-    torch.cuda.synchronize(); e0.record()
-    for s in range(40):
-        t2.process_ptr(base + 4 * NF * (s % RING), stride, NF); t2.read_device()
-    e1.record(); torch.cuda.synchronize()
-    print("TP+K20 process packed=%d : %.4f ms/block" % (packed, e0.elapsed_time(e1) / 40))
