@@ -63,3 +63,35 @@ for _ in range(20):
 torch.cuda.synchronize()
 print("torch pinned H2D contiguous 64 MiB: %.3f ms per block" % ((time.perf_counter() - t0) / 20 * 1e3))
 
+
+# true-peak kernels: process_max (FIR only) and process + K-meter (lock-step vs warp-specialised pipeline)
+def tp_ms(bank, mode, read, k=40):
+    for s in range(5):
+        bank.process_ptr(base + 4 * NF * (s % RING), stride, NF, mode)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(k):
+        bank.process_ptr(base + 4 * NF * (s % RING), stride, NF, mode)
+        if read:
+            bank.read_device()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / k
+
+
+t = B.TruePeakKmeter(2 * N, flags=B.TPK_TRUEPEAK)
+print("FIR process_max : %.4f ms/block" % tp_ms(t, B.TP_MODE_MAX, False))
+for pipe in (0, 1):
+    os.environ["B200M_TPK_PIPELINE"] = str(pipe)
+    t2 = B.TruePeakKmeter(2 * N)
+    print("TP+K20 process pipeline=%d : %.4f ms/block" % (pipe, tp_ms(t2, B.TP_MODE_PROCESS, True)))
+e = B.Ebu_r128_proc(N, 2); e.integr_start()
+for s in range(300):
+    e.process_ptr(base + 4 * NF * (s % RING), stride, NF)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for s in range(117):
+    e.process_ptr(base + 4 * NF * (s % RING), stride, NF)
+e1.record(); torch.cuda.synchronize()
+print("EBU R128 only : %.4f ms/block" % (e0.elapsed_time(e1) / 117))
