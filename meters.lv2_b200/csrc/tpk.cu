@@ -288,191 +288,11 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     }
 }
 
-// ---- warp-specialised pipeline for process() (true-peak ballistics, optional K-meter) ------------------------
-// ncu on tpk_kernel<16,64,TP,proc,KM>: fp32 issue 82 %, `barrier` stall 4 cycles per instruction — the FIR warps wait
-// at __syncthreads while one warp walks the serial ballistics.  Here the roles are decoupled: four FIR warps and the
-// K-meter warp advance chunk by chunk in lock step (named barrier 1), the ballistics warp runs one chunk behind on a
-// double-buffered |out| tile handed over with full/empty named barriers (ids 2..5), so the serial chain (≈52 cycles per
-// input sample) hides under the FIR of the next chunk instead of stalling it.
-constexpr int PIPE_CH = 16, PIPE_TC = 64, PIPE_FIRW = 4;
-constexpr int PIPE_GROUP = (PIPE_FIRW + 1) * 32;       // FIR warps + K-meter warp
-constexpr int PIPE_THREADS = PIPE_GROUP + 32;          // + ballistics warp
-
-B200M_DEV void nbar_sync (int id, int n) { asm volatile ("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-B200M_DEV void nbar_arrive (int id, int n) { asm volatile ("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-
-template <bool KM>
-__global__ void __launch_bounds__ (PIPE_THREADS, 4)
-tpk_pipe_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
-                 float* __restrict__ dbg)
-{
-    constexpr int CH = PIPE_CH, TC = PIPE_TC, XP = 48 + TC + 4, OP = 4 * TC + 4, GPC = TC / 4;
-    __shared__ __align__ (16) float xs[2][CH][XP];
-    __shared__ __align__ (16) float ob[2][CH][OP];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = c_first + blockIdx.x * CH;
-    const int nchunks = (nfram + TC - 1) / TC;
-
-    if (warp == PIPE_FIRW + 1) {
-        // ===== ballistics warp: lane = filter * 16 + channel (truepeakdsp.cc:52-97) =====
-        const int tch = lane & 15, filt = lane >> 4;
-        const int chs = min (c0 + tch, n_chan - 1);
-        const bool live = (c0 + tch) < n_chan;
-        const int res = st.tp_res[chs];
-        float m = res ? 0.0f : st.tp_m[chs], p = res ? 0.0f : st.tp_p[chs];
-        const float a = filt ? st.tp_z2[chs] : st.tp_z1[chs];
-        float z = a > 20 ? 20 : (a < 0 ? 0 : a);
-        const float wf = filt ? prm.w2 : prm.w1;
-        for (int c = 0; c < nchunks; ++c) {
-            const int b = c & 1, len = min (TC, nfram - c * TC);
-            nbar_sync (2 + b, PIPE_THREADS);                  // |out| tile of chunk c is complete
-            const float4* b4 = reinterpret_cast<const float4*> (&ob[b][tch][0]);
-            for (int j = 0; j < len; ++j) {
-                const float4 v4 = b4[(j & 3) * GPC + (j >> 2)];
-                z = __fmul_rn (z, prm.w3);
-                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float v = vv[i];
-                    if (v > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v, z)));
-                    if (v > p) p = v;
-                }
-                const float t = __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16));    // z1 + z2
-                if (t > m) m = t;
-            }
-            if (c + 2 < nchunks) nbar_arrive (4 + b, PIPE_THREADS);   // tile b may be overwritten by chunk c + 2
-        }
-        if (live) {
-            if (filt) st.tp_z2[chs] = __fadd_rn (z, 1e-20f);          // :86-87
-            else {
-                st.tp_z1[chs] = __fadd_rn (z, 1e-20f);
-                m = __fmul_rn (m, prm.g);                               // :89
-                if (res) { st.tp_m[chs] = m; st.tp_p[chs] = p; st.tp_res[chs] = 0; }
-                else {
-                    if (m > st.tp_m[chs]) st.tp_m[chs] = m;
-                    if (p > st.tp_p[chs]) st.tp_p[chs] = p;
-                }
-            }
-        }
-        return;
-    }
-
-    // ===== FIR group: warps 0..3 compute the oversampled stream, warp 4 runs the K-meter =====
-    auto load_chunk = [&] (int c, int buf) {
-        if (c < nchunks) {
-            const int s0 = c * TC;
-            if (aligned) {
-                for (int idx = tid; idx < CH * GPC; idx += PIPE_GROUP) {
-                    const int r = idx / GPC, c4 = (idx % GPC) * 4;
-                    const int ch = min (c0 + r, n_chan - 1);
-                    const int left = (nfram - (s0 + c4)) * 4;
-                    const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
-                    cp_async16 (&xs[buf][r][48 + c4], nb ? in + (size_t)ch * stride + s0 + c4 : in, nb);
-                }
-            } else {
-                for (int idx = tid; idx < CH * TC; idx += PIPE_GROUP) {
-                    const int r = idx / TC, cc = idx % TC;
-                    const int ch = min (c0 + r, n_chan - 1);
-                    const bool ok = (s0 + cc) < nfram;
-                    cp_async4 (&xs[buf][r][48 + cc], ok ? in + (size_t)ch * stride + s0 + cc : in, ok ? 4 : 0);
-                }
-            }
-        }
-        cp_async_commit ();
-    };
-    for (int idx = tid; idx < CH * 48; idx += PIPE_GROUP) {
-        const int r = idx / 48, j = idx % 48;
-        xs[0][r][j] = st.hist[(size_t)min (c0 + r, n_chan - 1) * 48 + j];
-    }
-    load_chunk (0, 0);
-
-    const bool is_km = KM && warp == PIPE_FIRW && lane < CH;
-    const int kch = min (c0 + lane, n_chan - 1);
-    float kz1 = 0, kz2 = 0, kt = 0;
-    if (is_km) {
-        const float a = st.km_z1[kch], b = st.km_z2[kch];                // kmeterdsp.cc:74-75
-        kz1 = a > 50 ? 50 : (a < 0 ? 0 : a);
-        kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
-    }
-    const int km_n = (nfram / 4) * 4;
-
-    for (int c = 0; c < nchunks; ++c) {
-        const int buf = c & 1, s0 = c * TC, len = min (TC, nfram - s0);
-        cp_async_wait<0> ();
-        nbar_sync (1, PIPE_GROUP);                          // chunk c (with its 48-sample prefix) is in xs[buf]
-        for (int idx = tid; idx < CH * 48; idx += PIPE_GROUP) {
-            const int r = idx / 48, j = idx % 48;
-            xs[buf ^ 1][r][j] = xs[buf][r][len + j];
-        }
-        load_chunk (c + 1, buf ^ 1);
-        if (c >= 2) nbar_sync (4 + buf, PIPE_THREADS);      // ballistics is done with the tile written two chunks ago
-        if (warp < PIPE_FIRW) {
-#pragma unroll 1
-            for (int item = tid; item < CH * GPC; item += PIPE_FIRW * 32) {
-                const int r = item / GPC, q = item % GPC;
-                if (4 * q < len) {
-                    float w[52];
-                    const float4* xr = reinterpret_cast<const float4*> (&xs[buf][r][4 * q]);
-#pragma unroll
-                    for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-                    float o[16];
-                    fir16 (w, o);
-                    if (dbg && (c0 + r) < n_chan) {
-                        float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) d[i] = make_float4 (o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
-                    }
-                    float4* d = reinterpret_cast<float4*> (&ob[buf][r][0]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        d[i * GPC + q] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
-                }
-            }
-        } else if (is_km) {
-            const int e = min (len, km_n - s0);                           // kmeterdsp.cc:79-97
-            const float4* x4 = reinterpret_cast<const float4*> (&xs[buf][lane][48]);
-            const float om4 = __fmul_rn (4.0f, prm.omega);
-            for (int j = 0; j + 4 <= e; j += 4) {
-                const float4 v4 = x4[j >> 2];
-                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float s = __fmul_rn (vv[i], vv[i]);
-                    if (kt < s) kt = s;
-                    kz1 = __fadd_rn (kz1, __fmul_rn (prm.omega, __fsub_rn (s, kz1)));
-                }
-                kz2 = __fadd_rn (kz2, __fmul_rn (om4, __fsub_rn (kz1, kz2)));
-            }
-        }
-        nbar_arrive (2 + buf, PIPE_THREADS);                // hand the |out| tile of chunk c to the ballistics warp
-    }
-    cp_async_wait<0> ();
-    nbar_sync (1, PIPE_GROUP);                              // last prefix copy complete
-    {
-        const int hb = nchunks & 1;
-        for (int idx = tid; idx < CH * 48; idx += PIPE_GROUP) {
-            const int r = idx / 48, j = idx % 48;
-            if (c0 + r < n_chan) st.hist[(size_t)(c0 + r) * 48 + j] = xs[hb][r][j];
-        }
-    }
-    if (is_km && (c0 + lane) < n_chan) {
-        if (isnan (kz1)) kz1 = 0;                           // :101-103
-        if (isnan (kz2)) kz2 = 0;
-        if (!finitef_ (kt)) kt = 0;
-        st.km_z1[kch] = __fadd_rn (kz1, 1e-20f);
-        st.km_z2[kch] = __fadd_rn (kz2, 1e-20f);
-        const float s = __fsqrt_rn (__fmul_rn (2.0f, kz2));
-        const float t = __fsqrt_rn (kt);
-        if (st.km_flag[kch]) { st.km_rms[kch] = s; st.km_flag[kch] = 0; }
-        else if (s > st.km_rms[kch]) st.km_rms[kch] = s;
-        float pk = st.km_peak[kch]; int cnt = st.km_cnt[kch];
-        if (t >= pk) { pk = t; cnt = prm.hold; }            // :125-139
-        else if (cnt > 0) cnt -= nfram;
-        else { pk = __fmul_rn (pk, prm.fall); pk = __fadd_rn (pk, 1e-10f); }
-        st.km_peak[kch] = pk; st.km_cnt[kch] = cnt;
-        st.km_fall[kch] = prm.fall; st.km_fpp[kch] = nfram;
-    }
-}
+// Tried and dropped (round 1): a warp-specialised pipeline for process() — four FIR warps + a K-meter warp in lock
+// step, the ballistics warp one chunk behind on a double-buffered |out| tile with full/empty named barriers.  It was
+// bit-exact but slower (372 us vs 286 us per 16384 x 1024 block): 48 KB of shared memory and 80 registers x 192 threads
+// cut residency to 4 CTAs/SM (1.73 waves), and three role bodies (26 KB FIR + ballistics + K-meter) overflow the 32 KB
+// instruction cache (ncu: no_instruction 0.45, barrier 2.8 cycles per issued instruction, fma pipe 60 %).
 
 __global__ void tpk_read_kernel (int n_chan, uint32_t flags, TpkState st, b200m_tpk_result* __restrict__ out)
 {
@@ -501,7 +321,6 @@ struct b200m_tpk {
     int device; uint32_t n_chan, flags; float fsamp;
     TpkParams prm; float ctab[120];
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
-    int pipeline = 1;                       // process(): warp-specialised pipeline (B200M_TPK_PIPELINE=0 selects the lock-step kernel)
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 
@@ -559,11 +378,6 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
         if (ready) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
 #define TPK_GO(CH, TC, TP, MX, KM) tpk_kernel<CH, TC, TP, MX, KM><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg)
         if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true); else TPK_GO (8, 256, true, true, false); }
-        else if (tp && h->pipeline) {
-            const int grid = (ce - cf + PIPE_CH - 1) / PIPE_CH;
-            if (km) tpk_pipe_kernel<true><<<grid, PIPE_THREADS, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg);
-            else    tpk_pipe_kernel<false><<<grid, PIPE_THREADS, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg);
-        }
         else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
         else TPK_GO (16, 64, false, false, true);
 #undef TPK_GO
@@ -602,7 +416,6 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     b200m_tpk* h = new (std::nothrow) b200m_tpk;
     if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
     h->device = device; h->n_chan = n_chan; h->flags = flags; h->fsamp = fsamp;
-    if (const char* v = getenv ("B200M_TPK_PIPELINE")) h->pipeline = atoi (v);
     tpk_design (fsamp, h->prm, h->ctab);
     cudaError_t e = cudaMemcpyToSymbol (c_tp_tab, h->ctab, sizeof (h->ctab));
     auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };

@@ -81,10 +81,8 @@ def tp_ms(bank, mode, read, k=40):
 
 t = B.TruePeakKmeter(2 * N, flags=B.TPK_TRUEPEAK)
 print("FIR process_max : %.4f ms/block" % tp_ms(t, B.TP_MODE_MAX, False))
-for pipe in (0, 1):
-    os.environ["B200M_TPK_PIPELINE"] = str(pipe)
-    t2 = B.TruePeakKmeter(2 * N)
-    print("TP+K20 process pipeline=%d : %.4f ms/block" % (pipe, tp_ms(t2, B.TP_MODE_PROCESS, True)))
+t2 = B.TruePeakKmeter(2 * N)
+print("TP+K20 process : %.4f ms/block" % tp_ms(t2, B.TP_MODE_PROCESS, True))
 e = B.Ebu_r128_proc(N, 2); e.integr_start()
 for s in range(300):
     e.process_ptr(base + 4 * NF * (s % RING), stride, NF)
