@@ -35,9 +35,143 @@ struct TpkState {                           // SoA, one entry per channel
     float *km_z1, *km_z2, *km_rms, *km_peak, *km_fall; int *km_cnt, *km_fpp, *km_flag;
 };
 
+// The zita table depends only on (hl = 24, np = 4, fr = 1.0), not on the sample rate, so its 120 floats are universal
+// constants.  They are restated here as literals (hex floats = the values libm produces for the formula in
+// zita_table() below): with the tap loops fully unrolled the literals become FMUL immediates, which removes the ~50
+// uniform constant loads per 16 outputs that the constant-bank form needs.  b200m_tpk_create compares the host-computed
+// table with these literals bit for bit and falls back to the constant-bank kernels if they ever differ.
+B200M_DEV float zita_lit (int i)
+{
+    switch (i) {
+    case 0: return 0x1.0e8cc60000000p-65f;
+    case 1: return -0x1.f4da040000000p-63f;
+    case 2: return -0x1.1ecee20000000p-64f;
+    case 3: return -0x1.9d9bde0000000p-62f;
+    case 4: return 0x1.f84c660000000p-60f;
+    case 5: return -0x1.5e4cb20000000p-60f;
+    case 6: return -0x1.9321ea0000000p-60f;
+    case 7: return -0x1.b534440000000p-59f;
+    case 8: return 0x1.d2d4d80000000p-57f;
+    case 9: return -0x1.bb55ce0000000p-58f;
+    case 10: return -0x1.6e155a0000000p-57f;
+    case 11: return -0x1.816e140000000p-57f;
+    case 12: return 0x1.b8ff340000000p-55f;
+    case 13: return -0x1.28f2680000000p-56f;
+    case 14: return 0x1.62bccc0000000p-56f;
+    case 15: return -0x1.9e31840000000p-56f;
+    case 16: return 0x1.d96a6a0000000p-56f;
+    case 17: return -0x1.092e9c0000000p-55f;
+    case 18: return 0x1.237b360000000p-55f;
+    case 19: return -0x1.3a9ac60000000p-55f;
+    case 20: return 0x1.4da4960000000p-55f;
+    case 21: return -0x1.5bd4640000000p-55f;
+    case 22: return 0x1.6495740000000p-55f;
+    case 23: return 0x1.0000000000000p+0f;
+    case 24: return -0x1.d0758c0000000p-20f;
+    case 25: return 0x1.74f3c80000000p-17f;
+    case 26: return -0x1.21b2780000000p-15f;
+    case 27: return 0x1.5cf90e0000000p-14f;
+    case 28: return -0x1.6c77cc0000000p-13f;
+    case 29: return 0x1.58b43e0000000p-12f;
+    case 30: return -0x1.2e2f240000000p-11f;
+    case 31: return 0x1.f29ba20000000p-11f;
+    case 32: return -0x1.87672e0000000p-10f;
+    case 33: return 0x1.26d2d00000000p-9f;
+    case 34: return -0x1.ad12540000000p-9f;
+    case 35: return 0x1.2f4f900000000p-8f;
+    case 36: return -0x1.a293f80000000p-8f;
+    case 37: return 0x1.1b24ca0000000p-7f;
+    case 38: return -0x1.7912360000000p-7f;
+    case 39: return 0x1.f0635e0000000p-7f;
+    case 40: return -0x1.447e240000000p-6f;
+    case 41: return 0x1.a7c41a0000000p-6f;
+    case 42: return -0x1.168e760000000p-5f;
+    case 43: return 0x1.7511480000000p-5f;
+    case 44: return -0x1.03d1200000000p-4f;
+    case 45: return 0x1.88e9740000000p-4f;
+    case 46: return -0x1.6c09600000000p-3f;
+    case 47: return 0x1.ccb95c0000000p-1f;
+    case 48: return -0x1.1c1fd00000000p-20f;
+    case 49: return 0x1.7106020000000p-17f;
+    case 50: return -0x1.3e6cae0000000p-15f;
+    case 51: return 0x1.927a360000000p-14f;
+    case 52: return -0x1.b144fc0000000p-13f;
+    case 53: return 0x1.a2f3160000000p-12f;
+    case 54: return -0x1.75b1180000000p-11f;
+    case 55: return 0x1.38a6c40000000p-10f;
+    case 56: return -0x1.f0902a0000000p-10f;
+    case 57: return 0x1.79a7c20000000p-9f;
+    case 58: return -0x1.1509ce0000000p-8f;
+    case 59: return 0x1.8a56220000000p-8f;
+    case 60: return -0x1.11a21c0000000p-7f;
+    case 61: return 0x1.73e48e0000000p-7f;
+    case 62: return -0x1.f1065a0000000p-7f;
+    case 63: return 0x1.47f5e80000000p-6f;
+    case 64: return -0x1.ad4f620000000p-6f;
+    case 65: return 0x1.183a9a0000000p-5f;
+    case 66: return -0x1.6f76720000000p-5f;
+    case 67: return 0x1.e924540000000p-5f;
+    case 68: return -0x1.50663a0000000p-4f;
+    case 69: return 0x1.ef2dda0000000p-4f;
+    case 70: return -0x1.aa96140000000p-3f;
+    case 71: return 0x1.4546e40000000p-1f;
+    case 72: return -0x1.89a1500000000p-23f;
+    case 73: return 0x1.5abb860000000p-18f;
+    case 74: return -0x1.57d15a0000000p-16f;
+    case 75: return 0x1.cbb6c20000000p-15f;
+    case 76: return -0x1.ffab940000000p-14f;
+    case 77: return 0x1.faa5820000000p-13f;
+    case 78: return -0x1.cc49100000000p-12f;
+    case 79: return 0x1.86d2e80000000p-11f;
+    case 80: return -0x1.3a24580000000p-10f;
+    case 81: return 0x1.e2abfe0000000p-10f;
+    case 82: return -0x1.65134e0000000p-9f;
+    case 83: return 0x1.ffdecc0000000p-9f;
+    case 84: return -0x1.654aee0000000p-8f;
+    case 85: return 0x1.e7f28c0000000p-8f;
+    case 86: return -0x1.474f580000000p-7f;
+    case 87: return 0x1.b124380000000p-7f;
+    case 88: return -0x1.1bf13a0000000p-6f;
+    case 89: return 0x1.72b7c40000000p-6f;
+    case 90: return -0x1.e52f3e0000000p-6f;
+    case 91: return 0x1.414ca20000000p-5f;
+    case 92: return -0x1.b5509c0000000p-5f;
+    case 93: return 0x1.3ad9d40000000p-4f;
+    case 94: return -0x1.00d0b60000000p-3f;
+    case 95: return 0x1.31e2140000000p-2f;
+    case 96: return -0x0.0p+0f;
+    case 97: return 0x1.0e8cc60000000p-65f;
+    case 98: return -0x1.f4da040000000p-63f;
+    case 99: return -0x1.1ecee20000000p-64f;
+    case 100: return -0x1.9d9bde0000000p-62f;
+    case 101: return 0x1.f84c660000000p-60f;
+    case 102: return -0x1.5e4cb20000000p-60f;
+    case 103: return -0x1.9321ea0000000p-60f;
+    case 104: return -0x1.b534440000000p-59f;
+    case 105: return 0x1.d2d4d80000000p-57f;
+    case 106: return -0x1.bb55ce0000000p-58f;
+    case 107: return -0x1.6e155a0000000p-57f;
+    case 108: return -0x1.816e140000000p-57f;
+    case 109: return 0x1.b8ff340000000p-55f;
+    case 110: return -0x1.28f2680000000p-56f;
+    case 111: return 0x1.62bccc0000000p-56f;
+    case 112: return -0x1.9e31840000000p-56f;
+    case 113: return 0x1.d96a6a0000000p-56f;
+    case 114: return -0x1.092e9c0000000p-55f;
+    case 115: return 0x1.237b360000000p-55f;
+    case 116: return -0x1.3a9ac60000000p-55f;
+    case 117: return 0x1.4da4960000000p-55f;
+    case 118: return -0x1.5bd4640000000p-55f;
+    case 119: return 0x1.6495740000000p-55f;
+    default: return 0.0f;
+    }
+}
+static const float h_zita_lit[120] = {0x1.0e8cc60000000p-65f, -0x1.f4da040000000p-63f, -0x1.1ecee20000000p-64f, -0x1.9d9bde0000000p-62f, 0x1.f84c660000000p-60f, -0x1.5e4cb20000000p-60f, -0x1.9321ea0000000p-60f, -0x1.b534440000000p-59f, 0x1.d2d4d80000000p-57f, -0x1.bb55ce0000000p-58f, -0x1.6e155a0000000p-57f, -0x1.816e140000000p-57f, 0x1.b8ff340000000p-55f, -0x1.28f2680000000p-56f, 0x1.62bccc0000000p-56f, -0x1.9e31840000000p-56f, 0x1.d96a6a0000000p-56f, -0x1.092e9c0000000p-55f, 0x1.237b360000000p-55f, -0x1.3a9ac60000000p-55f, 0x1.4da4960000000p-55f, -0x1.5bd4640000000p-55f, 0x1.6495740000000p-55f, 0x1.0000000000000p+0f, -0x1.d0758c0000000p-20f, 0x1.74f3c80000000p-17f, -0x1.21b2780000000p-15f, 0x1.5cf90e0000000p-14f, -0x1.6c77cc0000000p-13f, 0x1.58b43e0000000p-12f, -0x1.2e2f240000000p-11f, 0x1.f29ba20000000p-11f, -0x1.87672e0000000p-10f, 0x1.26d2d00000000p-9f, -0x1.ad12540000000p-9f, 0x1.2f4f900000000p-8f, -0x1.a293f80000000p-8f, 0x1.1b24ca0000000p-7f, -0x1.7912360000000p-7f, 0x1.f0635e0000000p-7f, -0x1.447e240000000p-6f, 0x1.a7c41a0000000p-6f, -0x1.168e760000000p-5f, 0x1.7511480000000p-5f, -0x1.03d1200000000p-4f, 0x1.88e9740000000p-4f, -0x1.6c09600000000p-3f, 0x1.ccb95c0000000p-1f, -0x1.1c1fd00000000p-20f, 0x1.7106020000000p-17f, -0x1.3e6cae0000000p-15f, 0x1.927a360000000p-14f, -0x1.b144fc0000000p-13f, 0x1.a2f3160000000p-12f, -0x1.75b1180000000p-11f, 0x1.38a6c40000000p-10f, -0x1.f0902a0000000p-10f, 0x1.79a7c20000000p-9f, -0x1.1509ce0000000p-8f, 0x1.8a56220000000p-8f, -0x1.11a21c0000000p-7f, 0x1.73e48e0000000p-7f, -0x1.f1065a0000000p-7f, 0x1.47f5e80000000p-6f, -0x1.ad4f620000000p-6f, 0x1.183a9a0000000p-5f, -0x1.6f76720000000p-5f, 0x1.e924540000000p-5f, -0x1.50663a0000000p-4f, 0x1.ef2dda0000000p-4f, -0x1.aa96140000000p-3f, 0x1.4546e40000000p-1f, -0x1.89a1500000000p-23f, 0x1.5abb860000000p-18f, -0x1.57d15a0000000p-16f, 0x1.cbb6c20000000p-15f, -0x1.ffab940000000p-14f, 0x1.faa5820000000p-13f, -0x1.cc49100000000p-12f, 0x1.86d2e80000000p-11f, -0x1.3a24580000000p-10f, 0x1.e2abfe0000000p-10f, -0x1.65134e0000000p-9f, 0x1.ffdecc0000000p-9f, -0x1.654aee0000000p-8f, 0x1.e7f28c0000000p-8f, -0x1.474f580000000p-7f, 0x1.b124380000000p-7f, -0x1.1bf13a0000000p-6f, 0x1.72b7c40000000p-6f, -0x1.e52f3e0000000p-6f, 0x1.414ca20000000p-5f, -0x1.b5509c0000000p-5f, 0x1.3ad9d40000000p-4f, -0x1.00d0b60000000p-3f, 0x1.31e2140000000p-2f, -0x0.0p+0f, 0x1.0e8cc60000000p-65f, -0x1.f4da040000000p-63f, -0x1.1ecee20000000p-64f, -0x1.9d9bde0000000p-62f, 0x1.f84c660000000p-60f, -0x1.5e4cb20000000p-60f, -0x1.9321ea0000000p-60f, -0x1.b534440000000p-59f, 0x1.d2d4d80000000p-57f, -0x1.bb55ce0000000p-58f, -0x1.6e155a0000000p-57f, -0x1.816e140000000p-57f, 0x1.b8ff340000000p-55f, -0x1.28f2680000000p-56f, 0x1.62bccc0000000p-56f, -0x1.9e31840000000p-56f, 0x1.d96a6a0000000p-56f, -0x1.092e9c0000000p-55f, 0x1.237b360000000p-55f, -0x1.3a9ac60000000p-55f, 0x1.4da4960000000p-55f, -0x1.5bd4640000000p-55f, 0x1.6495740000000p-55f};
+
 // 16 outputs (4 input positions x 4 phases) from a 52-sample window; w[j] = x[kb-48+j].
 // out[4k+ph] = (1e-20f + sum_i (x[k-47+i]*c1[i] + x[k-i]*c2[i])) - 1e-20f, pair-sum first, i ascending
 // (resampler.cc:213-230 with c1 = ctab + hl*ph, c2 = ctab + hl*(np-ph)).
+template <bool IMM>
 B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
 {
     float acc[16];
@@ -47,7 +181,8 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
     for (int i = 0; i < 24; ++i) {
 #pragma unroll
         for (int ph = 0; ph < 4; ++ph) {
-            const float c1 = c_tp_tab[24 * ph + i], c2 = c_tp_tab[24 * (4 - ph) + i];
+            const float c1 = IMM ? zita_lit (24 * ph + i) : c_tp_tab[24 * ph + i];
+            const float c2 = IMM ? zita_lit (24 * (4 - ph) + i) : c_tp_tab[24 * (4 - ph) + i];
 #pragma unroll
             for (int r = 0; r < 4; ++r)
                 acc[4 * r + ph] = __fadd_rn (acc[4 * r + ph], __fadd_rn (__fmul_rn (w[r + i + 1], c1), __fmul_rn (w[r + 48 - i], c2)));
@@ -68,7 +203,7 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
 // 16 channels x {z1 filter, z2 filter} = 32 busy lanes (the two one-pole attack filters are independent until
 // the per-sample m = max (m, z1 + z2), which costs one shuffle), so the serial part issues ~1/4 of the
 // instructions it would with one channel per lane.
-template <int CH, int TC, bool TP, bool TPMAX, bool KM>
+template <int CH, int TC, bool TP, bool TPMAX, bool KM, bool IMM>
 __global__ void __launch_bounds__ (TPK_THREADS)
 tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
             float* __restrict__ dbg)
@@ -167,7 +302,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
 #pragma unroll
                     for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
                     float o[16];
-                    fir16 (w, o);
+                    fir16<IMM> (w, o);
                     if (dbg && (c0 + r) < n_chan) {
                         float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
 #pragma unroll
@@ -321,6 +456,7 @@ struct b200m_tpk {
     int device; uint32_t n_chan, flags; float fsamp;
     TpkParams prm; float ctab[120];
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
+    int imm = 0;                            // host table == literal table: use the immediate-coefficient kernels
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 
@@ -376,10 +512,11 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
         const int cf = (int)bounds[sl], ce = (int)bounds[sl + 1];
         if (ce <= cf) continue;
         if (ready) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
-#define TPK_GO(CH, TC, TP, MX, KM) tpk_kernel<CH, TC, TP, MX, KM><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg)
+#define TPK_GO(CH, TC, TP, MX, KM) do { if (h->imm) tpk_kernel<CH, TC, TP, MX, KM, true><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg); \
+                                        else tpk_kernel<CH, TC, TP, MX, KM, false><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg); } while (0)
         if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true); else TPK_GO (8, 256, true, true, false); }
         else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
-        else TPK_GO (16, 64, false, false, true);
+        else tpk_kernel<16, 64, false, false, true, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg);
 #undef TPK_GO
         B200M_LAUNCHED (1);
     }
@@ -417,6 +554,8 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
     h->device = device; h->n_chan = n_chan; h->flags = flags; h->fsamp = fsamp;
     tpk_design (fsamp, h->prm, h->ctab);
+    h->imm = memcmp (h->ctab, h_zita_lit, sizeof (h->ctab)) == 0;
+    if (const char* v = getenv ("B200M_TPK_IMM")) h->imm = h->imm && atoi (v);
     cudaError_t e = cudaMemcpyToSymbol (c_tp_tab, h->ctab, sizeof (h->ctab));
     auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
     const size_t n = n_chan;
