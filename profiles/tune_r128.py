@@ -86,16 +86,13 @@ for imm in (0, 1):
     t2 = B.TruePeakKmeter(2 * N)
     print("TP+K20 process imm=%d : %.4f ms/block" % (imm, tp_ms(t2, B.TP_MODE_PROCESS, True)))
     del t, t2
-for unr in (2, 4, 8):
-    os.environ["B200M_EBU_UNROLL"] = str(unr)
-    e = B.Ebu_r128_proc(N, 2); e.integr_start()
-    for s in range(300):
-        e.process_ptr(base + 4 * NF * (s % RING), stride, NF)
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for s in range(117):
-        e.process_ptr(base + 4 * NF * (s % RING), stride, NF)
-    e1.record(); torch.cuda.synchronize()
-    print("EBU R128 only unroll=%d : %.4f ms/block" % (unr, e0.elapsed_time(e1) / 117))
-    del e
+e = B.Ebu_r128_proc(N, 2); e.integr_start()
+for s in range(300):
+    e.process_ptr(base + 4 * NF * (s % RING), stride, NF)
+torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for s in range(117):
+    e.process_ptr(base + 4 * NF * (s % RING), stride, NF)
+e1.record(); torch.cuda.synchronize()
+print("EBU R128 only : %.4f ms/block" % (e0.elapsed_time(e1) / 117))
