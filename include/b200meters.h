@@ -191,6 +191,25 @@ int b200m_cor_state (b200m_cor* h, float* state5, void* stream);          /* [n]
 int b200m_cor_coeffs (const b200m_cor* h, float w[2]);
 
 /* ======================================================================================
+ * Needle-meter ballistics bank — replaces LV2M::Vumeterdsp (jmeters/vumeterdsp.cc:45-93),
+ * Iec1ppmdsp / Iec2ppmdsp (jmeters/iec1ppmdsp.cc, iec2ppmdsp.cc :47-99) and Msppmdsp (jmeters/msppmdsp.cc:50-143)
+ * as driven by run() and bbcm_run() (src/meters.cc:298-331,552-589).
+ * kind VU / IEC1 / IEC2: n_units mono meters (row i = meter i).  kind MS: n_units stereo pairs (rows 2i, 2i+1),
+ * two meters per pair, M = processM at index 2i, S = processS at index 2i+1.
+ * ====================================================================================== */
+typedef struct b200m_ppm b200m_ppm;
+enum { B200M_PPM_VU = 0, B200M_PPM_IEC1 = 1, B200M_PPM_IEC2 = 2, B200M_PPM_MS = 3 };
+int b200m_ppm_create (b200m_ppm** out, int device, uint32_t n_units, float fsamp, int kind);
+int b200m_ppm_destroy (b200m_ppm* h);
+int b200m_ppm_set_gain (b200m_ppm* h, float db_m, float db_s);       /* Msppmdsp::set_gain of the M and S meters (default -6, -6) */
+int b200m_ppm_process_device (b200m_ppm* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
+int b200m_ppm_process_host (b200m_ppm* h, const float* in, size_t stride, uint32_t nfram);
+int b200m_ppm_read_device (b200m_ppm* h, void* stream);                /* read(): _res = true, value = _g * _m */
+int b200m_ppm_results (b200m_ppm* h, float* out, void* stream);        /* one float per meter */
+int b200m_ppm_state (b200m_ppm* h, float* state4, void* stream);       /* per meter: z1 z2 m res */
+int b200m_design_ppm (int kind, float fsamp, float w[4]);              /* w1 w2 w3 g (VU: w 0 0 g) */
+
+/* ======================================================================================
  * 30-band 1/3-octave spectrum bank — replaces spectrum_instantiate / spectrum_run
  * (src/spectrumlv2.c:73-121,159-257) over bandpass_setup / bandpass_process (src/spectr.c:68-206).
  * ====================================================================================== */

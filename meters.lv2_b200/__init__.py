@@ -91,6 +91,16 @@ _PROTOS = {
     "b200m_cor_results": (C.c_int, [_v, _v, _v]),
     "b200m_cor_state": (C.c_int, [_v, _v, _v]),
     "b200m_cor_coeffs": (C.c_int, [_v, _v]),
+    # needle-meter ballistics
+    "b200m_ppm_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_float, C.c_int]),
+    "b200m_ppm_destroy": (C.c_int, [_v]),
+    "b200m_ppm_set_gain": (C.c_int, [_v, C.c_float, C.c_float]),
+    "b200m_ppm_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
+    "b200m_ppm_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
+    "b200m_ppm_read_device": (C.c_int, [_v, _v]),
+    "b200m_ppm_results": (C.c_int, [_v, _v, _v]),
+    "b200m_ppm_state": (C.c_int, [_v, _v, _v]),
+    "b200m_design_ppm": (C.c_int, [C.c_int, C.c_float, _v]),
     # spectr30
     "b200m_spec_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_double]),
     "b200m_spec_destroy": (C.c_int, [_v]),
@@ -400,6 +410,51 @@ class Stcorrdsp(_Bank):
         w = np.empty(2, np.float32)
         _ck(lib().b200m_cor_coeffs(self.h, _np_ptr(w)))
         return w
+
+
+PPM_VU, PPM_IEC1, PPM_IEC2, PPM_MS = 0, 1, 2, 3
+
+
+def design_ppm(kind, fsamp):
+    w = np.empty(4, np.float32)
+    _ck(lib().b200m_design_ppm(kind, fsamp, _np_ptr(w)))
+    return w
+
+
+class NeedleMeters(_Bank):
+    """N x Vumeterdsp / Iec1ppmdsp / Iec2ppmdsp, or N stereo pairs x (Msppmdsp M, Msppmdsp S) (jmeters/*.cc)."""
+    _destroy = "b200m_ppm_destroy"
+
+    def __init__(self, n_units, kind, fsamp=48000.0, device=0):
+        super().__init__()
+        self.n_units, self.kind = n_units, kind
+        self.rows = 2 * n_units if kind == PPM_MS else n_units
+        self.n_meters = self.rows
+        _ck(lib().b200m_ppm_create(C.byref(self.h), device, n_units, fsamp, kind))
+
+    def set_gain(self, db_m, db_s):
+        _ck(lib().b200m_ppm_set_gain(self.h, db_m, db_s))
+
+    def process(self, x, stream=None):
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == self.rows
+            _ck(lib().b200m_ppm_process_host(self.h, p, s, n))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == self.rows
+            _ck(lib().b200m_ppm_process_device(self.h, p, s, n, _stream_ptr(stream)))
+
+    def read(self, stream=None):
+        _ck(lib().b200m_ppm_read_device(self.h, _stream_ptr(stream)))
+        out = np.empty(self.n_meters, np.float32)
+        _ck(lib().b200m_ppm_results(self.h, _np_ptr(out), _stream_ptr(stream)))
+        return out
+
+    def state(self, stream=None):
+        s = np.empty((self.n_meters, 4), np.float32)
+        _ck(lib().b200m_ppm_state(self.h, _np_ptr(s), _stream_ptr(stream)))
+        return s
 
 
 class Spectr30(_Bank):

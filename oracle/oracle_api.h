@@ -67,6 +67,17 @@ void  orc_km_peek     (void* h, float* state8);                  /* [n][8] z1 z2
 void  orc_km_reset    (void* h, int inst);
 void  orc_km_coeffs   (void* h, float* omega, int* hold);
 
+/* ---- needle-meter ballistics (jmeters/vumeterdsp.cc, iec1ppmdsp.cc, iec2ppmdsp.cc, msppmdsp.cc) ----
+ * kind 0 VU, 1 IEC type I PPM (DIN/Nordic), 2 IEC type II PPM (BBC/EBU): n mono meters, channel i = row i.
+ * kind 3 M/S PPM (BBC M6): n stereo pairs (rows 2i, 2i+1), two meters per pair: M = processM, S = processS */
+void* orc_ppm_create  (int n, float fsamp, int kind);
+void  orc_ppm_destroy (void* h);
+void  orc_ppm_process (void* h, const float* in, size_t stride, int nfram, int nthreads);
+void  orc_ppm_read    (void* h, float* out);              /* read(): kind 0-2 [n]; kind 3 [n][2] = M, S */
+void  orc_ppm_peek    (void* h, float* state4);           /* per meter z1 z2 m res; kind 3: [n][2][4] */
+void  orc_ppm_set_gain(void* h, float db_m, float db_s);  /* kind 3: Msppmdsp::set_gain of the M and S meters */
+void  orc_ppm_coeffs  (void* h, float* w4);               /* w1 w2 w3 g   (VU: w, 0, 0, g) */
+
 /* ---- Stereo correlation (jmeters/stcorrdsp.h:27-55) ---- */
 void* orc_cor_create  (int n, int fsamp, float flp, float tcf);
 void  orc_cor_destroy (void* h);

@@ -282,6 +282,49 @@ struct Kmeter {
 float Kmeter::omega, Kmeter::fsamp; int Kmeter::hold;
 
 // =====================================================================================
+// Needle-meter ballistics — jmeters/vumeterdsp.cc, iec1ppmdsp.cc, iec2ppmdsp.cc, msppmdsp.cc
+// =====================================================================================
+struct Needle {                                  // one meter: kind 0 VU, 1 IEC-I, 2 IEC-II, 3 M/S PPM (mid), 4 M/S PPM (side)
+    float z1 = 0, z2 = 0, m = 0; bool res = true; float db = 0, mv = 1.0f;
+    static float w1, w2, w3, g;
+    static void init (int kind, float fs) {
+        if (kind == 0) { w1 = 11.1f / fs; w2 = w3 = 0; g = 1.5f * 1.571f; }                                  // vumeterdsp.cc:89-93
+        else if (kind == 1) { w1 = 450.0f / fs; w2 = 1300.0f / fs; w3 = 1.0f - 5.4f / fs; g = 0.5108f; }     // iec1ppmdsp.cc:93-99
+        else { w1 = 200.0f / fs; w2 = 860.0f / fs; w3 = 1.0f - 4.0f / fs; g = 0.5141f; }                     // iec2ppmdsp.cc:93-99, msppmdsp.cc:127-133
+    }
+    void set_gain (float d) { if (db == d) return; db = d; mv = powf (10, .05 * d); }                        // msppmdsp.cc:135-143
+    void vu (const float* p, int n) {            // Vumeterdsp::process :45-73
+        float a = z1 > 20 ? 20 : (z1 < -20 ? -20 : z1), b = z2 > 20 ? 20 : (z2 < -20 ? -20 : z2), mm = res ? 0 : m;
+        res = false;
+        for (int q = n / 4; q > 0; --q) {
+            const float t2 = b / 2;
+            for (int i = 0; i < 4; ++i) { const float t1 = fabsf (*p++) - t2; a += w1 * (t1 - a); }
+            b += 4 * w1 * (a - b);
+            if (b > mm) mm = b;
+        }
+        if (!fin (a)) { z1 = 0; mm = INFINITY; } else z1 = a;
+        if (!fin (b)) { z2 = 0; mm = INFINITY; } else z2 = b + 1e-10f;
+        m = mm;
+    }
+    // Iec1ppmdsp/Iec2ppmdsp::process (:47-80), Msppmdsp::processM/S (:50-118): t(i) yields the rectified sample
+    template <class F> void ppm (int n, F t) {
+        float a = z1 > 20 ? 20 : (z1 < 0 ? 0 : z1), b = z2 > 20 ? 20 : (z2 < 0 ? 0 : z2), mm = res ? 0 : m;
+        res = false;
+        int k = 0;
+        for (int q = n / 4; q > 0; --q) {
+            a *= w3; b *= w3;
+            for (int i = 0; i < 4; ++i) { const float v = t (k++); if (v > a) a += w1 * (v - a); if (v > b) b += w2 * (v - b); }
+            const float s = a + b;
+            if (s > mm) mm = s;
+        }
+        z1 = a + 1e-10f; z2 = b + 1e-10f; m = mm;
+    }
+    float read () { res = true; return g * m; }
+};
+float Needle::w1, Needle::w2, Needle::w3, Needle::g;
+struct NeedleBank { int n, kind; std::vector<Needle> v; };
+
+// =====================================================================================
 // Stereo correlation — jmeters/stcorrdsp.cc
 // =====================================================================================
 struct Stcorr {
@@ -590,6 +633,33 @@ void orc_km_peek (void* h, float* s) {
 }
 void orc_km_reset (void* h, int inst) { auto* b = (Bank<Kmeter>*)h; for (int i = 0; i < b->n; ++i) if (inst < 0 || i == inst) b->v[i].reset (); }
 void orc_km_coeffs (void*, float* omega, int* hold) { *omega = Kmeter::omega; *hold = Kmeter::hold; }
+
+void* orc_ppm_create (int n, float fs, int kind) {
+    auto* b = new NeedleBank; b->n = n; b->kind = kind; b->v.resize (kind == 3 ? 2 * n : n); Needle::init (kind, fs);
+    if (kind == 3) for (auto& m : b->v) m.set_gain (-6);
+    return b;
+}
+void orc_ppm_destroy (void* h) { delete (NeedleBank*)h; }
+void orc_ppm_process (void* h, const float* in, size_t stride, int nfram, int nthreads) {
+    auto* b = (NeedleBank*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            if (b->kind == 0) b->v[i].vu (in + (size_t)i * stride, nfram);
+            else if (b->kind < 3) { const float* p = in + (size_t)i * stride; b->v[i].ppm (nfram, [=] (int k) { return fabsf (p[k]); }); }
+            else {
+                const float* l = in + (size_t)(2 * i) * stride; const float* r = l + stride;
+                Needle& M = b->v[2 * i]; Needle& S = b->v[2 * i + 1];
+                const float gm = M.mv, gs = S.mv;
+                M.ppm (nfram, [=] (int k) { return gm * fabsf (l[k] + r[k]); });
+                S.ppm (nfram, [=] (int k) { return gs * fabsf (l[k] - r[k]); });
+            }
+        }
+    });
+}
+void orc_ppm_read (void* h, float* out) { auto* b = (NeedleBank*)h; for (size_t i = 0; i < b->v.size (); ++i) out[i] = b->v[i].read (); }
+void orc_ppm_peek (void* h, float* s) { auto* b = (NeedleBank*)h; for (size_t i = 0; i < b->v.size (); ++i) { s[4 * i] = b->v[i].z1; s[4 * i + 1] = b->v[i].z2; s[4 * i + 2] = b->v[i].m; s[4 * i + 3] = b->v[i].res; } }
+void orc_ppm_set_gain (void* h, float db_m, float db_s) { auto* b = (NeedleBank*)h; if (b->kind != 3) return; for (int i = 0; i < b->n; ++i) { b->v[2 * i].set_gain (db_m); b->v[2 * i + 1].set_gain (db_s); } }
+void orc_ppm_coeffs (void* h, float* w) { (void)h; w[0] = Needle::w1; w[1] = Needle::w2; w[2] = Needle::w3; w[3] = Needle::g; }
 
 void* orc_cor_create (int n, int fs, float flp, float tcf) { auto* b = new Bank<Stcorr>; b->n = n; b->v.resize (n); Stcorr::init (fs, flp, tcf); return b; }
 void orc_cor_destroy (void* h) { delete (Bank<Stcorr>*)h; }

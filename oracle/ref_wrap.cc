@@ -21,6 +21,10 @@
 #include "jmeters/truepeakdsp.h"
 #include "jmeters/kmeterdsp.h"
 #include "jmeters/stcorrdsp.h"
+#include "jmeters/vumeterdsp.h"
+#include "jmeters/iec1ppmdsp.h"
+#include "jmeters/iec2ppmdsp.h"
+#include "jmeters/msppmdsp.h"
 #include "ebumeter/ebu_r128_proc.h"
 #include "zita-resampler/resampler-table.h"
 #undef private
@@ -203,6 +207,76 @@ void orc_km_peek (void* h, float* s)
 }
 void orc_km_reset (void* h, int inst) { KmB* b = (KmB*)h; for (int i = 0; i < b->n; ++i) if (inst < 0 || i == inst) b->p[i]->reset (); }
 void orc_km_coeffs (void*, float* omega, int* hold) { *omega = Kmeterdsp::_omega; *hold = Kmeterdsp::_hold; }
+
+/* ------------------------------------------------------------------ needle-meter ballistics */
+struct PpmB { int n, kind; std::vector<Vumeterdsp*> vu; std::vector<Iec1ppmdsp*> p1; std::vector<Iec2ppmdsp*> p2; std::vector<Msppmdsp*> ms; };
+void* orc_ppm_create (int n, float fsamp, int kind)
+{
+    PpmB* b = new PpmB; b->n = n; b->kind = kind;
+    for (int i = 0; i < n; ++i) {
+        if (kind == 0) { b->vu.push_back (new Vumeterdsp); }
+        else if (kind == 1) { b->p1.push_back (new Iec1ppmdsp); }
+        else if (kind == 2) { b->p2.push_back (new Iec2ppmdsp); }
+        else { b->ms.push_back (new Msppmdsp (-6)); b->ms.push_back (new Msppmdsp (-6)); }    /* src/meters.cc:210-212 */
+    }
+    if (kind == 0) Vumeterdsp::init (fsamp); else if (kind == 1) Iec1ppmdsp::init (fsamp); else if (kind == 2) Iec2ppmdsp::init (fsamp); else Msppmdsp::init (fsamp);
+    return b;
+}
+void orc_ppm_destroy (void* h)
+{
+    PpmB* b = (PpmB*)h;
+    for (auto p : b->vu) delete p; for (auto p : b->p1) delete p; for (auto p : b->p2) delete p; for (auto p : b->ms) delete p;
+    delete b;
+}
+void orc_ppm_process (void* h, const float* in, size_t stride, int nfram, int nthreads)
+{
+    PpmB* b = (PpmB*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            float* p = const_cast<float*> (in + (size_t)i * stride);
+            if (b->kind == 0) b->vu[i]->process (p, nfram);
+            else if (b->kind == 1) b->p1[i]->process (p, nfram);
+            else if (b->kind == 2) b->p2[i]->process (p, nfram);
+            else {
+                float* l = const_cast<float*> (in + (size_t)(2 * i) * stride); float* r = l + stride;
+                b->ms[2 * i]->processM (l, r, nfram); b->ms[2 * i + 1]->processS (l, r, nfram);
+            }
+        }
+    });
+}
+void orc_ppm_read (void* h, float* out)
+{
+    PpmB* b = (PpmB*)h;
+    for (int i = 0; i < b->n; ++i) {
+        if (b->kind == 0) out[i] = b->vu[i]->read (); else if (b->kind == 1) out[i] = b->p1[i]->read (); else if (b->kind == 2) out[i] = b->p2[i]->read ();
+        else { out[2 * i] = b->ms[2 * i]->read (); out[2 * i + 1] = b->ms[2 * i + 1]->read (); }
+    }
+}
+void orc_ppm_peek (void* h, float* s)
+{
+    PpmB* b = (PpmB*)h;
+    const int nm = b->kind == 3 ? 2 * b->n : b->n;
+    for (int i = 0; i < nm; ++i) {
+        float* o = s + 4 * i;
+        if (b->kind == 0) { o[0] = b->vu[i]->_z1; o[1] = b->vu[i]->_z2; o[2] = b->vu[i]->_m; o[3] = b->vu[i]->_res; }
+        else if (b->kind == 1) { o[0] = b->p1[i]->_z1; o[1] = b->p1[i]->_z2; o[2] = b->p1[i]->_m; o[3] = b->p1[i]->_res; }
+        else if (b->kind == 2) { o[0] = b->p2[i]->_z1; o[1] = b->p2[i]->_z2; o[2] = b->p2[i]->_m; o[3] = b->p2[i]->_res; }
+        else { o[0] = b->ms[i]->_z1; o[1] = b->ms[i]->_z2; o[2] = b->ms[i]->_m; o[3] = b->ms[i]->_res; }
+    }
+}
+void orc_ppm_set_gain (void* h, float db_m, float db_s)
+{
+    PpmB* b = (PpmB*)h;
+    for (int i = 0; i < (int)b->ms.size () / 2; ++i) { b->ms[2 * i]->set_gain (db_m); b->ms[2 * i + 1]->set_gain (db_s); }
+}
+void orc_ppm_coeffs (void* h, float* w)
+{
+    PpmB* b = (PpmB*)h;
+    if (b->kind == 0) { w[0] = Vumeterdsp::_w; w[1] = 0; w[2] = 0; w[3] = Vumeterdsp::_g; }
+    else if (b->kind == 1) { w[0] = Iec1ppmdsp::_w1; w[1] = Iec1ppmdsp::_w2; w[2] = Iec1ppmdsp::_w3; w[3] = Iec1ppmdsp::_g; }
+    else if (b->kind == 2) { w[0] = Iec2ppmdsp::_w1; w[1] = Iec2ppmdsp::_w2; w[2] = Iec2ppmdsp::_w3; w[3] = Iec2ppmdsp::_g; }
+    else { w[0] = Msppmdsp::_w1; w[1] = Msppmdsp::_w2; w[2] = Msppmdsp::_w3; w[3] = Msppmdsp::_g; }
+}
 
 /* ------------------------------------------------------------------ Stcorr */
 struct CorB { int n; std::vector<Stcorrdsp*> p; };

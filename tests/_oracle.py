@@ -52,6 +52,13 @@ def _proto(lib):
         "orc_km_peek": (None, [_v, _v]),
         "orc_km_reset": (None, [_v, C.c_int]),
         "orc_km_coeffs": (None, [_v, _v, _v]),
+        "orc_ppm_create": (_v, [C.c_int, C.c_float, C.c_int]),
+        "orc_ppm_destroy": (None, [_v]),
+        "orc_ppm_process": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int]),
+        "orc_ppm_read": (None, [_v, _v]),
+        "orc_ppm_peek": (None, [_v, _v]),
+        "orc_ppm_set_gain": (None, [_v, C.c_float, C.c_float]),
+        "orc_ppm_coeffs": (None, [_v, _v]),
         "orc_cor_create": (_v, [C.c_int, C.c_int, C.c_float, C.c_float]),
         "orc_cor_destroy": (None, [_v]),
         "orc_cor_process": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int]),
@@ -221,6 +228,45 @@ class Kmeter:
         o = np.empty(1, np.float32); h = np.empty(1, np.int32)
         self.L.orc_km_coeffs(self.h, ptr(o), ptr(h))
         return o[0], int(h[0])
+
+
+PPM_VU, PPM_IEC1, PPM_IEC2, PPM_MS = 0, 1, 2, 3
+
+
+class Needle:
+    """kind 0 VU / 1 IEC-I / 2 IEC-II: n mono meters; kind 3 M/S PPM: n stereo pairs, two meters (M, S) per pair."""
+
+    def __init__(self, n, kind, fsamp=48000.0, oracle="best"):
+        self.L = load(oracle); self.n, self.kind = n, kind
+        self.nm = 2 * n if kind == PPM_MS else n
+        self.h = self.L.orc_ppm_create(n, fsamp, kind)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_ppm_destroy(self.h); self.h = None
+
+    def process(self, x, nthreads=1):
+        p, s = planar(x)
+        assert x.shape[0] == self.nm
+        self.L.orc_ppm_process(self.h, p, s, x.shape[1], nthreads)
+
+    def read(self):
+        o = np.empty(self.nm, np.float32)
+        self.L.orc_ppm_read(self.h, ptr(o))
+        return o
+
+    def peek(self):
+        s = np.empty((self.nm, 4), np.float32)
+        self.L.orc_ppm_peek(self.h, ptr(s))
+        return s
+
+    def set_gain(self, db_m, db_s):
+        self.L.orc_ppm_set_gain(self.h, db_m, db_s)
+
+    def coeffs(self):
+        w = np.empty(4, np.float32)
+        self.L.orc_ppm_coeffs(self.h, ptr(w))
+        return w
 
 
 class Stcorr:

@@ -23,6 +23,7 @@ BLOCKS = [1024] * 130 + [480, 64, 8192, 1, 3, 1023]
 
 def compute(kind):
     out = {}
+    kind_o = kind
     x = S.white(8, sum(BLOCKS), seed=0xC0FFEE)
     x[6, 5000:5010] = [np.nan, np.inf, -np.inf, 1e-42, 0, 1, -1, 1e-30, 3e38, -3e38]
     e = O.Ebu(4, 2, kind=kind); e.integr("start")
@@ -48,6 +49,16 @@ def compute(kind):
     ports = sp.read()
     out["spec_ports"] = ports[:, :30].copy(); out["spec_maxports"] = ports[:, 30:].copy()
     out["spec_coeffs"] = sp.coeffs()
+    # needle-meter ballistics (VU, IEC I, IEC II, M/S PPM)
+    for nk in range(4):
+        nm = O.Needle(4, nk, oracle=kind_o)
+        reads = []
+        pos2 = 0
+        for i, n in enumerate(BLOCKS[:40]):
+            blk = np.ascontiguousarray((x[:8 if nk == 3 else 4, pos2:pos2 + n] * np.float32(3.0))); pos2 += n
+            nm.process(blk); reads.append(nm.read())
+        out["needle_reads_%d" % nk] = np.stack(reads)
+        out["needle_state_%d" % nk] = nm.peek()
     # 997 Hz / -23 dBFS tone (EBU Tech 3341 case 1)
     s = S.sine(1024 * 300, 997.0, amp=10 ** (-23 / 20)); y = np.ascontiguousarray(np.stack([s, s]))
     e2 = O.Ebu(1, 2, kind=kind); e2.integr("start")

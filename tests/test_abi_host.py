@@ -65,6 +65,8 @@ def test_host_design_bitwise_equals_oracle(fs):
     assert np.array_equal(u32(w), u32(ow)) and np.array_equal(u32(t), u32(ot))
     assert u32(k[:1])[0] == u32(np.float32(om))[()] and int(k[1]) == oh
     assert np.array_equal(u32(B.design_cor(fs)), u32(O.Stcorr(1, fs).coeffs()))
+    for k in range(4):
+        assert np.array_equal(u32(B.design_ppm(k, fs)), u32(O.Needle(1, k, fs).coeffs())), k
     W = B.design_spec(fs)
     R = O.Spectr30(1, 2, fs).coeffs()
     assert np.array_equal(W.view(np.uint64), R.view(np.uint64))

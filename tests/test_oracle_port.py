@@ -94,6 +94,23 @@ def test_spectr_port_equals_reference(nchan, rate):
     assert np.array_equal(za[0].view(np.uint64), zb[0].view(np.uint64)) and np.array_equal(u32(za[1]), u32(zb[1]))
 
 
+@needs_both
+@pytest.mark.parametrize("kind", [0, 1, 2, 3])
+def test_needle_meters_port_equals_reference(kind):
+    n = 5
+    rows = 2 * n if kind == 3 else n
+    x = S.nasty(rows, sum(BLOCKS), seed=106 + kind) * np.float32(3.0)
+    a, b = O.Needle(n, kind, oracle="reference"), O.Needle(n, kind, oracle="port")
+    assert np.array_equal(u32(a.coeffs()), u32(b.coeffs()))
+    if kind == 3:
+        a.set_gain(-6, 14); b.set_gain(-6, 14)
+    for i, blk in enumerate(_blocks(x, BLOCKS)):
+        a.process(blk); b.process(blk)
+        if i % 2:
+            assert np.array_equal(u32(a.read()), u32(b.read()))
+    assert np.array_equal(u32(a.peek()), u32(b.peek()))
+
+
 @needs_port
 def test_port_phasewheel_against_numpy_fft():
     """the FFT restatement (FFTW absent => parity unpinned) is at least a correct DFT of the windowed ring."""
