@@ -210,6 +210,30 @@ int b200m_ppm_state (b200m_ppm* h, float* state4, void* stream);       /* per me
 int b200m_design_ppm (int kind, float fsamp, float w[4]);              /* w1 w2 w3 g (VU: w 0 0 g) */
 
 /* ======================================================================================
+ * Bit-meter and signal-distribution-histogram banks, N mono instances each.
+ * bit-meter: float_stats + the acquisition / ~5 fps window logic of bim_run (src/bitmeter.c:63-105,248-327);
+ *   results = int32 histS[584] (layout src/uris.h:52-60), counters {zero,pos,nan,inf,den}, {min,max}, integration time.
+ * SigDistHist: the sample loop of sdh_run (src/sigdistlv2.c:287-327): int32 histS[361], {max count, peak bin},
+ *   {sum, running mean, running variance accumulator} in double, integration time.
+ * Controls mirror the plugins' CTL_* messages (src/uris.h:187-203).
+ * ====================================================================================== */
+typedef struct b200m_bim b200m_bim;
+typedef struct b200m_sdh b200m_sdh;
+enum { B200M_CTL_START = 1, B200M_CTL_PAUSE = 2, B200M_CTL_RESET = 3, B200M_CTL_AVERAGE = 4, B200M_CTL_WINDOWED = 5 };
+int b200m_bim_create (b200m_bim** out, int device, uint32_t n_inst, double rate);
+int b200m_bim_destroy (b200m_bim* h);
+int b200m_bim_control (b200m_bim* h, int cmd, void* stream);
+int b200m_bim_run_device (b200m_bim* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
+int b200m_bim_run_host (b200m_bim* h, const float* in, size_t stride, uint32_t nfram);
+int b200m_bim_results (b200m_bim* h, uint32_t inst, int32_t* hist584, int32_t* cnt5, float* minmax2, int64_t* integration_time, void* stream);
+int b200m_sdh_create (b200m_sdh** out, int device, uint32_t n_inst, double rate);
+int b200m_sdh_destroy (b200m_sdh* h);
+int b200m_sdh_control (b200m_sdh* h, int cmd, void* stream);
+int b200m_sdh_run_device (b200m_sdh* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
+int b200m_sdh_run_host (b200m_sdh* h, const float* in, size_t stride, uint32_t nfram);
+int b200m_sdh_results (b200m_sdh* h, uint32_t inst, int32_t* hist361, int32_t* max_peak2, double* avg_tmp_var3, int64_t* integration_time, void* stream);
+
+/* ======================================================================================
  * 30-band 1/3-octave spectrum bank — replaces spectrum_instantiate / spectrum_run
  * (src/spectrumlv2.c:73-121,159-257) over bandpass_setup / bandpass_process (src/spectr.c:68-206).
  * ====================================================================================== */

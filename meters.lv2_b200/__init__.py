@@ -101,6 +101,19 @@ _PROTOS = {
     "b200m_ppm_results": (C.c_int, [_v, _v, _v]),
     "b200m_ppm_state": (C.c_int, [_v, _v, _v]),
     "b200m_design_ppm": (C.c_int, [C.c_int, C.c_float, _v]),
+    # bit-meter, signal distribution histogram
+    "b200m_bim_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_double]),
+    "b200m_bim_destroy": (C.c_int, [_v]),
+    "b200m_bim_control": (C.c_int, [_v, C.c_int, _v]),
+    "b200m_bim_run_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
+    "b200m_bim_run_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
+    "b200m_bim_results": (C.c_int, [_v, C.c_uint32, _v, _v, _v, _v, _v]),
+    "b200m_sdh_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_double]),
+    "b200m_sdh_destroy": (C.c_int, [_v]),
+    "b200m_sdh_control": (C.c_int, [_v, C.c_int, _v]),
+    "b200m_sdh_run_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
+    "b200m_sdh_run_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
+    "b200m_sdh_results": (C.c_int, [_v, C.c_uint32, _v, _v, _v, _v, _v]),
     # spectr30
     "b200m_spec_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_double]),
     "b200m_spec_destroy": (C.c_int, [_v]),
@@ -455,6 +468,54 @@ class NeedleMeters(_Bank):
         s = np.empty((self.n_meters, 4), np.float32)
         _ck(lib().b200m_ppm_state(self.h, _np_ptr(s), _stream_ptr(stream)))
         return s
+
+
+CTL_START, CTL_PAUSE, CTL_RESET, CTL_AVERAGE, CTL_WINDOWED = 1, 2, 3, 4, 5
+
+
+class _StatBank(_Bank):
+    _pfx = None
+
+    def __init__(self, n_inst, rate=48000.0, device=0):
+        super().__init__()
+        self.n_inst = n_inst
+        _ck(getattr(lib(), self._pfx + "create")(C.byref(self.h), device, n_inst, rate))
+
+    def control(self, cmd, stream=None):
+        _ck(getattr(lib(), self._pfx + "control")(self.h, cmd, _stream_ptr(stream)))
+
+    def run(self, x, stream=None):
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == self.n_inst
+            _ck(getattr(lib(), self._pfx + "run_host")(self.h, p, s, n))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == self.n_inst
+            _ck(getattr(lib(), self._pfx + "run_device")(self.h, p, s, n, _stream_ptr(stream)))
+
+    def run_ptr(self, ptr, stride, nfram, stream=None):
+        _ck(getattr(lib(), self._pfx + "run_device")(self.h, C.c_void_p(ptr), stride, nfram, _stream_ptr(stream)))
+
+
+class Bitmeter(_StatBank):
+    """N x the bit-meter plugin's statistics (src/bitmeter.c:63-105,248-327)."""
+    _destroy, _pfx = "b200m_bim_destroy", "b200m_bim_"
+
+    def results(self, inst, stream=None):
+        h = np.empty(584, np.int32); c = np.empty(5, np.int32); mm = np.empty(2, np.float32); it = C.c_int64(0)
+        _ck(lib().b200m_bim_results(self.h, inst, _np_ptr(h), _np_ptr(c), _np_ptr(mm), C.byref(it), _stream_ptr(stream)))
+        return h, c, mm, it.value
+
+
+class SigDistHist(_StatBank):
+    """N x the signal-distribution-histogram plugin's statistics (src/sigdistlv2.c:287-327)."""
+    _destroy, _pfx = "b200m_sdh_destroy", "b200m_sdh_"
+
+    def results(self, inst, stream=None):
+        h = np.empty(361, np.int32); mp = np.empty(2, np.int32); av = np.empty(3, np.float64); it = C.c_int64(0)
+        _ck(lib().b200m_sdh_results(self.h, inst, _np_ptr(h), _np_ptr(mp), _np_ptr(av), C.byref(it), _stream_ptr(stream)))
+        return h, mp, av, it.value
 
 
 class Spectr30(_Bank):

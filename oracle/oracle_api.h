@@ -94,6 +94,22 @@ void  orc_spec_read   (void* h, float* out60);                   /* [n_inst][60]
 void  orc_spec_state  (void* h, int inst, double* z360, float* val30, float* max30);
 void  orc_spec_coeffs (void* h, double* W);                      /* [30][6][6] a0 a1 a2 b0 b1 b2 */
 
+/* ---- bit-meter (src/bitmeter.c: float_stats :63-105, bim_run :181-348), n mono instances ----
+ * kind "reference" drives the plugin's own LV2 run(); result fields are read from the instance after each run().
+ * average != 0 = CTL_AVERAGE (cumulative); 0 = windowed: statistics are cleared about 5 times per second (:264,325-327) */
+void* orc_bim_create  (int n, float rate);
+void  orc_bim_destroy (void* h);
+void  orc_bim_mode    (void* h, int average, int integrating);
+void  orc_bim_process (void* h, const float* in, size_t stride, int nfram, int nthreads);
+void  orc_bim_read    (void* h, int inst, int32_t* hist584, int32_t* cnt5, float* minmax2, int64_t* itime); /* cnt5 = zero pos nan inf den */
+
+/* ---- signal distribution histogram (src/sigdistlv2.c: sdh_run :200-396, loop :303-318), n mono instances ---- */
+void* orc_sdh_create  (int n, float rate);
+void  orc_sdh_destroy (void* h);
+void  orc_sdh_integrate (void* h, int on);
+void  orc_sdh_process (void* h, const float* in, size_t stride, int nfram, int nthreads);
+void  orc_sdh_read    (void* h, int inst, int32_t* hist361, int32_t* maxpeak2, double* avg_tmp_var3, int64_t* itime);
+
 /* ---- phasewheel / stereoscope FFT analysis (gui/fft.c:208-340, gui/phasewheel.c:1307-1342) ----
  * kind "reference" returns NULL from orc_pw_create: FFTW3 is not vendored and absent here. */
 void* orc_pw_create   (int n_inst, int fft_bins, double rate);

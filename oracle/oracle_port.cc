@@ -469,6 +469,63 @@ struct Spec {
 };
 
 // =====================================================================================
+// Bit-meter — src/bitmeter.c ; signal distribution histogram — src/sigdistlv2.c
+// =====================================================================================
+struct Bim {
+    int32_t hist[584]; int zero, pos, nan_, inf_, den; float mn, mx; uint64_t itime; int resync; bool average, integrating; double rate;
+    void clear () { memset (hist, 0, sizeof (hist)); mn = INFINITY; mx = 0; zero = pos = 0; itime = 0; }      // bim_clear :46-54
+    void init (double r) { rate = r; average = false; integrating = true; resync = 0; clear (); nan_ = inf_ = den = 0; }   // :146-157, bim_reset :56-59
+    void stats (const float* sp) {                      // float_stats :63-105
+        uint32_t v; memcpy (&v, sp, 4);
+        unsigned e = (v & 0x7f800000u) >> 23; const bool positive = !(v & 0x80000000u);
+        v &= 0x7fffff;
+        if (e == 255) { if (v == 0) ++inf_; else ++nan_; return; }
+        if (e == 0 && v == 0) { ++zero; return; }
+        if (e == 0) ++den;
+        if (positive) ++pos;
+        if (e > 0) {
+            const float a = fabsf (*sp);
+            if (a > mx) mx = a;
+            if (a < mn) mn = a;
+            ++hist[23 + e]; ++hist[303 + e];            // BIM_NHIT, BIM_NONE (src/uris.h:52-60)
+        } else e = 1;
+        for (int k = 0; k < 23; ++k) {
+            ++hist[0 + e + k];                          // BIM_DHIT
+            if (v & (1u << k)) { ++hist[280 + e + k]; ++hist[560 + k]; }   // BIM_DONE, BIM_DSET
+        }
+    }
+    void run (const float* in, uint32_t n) {            // bim_run :248-327 (audio part + the ~5 fps window)
+        if (integrating && itime < 2147483647) {
+            if (itime > 2147483647 - n) itime = 2147483647;
+            else { for (uint32_t s = 0; s < n; ++s) stats (in + s); itime += n; }
+        }
+        const int fps_limit = n * ceil (rate / (5.f * n));
+        resync += n;
+        if (resync >= fps_limit) { resync = resync % fps_limit; if (!average) clear (); }
+    }
+};
+struct Sdh {
+    int32_t hist[361]; int mx, peak; double avg, tmp, var; uint64_t itime; bool integrating;
+    void init () { memset (hist, 0, sizeof (hist)); peak = -1; avg = tmp = var = 0; mx = 0; itime = 0; integrating = false; }   // sdh_instantiate :141-150
+    void run (const float* in, uint32_t n) {            // sdh_run :287-327
+        if (!(integrating && itime < 2147483647)) return;
+        if (itime > 2147483647 - n) { itime = 2147483647; return; }
+        for (uint32_t s = 0; s < n; ++s) {
+            const float val = in[s];
+            const float r = rintf (180.f + val * 150.f);
+            if (!(r >= 0.f && r < 361.f)) continue;     // int conversion of NaN / out-of-range is INT_MIN on x86: "bin < 0"
+            const int bin = (int)r;
+            if ((++hist[bin]) > mx) { mx = hist[bin]; peak = bin; }
+            avg += val;
+            const double m1 = tmp, cnt = (double)(itime + s + 1);
+            tmp = tmp + ((double)val - tmp) / cnt;
+            var = var + ((double)val - tmp) * ((double)val - m1);
+        }
+        itime += n;
+    }
+};
+
+// =====================================================================================
 // Phasewheel FFT analysis — gui/fft.c, gui/phasewheel.c (FFTW replaced by a double-precision DFT)
 // =====================================================================================
 void dft_r2c (const float* in, int N, std::vector<std::complex<double>>& X)   // X_k = sum x_n e^{-2 pi i nk/N}
@@ -685,6 +742,29 @@ void orc_spec_state (void* h, int inst, double* z, float* v, float* m) {
     for (int b = 0; b < 30; ++b) { v[b] = s.val[b]; m[b] = s.mx[b]; for (int q = 0; q < 6; ++q) { z[(b * 6 + q) * 2] = s.flt[b].f[q].z[0]; z[(b * 6 + q) * 2 + 1] = s.flt[b].f[q].z[1]; } }
 }
 void orc_spec_coeffs (void* h, double* W) { const Spec& s = ((Bank<Spec>*)h)->v[0]; for (int b = 0; b < 30; ++b) for (int q = 0; q < 6; ++q) for (int k = 0; k < 6; ++k) W[(b * 6 + q) * 6 + k] = s.flt[b].f[q].W[k]; }
+
+void* orc_bim_create (int n, float rate) { auto* b = new Bank<Bim>; b->n = n; b->v.resize (n); for (auto& m : b->v) m.init (rate); return b; }
+void  orc_bim_destroy (void* h) { delete (Bank<Bim>*)h; }
+void  orc_bim_mode (void* h, int average, int integrating) { for (auto& m : ((Bank<Bim>*)h)->v) { m.average = average; m.integrating = integrating; } }
+void  orc_bim_process (void* h, const float* in, size_t stride, int nfram, int nthreads) {
+    auto* b = (Bank<Bim>*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) { for (int i = a; i < e; ++i) b->v[i].run (in + (size_t)i * stride, (uint32_t)nfram); });
+}
+void  orc_bim_read (void* h, int inst, int32_t* hist, int32_t* c, float* mm, int64_t* it) {
+    const Bim& m = ((Bank<Bim>*)h)->v[inst];
+    memcpy (hist, m.hist, sizeof (m.hist)); c[0] = m.zero; c[1] = m.pos; c[2] = m.nan_; c[3] = m.inf_; c[4] = m.den; mm[0] = m.mn; mm[1] = m.mx; *it = (int64_t)m.itime;
+}
+void* orc_sdh_create (int n, float) { auto* b = new Bank<Sdh>; b->n = n; b->v.resize (n); for (auto& m : b->v) m.init (); return b; }
+void  orc_sdh_destroy (void* h) { delete (Bank<Sdh>*)h; }
+void  orc_sdh_integrate (void* h, int on) { for (auto& m : ((Bank<Sdh>*)h)->v) m.integrating = on; }
+void  orc_sdh_process (void* h, const float* in, size_t stride, int nfram, int nthreads) {
+    auto* b = (Bank<Sdh>*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) { for (int i = a; i < e; ++i) b->v[i].run (in + (size_t)i * stride, (uint32_t)nfram); });
+}
+void  orc_sdh_read (void* h, int inst, int32_t* hist, int32_t* mp, double* av, int64_t* it) {
+    const Sdh& m = ((Bank<Sdh>*)h)->v[inst];
+    memcpy (hist, m.hist, sizeof (m.hist)); mp[0] = m.mx; mp[1] = m.peak; av[0] = m.avg; av[1] = m.tmp; av[2] = m.var; *it = (int64_t)m.itime;
+}
 
 void* orc_pw_create (int n, int fft_bins, double rate) { auto* b = new Bank<Pw>; b->n = n; b->v.resize (n); for (auto& p : b->v) p.init (fft_bins, rate); return b; }
 void orc_pw_destroy (void* h) { delete (Bank<Pw>*)h; }

@@ -1,0 +1,90 @@
+// ref_plugins_tu.cc — compiles the reference's whole plugin glue (src/meters.cc and every .c/.cc it #includes)
+// UNMODIFIED, by path, against the stand-in LV2 headers in oracle/lv2stub, and drives individual plugins through
+// their own LV2_Descriptor (instantiate / connect_port / run) exactly as a host would.
+//
+// TEST INFRASTRUCTURE ONLY (see oracle_api.h).  No audio arithmetic lives here: the hooks below only create
+// instances, hand them buffers and copy internal result fields out (this TU sees LV2meter because it includes the
+// reference source textually).  Used for the rows whose arithmetic sits in the glue files themselves:
+// bit-meter float_stats (src/bitmeter.c:63-105), signal-distribution histogram (src/sigdistlv2.c:303-318).
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "src/meters.cc"
+
+namespace {
+
+std::vector<std::string> g_uris;                         // urid:map feature: index + 1 = URID
+LV2_URID map_uri (LV2_URID_Map_Handle, const char* uri)
+{
+    for (size_t i = 0; i < g_uris.size (); ++i) if (g_uris[i] == uri) return (LV2_URID)(i + 1);
+    g_uris.push_back (uri);
+    return (LV2_URID)g_uris.size ();
+}
+LV2_URID_Map g_map = {nullptr, map_uri};
+
+struct RefPlug {
+    const LV2_Descriptor* d; LV2_Handle h;
+    LV2_Atom_Sequence control;                             // empty event sequence
+    std::vector<uint64_t> notify;                          // 64 KiB, 8-byte aligned
+};
+
+const LV2_Descriptor* find_desc (const char* suffix)
+{
+    const std::string want = std::string (MTR_URI) + suffix;
+    for (uint32_t i = 0;; ++i) { const LV2_Descriptor* d = lv2_descriptor (i); if (!d) return nullptr; if (want == d->URI) return d; }
+}
+
+}  // namespace
+
+extern "C" {
+
+void* refplug_new (const char* uri_suffix, double rate)
+{
+    const LV2_Descriptor* d = find_desc (uri_suffix);
+    if (!d) return nullptr;
+    const LV2_Feature fmap = {LV2_URID__map, &g_map};
+    const LV2_Feature* feats[] = {&fmap, nullptr};
+    RefPlug* p = new RefPlug;
+    p->d = d; p->h = d->instantiate (d, rate, "", feats);
+    if (!p->h) { delete p; return nullptr; }
+    p->notify.assign (8192, 0);
+    p->control.atom.size = sizeof (LV2_Atom_Sequence_Body); p->control.atom.type = map_uri (nullptr, LV2_ATOM__Sequence);
+    p->control.body.unit = 0; p->control.body.pad = 0;
+    d->connect_port (p->h, 0, &p->control);
+    d->connect_port (p->h, 1, p->notify.data ());
+    return p;
+}
+void refplug_free (void* vp) { RefPlug* p = (RefPlug*)vp; p->d->cleanup (p->h); delete p; }
+void refplug_connect (void* vp, uint32_t port, void* data) { RefPlug* p = (RefPlug*)vp; p->d->connect_port (p->h, port, data); }
+void refplug_run (void* vp, uint32_t n)
+{
+    RefPlug* p = (RefPlug*)vp;
+    LV2_Atom_Sequence* s = (LV2_Atom_Sequence*)p->notify.data ();
+    s->atom.size = (uint32_t)(p->notify.size () * 8 - sizeof (LV2_Atom));   // host convention: capacity of the output port
+    s->atom.type = 0;
+    p->d->run (p->h, n);
+}
+
+/* bit-meter (src/bitmeter.c): mode = 1 -> CTL_AVERAGE (cumulative), 0 -> windowed (cleared ~5x per second) */
+void refbim_mode (void* vp, int average, int integrating) { LV2meter* m = (LV2meter*)((RefPlug*)vp)->h; m->bim_average = average; m->ebu_integrating = integrating; }
+void refbim_snapshot (void* vp, int32_t* hist584, int32_t* cnt5, float* minmax2, int64_t* itime)
+{
+    LV2meter* m = (LV2meter*)((RefPlug*)vp)->h;
+    memcpy (hist584, m->histS, BIM_LAST * sizeof (int32_t));
+    cnt5[0] = m->bim_zero; cnt5[1] = m->bim_pos; cnt5[2] = m->bim_nan; cnt5[3] = m->bim_inf; cnt5[4] = m->bim_den;
+    minmax2[0] = m->bim_min; minmax2[1] = m->bim_max; *itime = (int64_t)m->integration_time;
+}
+/* signal distribution histogram (src/sigdistlv2.c) */
+void refsdh_integrate (void* vp, int on) { LV2meter* m = (LV2meter*)((RefPlug*)vp)->h; m->ebu_integrating = on; }
+void refsdh_snapshot (void* vp, int32_t* hist361, int32_t* maxpeak2, double* avgtmpvar3, int64_t* itime)
+{
+    LV2meter* m = (LV2meter*)((RefPlug*)vp)->h;
+    memcpy (hist361, m->histS, DIST_BIN * sizeof (int32_t));
+    maxpeak2[0] = m->hist_maxS; maxpeak2[1] = m->hist_peakS;
+    avgtmpvar3[0] = m->hist_avgS; avgtmpvar3[1] = m->hist_tmpS; avgtmpvar3[2] = m->hist_varS; *itime = (int64_t)m->integration_time;
+}
+
+}  // extern "C"

@@ -327,6 +327,45 @@ void orc_spec_read (void* h, float* out) { SpB* b = (SpB*)h; memcpy (out, b->por
 void orc_spec_state (void* h, int inst, double* z, float* v, float* m) { refspec_state (((SpB*)h)->p[inst], z, v, m); }
 void orc_spec_coeffs (void* h, double* W) { refspec_coeffs (((SpB*)h)->p[0], W); }
 
+/* ------------------------------------------------------------------ bit-meter / SigDistHist through LV2 run() */
+void* refplug_new (const char* uri_suffix, double rate);
+void  refplug_free (void*);
+void  refplug_connect (void*, uint32_t port, void* data);
+void  refplug_run (void*, uint32_t n);
+void  refbim_mode (void*, int average, int integrating);
+void  refbim_snapshot (void*, int32_t*, int32_t*, float*, int64_t*);
+void  refsdh_integrate (void*, int on);
+void  refsdh_snapshot (void*, int32_t*, int32_t*, double*, int64_t*);
+
+struct PlugB { int n; std::vector<void*> p; };
+static void* plug_create (int n, const char* uri, double rate)
+{
+    PlugB* b = new PlugB; b->n = n;
+    for (int i = 0; i < n; ++i) { void* p = refplug_new (uri, rate); if (!p) { delete b; return 0; } b->p.push_back (p); }
+    return b;
+}
+static void plug_process (void* h, const float* in, size_t stride, int nfram, int nthreads)
+{
+    PlugB* b = (PlugB*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            float* p = const_cast<float*> (in + (size_t)i * stride);
+            refplug_connect (b->p[i], 2, p); refplug_connect (b->p[i], 3, p);      /* in-place */
+            refplug_run (b->p[i], (uint32_t)nfram);
+        }
+    });
+}
+void* orc_bim_create (int n, float rate) { return plug_create (n, "bitmeter", rate); }
+void  orc_bim_destroy (void* h) { PlugB* b = (PlugB*)h; for (auto p : b->p) refplug_free (p); delete b; }
+void  orc_bim_mode (void* h, int average, int integrating) { PlugB* b = (PlugB*)h; for (auto p : b->p) refbim_mode (p, average, integrating); }
+void  orc_bim_process (void* h, const float* in, size_t stride, int nfram, int nthreads) { plug_process (h, in, stride, nfram, nthreads); }
+void  orc_bim_read (void* h, int inst, int32_t* hist, int32_t* cnt5, float* mm, int64_t* it) { refbim_snapshot (((PlugB*)h)->p[inst], hist, cnt5, mm, it); }
+void* orc_sdh_create (int n, float rate) { return plug_create (n, "SigDistHist", rate); }
+void  orc_sdh_destroy (void* h) { orc_bim_destroy (h); }
+void  orc_sdh_integrate (void* h, int on) { PlugB* b = (PlugB*)h; for (auto p : b->p) refsdh_integrate (p, on); }
+void  orc_sdh_process (void* h, const float* in, size_t stride, int nfram, int nthreads) { plug_process (h, in, stride, nfram, nthreads); }
+void  orc_sdh_read (void* h, int inst, int32_t* hist, int32_t* mp, double* av, int64_t* it) { refsdh_snapshot (((PlugB*)h)->p[inst], hist, mp, av, it); }
+
 /* ------------------------------------------------------------------ phasewheel: FFTW3 absent */
 void* orc_pw_create (int, int, double) { return 0; }
 void  orc_pw_destroy (void*) {}

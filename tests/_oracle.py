@@ -59,6 +59,16 @@ def _proto(lib):
         "orc_ppm_peek": (None, [_v, _v]),
         "orc_ppm_set_gain": (None, [_v, C.c_float, C.c_float]),
         "orc_ppm_coeffs": (None, [_v, _v]),
+        "orc_bim_create": (_v, [C.c_int, C.c_float]),
+        "orc_bim_destroy": (None, [_v]),
+        "orc_bim_mode": (None, [_v, C.c_int, C.c_int]),
+        "orc_bim_process": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int]),
+        "orc_bim_read": (None, [_v, C.c_int, _v, _v, _v, _v]),
+        "orc_sdh_create": (_v, [C.c_int, C.c_float]),
+        "orc_sdh_destroy": (None, [_v]),
+        "orc_sdh_integrate": (None, [_v, C.c_int]),
+        "orc_sdh_process": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int]),
+        "orc_sdh_read": (None, [_v, C.c_int, _v, _v, _v, _v]),
         "orc_cor_create": (_v, [C.c_int, C.c_int, C.c_float, C.c_float]),
         "orc_cor_destroy": (None, [_v]),
         "orc_cor_process": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int]),
@@ -267,6 +277,52 @@ class Needle:
         w = np.empty(4, np.float32)
         self.L.orc_ppm_coeffs(self.h, ptr(w))
         return w
+
+
+class Bitmeter:
+    def __init__(self, n, rate=48000.0, oracle="best"):
+        self.L = load(oracle); self.n = n
+        self.h = self.L.orc_bim_create(n, rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_bim_destroy(self.h); self.h = None
+
+    def mode(self, average, integrating=True):
+        self.L.orc_bim_mode(self.h, int(average), int(integrating))
+
+    def process(self, x, nthreads=1):
+        p, s = planar(x)
+        assert x.shape[0] == self.n
+        self.L.orc_bim_process(self.h, p, s, x.shape[1], nthreads)
+
+    def read(self, inst):
+        h = np.empty(584, np.int32); c = np.empty(5, np.int32); mm = np.empty(2, np.float32); it = np.empty(1, np.int64)
+        self.L.orc_bim_read(self.h, inst, ptr(h), ptr(c), ptr(mm), ptr(it))
+        return h, c, mm, int(it[0])
+
+
+class SigDist:
+    def __init__(self, n, rate=48000.0, oracle="best"):
+        self.L = load(oracle); self.n = n
+        self.h = self.L.orc_sdh_create(n, rate)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_sdh_destroy(self.h); self.h = None
+
+    def integrate(self, on=True):
+        self.L.orc_sdh_integrate(self.h, int(on))
+
+    def process(self, x, nthreads=1):
+        p, s = planar(x)
+        assert x.shape[0] == self.n
+        self.L.orc_sdh_process(self.h, p, s, x.shape[1], nthreads)
+
+    def read(self, inst):
+        h = np.empty(361, np.int32); mp = np.empty(2, np.int32); av = np.empty(3, np.float64); it = np.empty(1, np.int64)
+        self.L.orc_sdh_read(self.h, inst, ptr(h), ptr(mp), ptr(av), ptr(it))
+        return h, mp, av, int(it[0])
 
 
 class Stcorr:

@@ -59,6 +59,18 @@ def compute(kind):
             nm.process(blk); reads.append(nm.read())
         out["needle_reads_%d" % nk] = np.stack(reads)
         out["needle_state_%d" % nk] = nm.peek()
+    # bit-meter (cumulative mode) and signal distribution histogram
+    bm = O.Bitmeter(4, oracle=kind_o); bm.mode(1)
+    sd = O.SigDist(4, oracle=kind_o); sd.integrate(True)
+    pos3 = 0
+    for n in BLOCKS[:30]:
+        blk = np.ascontiguousarray(x[4:8, pos3:pos3 + n]); pos3 += n
+        bm.process(blk); sd.process(blk)
+    for i in (0, 2):
+        h, c, mm, it = bm.read(i)
+        out["bim_hist_%d" % i], out["bim_cnt_%d" % i], out["bim_minmax_%d" % i] = h, c, mm
+        h, mp, av, it = sd.read(i)
+        out["sdh_hist_%d" % i], out["sdh_maxpeak_%d" % i], out["sdh_stats_%d" % i] = h, mp, av
     # 997 Hz / -23 dBFS tone (EBU Tech 3341 case 1)
     s = S.sine(1024 * 300, 997.0, amp=10 ** (-23 / 20)); y = np.ascontiguousarray(np.stack([s, s]))
     e2 = O.Ebu(1, 2, kind=kind); e2.integr("start")

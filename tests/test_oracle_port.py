@@ -111,6 +111,30 @@ def test_needle_meters_port_equals_reference(kind):
     assert np.array_equal(u32(a.peek()), u32(b.peek()))
 
 
+@needs_both
+def test_bitmeter_and_sigdist_port_equals_reference_plugins():
+    """the reference side runs the plugins' own LV2 run() (src/meters.cc compiled unmodified against oracle/lv2stub)"""
+    x = S.nasty(6, sum(BLOCKS), seed=111)
+    x[1] *= np.float32(1e-39); x[2] *= np.float32(3.0); x[3] = 0
+    for avg in (1, 0):
+        a, b = O.Bitmeter(6, oracle="reference"), O.Bitmeter(6, oracle="port")
+        a.mode(avg); b.mode(avg)
+        for blk in _blocks(x, BLOCKS):
+            a.process(blk); b.process(blk)
+            for i in range(6):
+                ra, rb = a.read(i), b.read(i)
+                assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]) and ra[3] == rb[3]
+                assert np.array_equal(ra[2].view(np.uint32), rb[2].view(np.uint32))
+    a, b = O.SigDist(6, oracle="reference"), O.SigDist(6, oracle="port")
+    a.integrate(); b.integrate()
+    for blk in _blocks(x, BLOCKS):
+        a.process(blk); b.process(blk)
+    for i in range(6):
+        ra, rb = a.read(i), b.read(i)
+        assert np.array_equal(ra[0], rb[0]) and np.array_equal(ra[1], rb[1]) and ra[3] == rb[3]
+        assert np.array_equal(ra[2].view(np.uint64), rb[2].view(np.uint64))
+
+
 @needs_port
 def test_port_phasewheel_against_numpy_fft():
     """the FFT restatement (FFTW absent => parity unpinned) is at least a correct DFT of the windowed ring."""
