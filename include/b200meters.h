@@ -148,6 +148,8 @@ int b200m_tpk_read_device (b200m_tpk* h, void* stream);
 int b200m_tpk_results (b200m_tpk* h, b200m_tpk_result* out, void* stream);
 /* TruePeakdsp::reset (:140-145) / Kmeterdsp::reset (kmeterdsp.cc:157-162); chan = -1: all */
 int b200m_tpk_reset (b200m_tpk* h, int32_t chan, void* stream);
+/* Kmeterdsp::reset of every channel only (reset_peaks of the TPnRMS / DR14 plugin, src/dr14.c:241-258) */
+int b200m_tpk_reset_kmeter (b200m_tpk* h, void* stream);
 /* host-designed constants: w[4] = w1 w2 w3 g (truepeakdsp.cc:153-157); ctab[120] = zita table
  * (zita-resampler/resampler-table.cc:52-75, hl=24 np=4 fr=1); km[2] = omega, (float)hold */
 int b200m_tpk_coeffs (const b200m_tpk* h, float w[4], float ctab[120], float km[2]);

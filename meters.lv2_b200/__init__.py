@@ -70,6 +70,7 @@ _PROTOS = {
     "b200m_tpk_read_device": (C.c_int, [_v, _v]),
     "b200m_tpk_results": (C.c_int, [_v, _v, _v]),
     "b200m_tpk_reset": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_tpk_reset_kmeter": (C.c_int, [_v, _v]),
     "b200m_tpk_coeffs": (C.c_int, [_v, _v, _v, _v]),
     "b200m_tpk_state": (C.c_int, [_v, _v, _v, _v, _v, _v, _v, _v]),
     "b200m_tpk_debug_capture": (C.c_int, [_v, C.c_int]),

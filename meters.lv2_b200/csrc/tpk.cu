@@ -643,6 +643,17 @@ int b200m_tpk_reset (b200m_tpk* h, int32_t chan, void* stream)
     return 0;
 }
 
+int b200m_tpk_reset_kmeter (b200m_tpk* h, void* stream)
+{
+    // reset_peaks of the TPnRMS/DR14 plugin resets only its K-meters (src/dr14.c:241-258)
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    DeviceGuard g (h->device);
+    tpk_reset_kernel<<<(h->n_chan + 127) / 128, 128, 0, tpk_stream (h, stream)>>> ((int)h->n_chan, -1, h->flags & B200M_TPK_KMETER, h->st);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
 int b200m_tpk_coeffs (const b200m_tpk* h, float w[4], float ctab[120], float km[2])
 {
     if (!h) return set_err (B200M_E_INVAL, "NULL handle");

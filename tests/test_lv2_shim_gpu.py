@@ -1,6 +1,8 @@
-"""GPU: the per-instance LV2 façade (lv2_descriptor / instantiate / connect_port / run / cleanup) driven the way
-an LV2 host drives meters.so (robtk/jackwrap.c:531-544), compared with the oracle DSP objects plus the reference's
-port glue (src/meters.cc:333-536, src/spectrumlv2.c:159-257) restated inline."""
+"""GPU: the per-instance LV2 façade (lv2_descriptor / instantiate / connect_port / run / cleanup) of libb200meters.so
+driven side by side with the REFERENCE plugins (oracle/_ref exports the reference's own lv2_descriptor: src/meters.cc
+compiled unmodified), the way an LV2 host drives meters.so (robtk/jackwrap.c:531-544).  Every control-port value must
+be bit-identical after every run(); cycles in which the reference emits rand()-based "force a parameter change"
+values are compared by their sign/threshold only."""
 import ctypes as C
 
 import numpy as np
@@ -17,8 +19,19 @@ class Desc(C.Structure):
     pass
 
 
+class Feature(C.Structure):
+    _fields_ = [("URI", C.c_char_p), ("data", C.c_void_p)]
+
+
+MAPFN = C.CFUNCTYPE(C.c_uint32, C.c_void_p, C.c_char_p)
+
+
+class UridMap(C.Structure):
+    _fields_ = [("handle", C.c_void_p), ("map", MAPFN)]
+
+
 Desc._fields_ = [("URI", C.c_char_p),
-                 ("instantiate", C.CFUNCTYPE(C.c_void_p, C.POINTER(Desc), C.c_double, C.c_char_p, C.c_void_p)),
+                 ("instantiate", C.CFUNCTYPE(C.c_void_p, C.POINTER(Desc), C.c_double, C.c_char_p, C.POINTER(C.POINTER(Feature)))),
                  ("connect_port", C.CFUNCTYPE(None, C.c_void_p, C.c_uint32, C.c_void_p)),
                  ("activate", C.c_void_p),
                  ("run", C.CFUNCTYPE(None, C.c_void_p, C.c_uint32)),
@@ -26,10 +39,23 @@ Desc._fields_ = [("URI", C.c_char_p),
                  ("cleanup", C.CFUNCTYPE(None, C.c_void_p)),
                  ("extension_data", C.c_void_p)]
 
+_uris = []
 
-def descriptors():
-    import meters_lv2_b200 as B
-    L = C.CDLL(B.LIB_PATH)
+
+@MAPFN
+def _map(handle, uri):
+    if uri not in _uris:
+        _uris.append(uri)
+    return _uris.index(uri) + 1
+
+
+_urid_map = UridMap(None, _map)
+_feat = Feature(b"http://lv2plug.in/ns/ext/urid#map", C.cast(C.pointer(_urid_map), C.c_void_p))
+_feats = (C.POINTER(Feature) * 2)(C.pointer(_feat), None)
+
+
+def descriptors(path):
+    L = C.CDLL(path)
     L.lv2_descriptor.restype = C.POINTER(Desc); L.lv2_descriptor.argtypes = [C.c_uint32]
     out, i = {}, 0
     while True:
@@ -38,18 +64,18 @@ def descriptors():
             break
         out[d.contents.URI[len(URI):].decode()] = d
         i += 1
-    return out
+    return out, L
 
 
 class Plugin:
     def __init__(self, d, rate=48000.0):
         self.d = d.contents
-        self.h = self.d.instantiate(d, rate, b"", None)
+        self.h = self.d.instantiate(d, rate, b"", _feats)
         assert self.h
-        self.bufs = {}
+        self.keep = {}
 
     def port(self, idx, arr):
-        self.bufs[idx] = arr
+        self.keep[idx] = arr
         self.d.connect_port(self.h, idx, arr.ctypes.data_as(C.c_void_p))
 
     def run(self, n):
@@ -63,66 +89,144 @@ def u32(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
+def _pair(name):
+    import meters_lv2_b200 as B
+    mine, l1 = descriptors(B.LIB_PATH)
+    ref, l2 = descriptors(O.PATHS["reference"])
+    return Plugin(mine[name]), Plugin(ref[name]), (l1, l2)
+
+
 def test_descriptor_table():
-    d = descriptors()
+    import meters_lv2_b200 as B
+    d, _ = descriptors(B.LIB_PATH)
     assert set(d) == {"COR", "spectr30mono", "spectr30stereo", "dBTPmono", "dBTPstereo", "K12mono", "K14mono", "K20mono",
-                      "K12stereo", "K14stereo", "K20stereo"}
+                      "K12stereo", "K14stereo", "K20stereo", "TPnRMSmono", "TPnRMSstereo", "BBCM6"} | {
+                          k + c for k in ("VU", "BBC", "EBU", "DIN", "NOR") for c in ("mono", "stereo")}
+    r, _ = descriptors(O.PATHS["reference"])
+    assert set(d) <= set(r) and len(r) == 38          # src/meters.cc:745-792
 
 
-def test_k20stereo_and_dbtp_and_cor_ports():
-    d = descriptors()
-    x = S.white(2, 1024 * 20, seed=91)
-    ctl = {k: np.zeros(1, np.float32) for k in range(10)}
-    # K20stereo: 0 ref, 1 in0, 2 out0, 3 level0, 4 in1, 5 out1, 6 level1, 7 peak0, 8 peak1, 9 hold
-    k = Plugin(d["K20stereo"]); t = Plugin(d["dBTPstereo"]); c = Plugin(d["COR"])
-    ports = {}
-    for name, p in (("k", k), ("t", t), ("c", c)):
-        ports[name] = {i: np.zeros(1, np.float32) for i in (0, 3, 6, 7, 8, 9)}
-        for i, a in ports[name].items():
-            p.port(i, a)
-    ok = O.Kmeter(2); ot = O.TruePeak(2); oc = O.Stcorr(1)
-    hold = 0.0; pmax = np.zeros(2, np.float32)
-    for b in range(20):
-        l = np.ascontiguousarray(x[0, b * 1024:(b + 1) * 1024]); r = np.ascontiguousarray(x[1, b * 1024:(b + 1) * 1024])
-        for p in (k, t, c):
-            p.port(1, l); p.port(2, l); p.port(4, r); p.port(5, r)       # in-place: out == in
+def _run_needle_family(name, ctl_ports, nch, script):
+    """ports 0..9 layout of src/meters.cc:59-70; `script` maps block index -> value written to port 0 (ref level)"""
+    g, r, keep = _pair(name)
+    x = S.white(2, 1024 * 24, seed=91)
+    gp = {i: np.zeros(1, np.float32) for i in ctl_ports}; rp = {i: np.zeros(1, np.float32) for i in ctl_ports}
+    for i in ctl_ports:
+        g.port(i, gp[i]); r.port(i, rp[i])
+    for b in range(24):
+        if b in script:
+            gp[0][0] = rp[0][0] = script[b]
+        bufs = [np.ascontiguousarray(x[c, b * 1024:(b + 1) * 1024]) for c in range(2)]
+        for p, cp in ((g, gp), (r, rp)):
+            mine = [a.copy() for a in bufs]
+            p.port(1, mine[0]); p.port(2, mine[0])
+            if nch == 2:
+                p.port(4, mine[1]); p.port(5, mine[1])
             p.run(1024)
-        blk = np.ascontiguousarray(x[:, b * 1024:(b + 1) * 1024])
-        ok.process(blk); ot.process(blk); oc.process(blk)
-        assert u32(ports["c"][3])[0] == u32(oc.read())[0]
-        if b == 0:
-            # p_refl starts at -9999 != *ref (0): the first run() of the dBTP / K-meter plugins is a peak-reset handshake
-            # cycle: reset, process, force a port change, return WITHOUT read() (src/meters.cc:339-357,381-389,444-489)
-            assert ports["k"][9][0] <= -1.0 and ports["t"][3][0] <= -500.0
-            continue
-        rms, pk = ok.read(); m, pp = ot.read()
-        hold = max(hold, float(pk.max())); pmax = np.maximum(pmax, pp)
-        assert u32(ports["k"][3])[0] == u32(rms[:1])[0] and u32(ports["k"][6])[0] == u32(rms[1:])[0]
-        assert u32(ports["k"][7])[0] == u32(pk[:1])[0] and u32(ports["k"][8])[0] == u32(pk[1:])[0]
-        assert ports["k"][9][0] == np.float32(hold)
-        assert u32(ports["t"][3])[0] == u32(m[:1])[0] and u32(ports["t"][6])[0] == u32(m[1:])[0]
-        assert u32(ports["t"][7])[0] == u32(pmax[:1])[0] and u32(ports["t"][8])[0] == u32(pmax[1:])[0]
-    # peak-reset handshake (port 0 re-used, src/meters.cc:339-357): |ref| < 3 resets, ports get a forced change
-    ports["k"][0][0] = 1.0
-    k.run(1024)
-    assert ports["k"][9][0] <= -1.0
-    for p in (k, t, c):
-        p.close()
+        for i in ctl_ports[1:]:
+            a, bb = gp[i][0], rp[i][0]
+            if bb <= -1.0 and (bb != np.floor(bb) or bb < -1.5):       # rand()-based forced change: same regime only
+                assert a <= -1.0, (name, b, i, a, bb)
+            else:
+                assert u32(gp[i])[0] == u32(rp[i])[0], (name, b, i, a, bb)
+    g.close(); r.close()
 
 
-def test_spectr30stereo_ports():
-    d = descriptors()
-    x = S.white(2, 1024 * 6, seed=92)
-    p = Plugin(d["spectr30stereo"])
-    out = np.zeros(60, np.float32); spd = np.ones(1, np.float32); rst = np.full(1, -4.0, np.float32); amp = np.zeros(1, np.float32)
-    for i in range(60):
-        p.d.connect_port(p.h, i, out[i:i + 1].ctypes.data_as(C.c_void_p))
-    p.port(60, spd); p.port(61, rst); p.port(62, amp)
-    o = O.Spectr30(1, 2)
-    for b in range(6):
-        l = np.ascontiguousarray(x[0, b * 1024:(b + 1) * 1024]); r = np.ascontiguousarray(x[1, b * 1024:(b + 1) * 1024])
-        p.port(64, l); p.port(65, l); p.port(66, r); p.port(67, r)
-        p.run(1024)
-        o.process(np.ascontiguousarray(x[:, b * 1024:(b + 1) * 1024]))
-        assert np.array_equal(u32(out), u32(o.read()[0]))
-    p.close()
+def test_kmeter_and_dbtp_plugins_vs_reference_plugins():
+    script = {12: 1.0, 13: 3.0, 14: 4.0, 18: -3.0, 19: 0.5}              # peak-reset handshake values on port 0
+    _run_needle_family("K20stereo", [0, 3, 6, 7, 8, 9], 2, script)
+    _run_needle_family("K14stereo", [0, 3, 6, 7, 8, 9], 2, {})
+    _run_needle_family("dBTPstereo", [0, 3, 6, 7, 8], 2, script)
+    _run_needle_family("K20mono", [0, 3, 4, 5], 1, script)                 # mono: ports 4, 5 re-used for peak / hold
+    _run_needle_family("dBTPmono", [0, 3, 4], 1, script)
+
+
+@pytest.mark.parametrize("name", ["VUstereo", "BBCstereo", "EBUmono", "DINstereo", "NORmono", "BBCM6"])
+def test_needle_plugins_vs_reference_plugins(name):
+    g, r, keep = _pair(name)
+    x = S.white(2, 1024 * 14, seed=95) * np.float32(2.0)
+    nch = 1 if name.endswith("mono") else 2
+    cps = [0, 3, 6, 7]
+    gp = {i: np.zeros(1, np.float32) for i in cps}; rp = {i: np.zeros(1, np.float32) for i in cps}
+    for i in cps:
+        g.port(i, gp[i]); r.port(i, rp[i])
+    for b in range(14):
+        if b == 5:
+            gp[0][0] = rp[0][0] = -18.0                                      # reference level -> rlgain
+        if b == 9:
+            gp[7][0] = rp[7][0] = 1.0                                        # BBCM6: port 7 > 0.5 -> S meter +14 dB
+        for p in (g, r):
+            a = np.ascontiguousarray(x[0, b * 1024:(b + 1) * 1024]); c = np.ascontiguousarray(x[1, b * 1024:(b + 1) * 1024])
+            p.port(1, a); p.port(2, a)
+            if nch == 2:
+                p.port(4, c); p.port(5, c)
+            p.run(1024)
+        assert u32(gp[3])[0] == u32(rp[3])[0], (name, b, gp[3][0], rp[3][0])
+        if nch == 2:
+            assert u32(gp[6])[0] == u32(rp[6])[0], (name, b, gp[6][0], rp[6][0])
+    g.close(); r.close()
+
+
+def test_cor_plugin_vs_reference_plugin():
+    g, r, keep = _pair("COR")
+    x = S.white(2, 1024 * 10, seed=93); x[1] = 0.5 * x[0] + 0.5 * x[1]
+    gl, rl = np.zeros(1, np.float32), np.zeros(1, np.float32)
+    g.port(3, gl); r.port(3, rl)
+    for b in range(10):
+        for p in (g, r):
+            a = np.ascontiguousarray(x[0, b * 1024:(b + 1) * 1024]); c = np.ascontiguousarray(x[1, b * 1024:(b + 1) * 1024])
+            o1, o2 = np.empty_like(a), np.empty_like(c)                     # out != in: pass-through copy
+            p.port(1, a); p.port(2, o1); p.port(4, c); p.port(5, o2)
+            p.run(1024)
+            assert np.array_equal(o1, a) and np.array_equal(o2, c)
+        assert u32(gl)[0] == u32(rl)[0]
+    g.close(); r.close()
+
+
+def test_spectr30_plugin_vs_reference_plugin():
+    g, r, keep = _pair("spectr30stereo")
+    x = S.white(2, 1024 * 8, seed=92)
+    outs = []
+    for p in (g, r):
+        out = np.zeros(60, np.float32); spd = np.ones(1, np.float32); rst = np.full(1, -4.0, np.float32); amp = np.zeros(1, np.float32)
+        for i in range(60):
+            p.d.connect_port(p.h, i, out[i:i + 1].ctypes.data_as(C.c_void_p))
+        p.port(60, spd); p.port(61, rst); p.port(62, amp)
+        outs.append((out, spd, rst))
+    for b in range(8):
+        if b == 4:
+            for o in outs:
+                o[1][0] = 3.0                                               # speed change: resets the peak hold (rst_h = 0)
+        for p in (g, r):
+            a = np.ascontiguousarray(x[0, b * 1024:(b + 1) * 1024]); c = np.ascontiguousarray(x[1, b * 1024:(b + 1) * 1024])
+            p.port(64, a); p.port(65, a); p.port(66, c); p.port(67, c)
+            p.run(1024)
+        go, ro = outs[0][0], outs[1][0]
+        assert np.array_equal(u32(go[:30]), u32(ro[:30])), b
+        pend = ro[30:] <= -500
+        assert np.array_equal(pend, go[30:] <= -500) and np.array_equal(u32(go[30:][~pend]), u32(ro[30:][~pend])), b
+    g.close(); r.close()
+
+
+def test_tpnrms_plugin_vs_reference_plugin():
+    g, r, keep = _pair("TPnRMSstereo")
+    x = S.white(2, 1024 * 16, seed=94); x[0, 3000:3010] = 0.0
+    ports = []
+    seq = np.zeros(4, np.uint32)                                            # empty LV2 atom sequence: {size = 8, type, unit, pad}
+    seq[0] = 8
+    for p in (g, r):
+        ctl = {i: np.zeros(1, np.float32) for i in (1, 2, 3, 6, 7, 8, 9, 10, 13, 14, 15, 16, 17, 18)}
+        for i, a in ctl.items():
+            p.port(i, a)
+        p.port(0, seq)
+        ports.append(ctl)
+    for b in range(16):
+        for ctl in ports:
+            ctl[2][0] = 1.0 if b == 9 else 0.0                              # reset button
+        for p in (g, r):
+            a = np.ascontiguousarray(x[0, b * 1024:(b + 1) * 1024]); c = np.ascontiguousarray(x[1, b * 1024:(b + 1) * 1024])
+            p.port(4, a); p.port(5, a); p.port(11, c); p.port(12, c)
+            p.run(1024)
+        for i in (3, 6, 7, 8, 9, 13, 14, 15, 16):
+            assert u32(ports[0][i])[0] == u32(ports[1][i])[0], (b, i, ports[0][i][0], ports[1][i][0])
+    g.close(); r.close()
