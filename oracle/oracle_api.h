@@ -58,6 +58,13 @@ void  orc_tp_upsample (float fsamp, const float* in, int n, int block, float* ou
  * and repeated for `nblocks` consecutive blocks (block b starts at in + b*nfram): the CPU baseline of bench.py */
 void  orc_r128_cycle  (void* ebu, void* tp, const float* in, size_t stride, int nfram, int nblocks, int nthreads);
 
+/* the EBUr128 PLUGIN itself (kind "reference" only; port returns NULL): n instances driven through ebur128_run,
+ * integration started and dBTP enabled as the UI would; out = [n][10]: the nine getters + tp_max (dBTP hold) */
+void* orc_ebuplug_create (int n, float rate, int dbtp);
+void  orc_ebuplug_destroy (void* h);
+void  orc_ebuplug_run (void* h, const float* in, size_t stride, int nfram, int nthreads);
+void  orc_ebuplug_read (void* h, float* out10);
+
 /* ---- K-meter (jmeters/kmeterdsp.h:27-62) ---- */
 void* orc_km_create   (int n, float fsamp);
 void  orc_km_destroy  (void* h);

@@ -743,6 +743,10 @@ void orc_spec_state (void* h, int inst, double* z, float* v, float* m) {
 }
 void orc_spec_coeffs (void* h, double* W) { const Spec& s = ((Bank<Spec>*)h)->v[0]; for (int b = 0; b < 30; ++b) for (int q = 0; q < 6; ++q) for (int k = 0; k < 6; ++k) W[(b * 6 + q) * 6 + k] = s.flt[b].f[q].W[k]; }
 
+void* orc_ebuplug_create (int, float, int) { return 0; }       // the plugin glue itself exists only as the reference build
+void  orc_ebuplug_destroy (void*) {}
+void  orc_ebuplug_run (void*, const float*, size_t, int, int) {}
+void  orc_ebuplug_read (void*, float*) {}
 void* orc_bim_create (int n, float rate) { auto* b = new Bank<Bim>; b->n = n; b->v.resize (n); for (auto& m : b->v) m.init (rate); return b; }
 void  orc_bim_destroy (void* h) { delete (Bank<Bim>*)h; }
 void  orc_bim_mode (void* h, int average, int integrating) { for (auto& m : ((Bank<Bim>*)h)->v) { m.average = average; m.integrating = integrating; } }

@@ -87,4 +87,21 @@ void refsdh_snapshot (void* vp, int32_t* hist361, int32_t* maxpeak2, double* avg
     avgtmpvar3[0] = m->hist_avgS; avgtmpvar3[1] = m->hist_tmpS; avgtmpvar3[2] = m->hist_varS; *itime = (int64_t)m->integration_time;
 }
 
+/* EBUr128 (src/ebulv2.cc): the UI's CTL_START / dBTP-enable messages are applied directly to the instance, the audio
+ * cycle then runs through the plugin's own ebur128_run; results are read back from the instance */
+void refebu_ctl (void* vp, int integrate, int dbtp)
+{
+    LV2meter* m = (LV2meter*)((RefPlug*)vp)->h;
+    if (integrate && !m->ebu_integrating) { m->ebu->integr_start (); m->ebu_integrating = true; }
+    if (!integrate && m->ebu_integrating) { m->ebu->integr_pause (); m->ebu_integrating = false; }
+    m->dbtp_enable = dbtp != 0;
+}
+void refebu_snapshot (void* vp, float* out10)
+{
+    LV2meter* m = (LV2meter*)((RefPlug*)vp)->h;
+    out10[0] = m->ebu->loudness_M (); out10[1] = m->ebu->maxloudn_M (); out10[2] = m->ebu->loudness_S (); out10[3] = m->ebu->maxloudn_S ();
+    out10[4] = m->ebu->integrated (); out10[5] = m->ebu->integ_thr (); out10[6] = m->ebu->range_min (); out10[7] = m->ebu->range_max ();
+    out10[8] = m->ebu->range_thr (); out10[9] = m->tp_max;
+}
+
 }  // extern "C"

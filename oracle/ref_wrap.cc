@@ -355,6 +355,26 @@ static void plug_process (void* h, const float* in, size_t stride, int nfram, in
         }
     });
 }
+void  refebu_ctl (void*, int integrate, int dbtp);
+void  refebu_snapshot (void*, float*);
+void* orc_ebuplug_create (int n, float rate, int dbtp)
+{
+    PlugB* b = (PlugB*)plug_create (n, "EBUr128", rate);
+    if (b) for (auto p : b->p) refebu_ctl (p, 1, dbtp);
+    return b;
+}
+void  orc_ebuplug_run (void* h, const float* in, size_t stride, int nfram, int nthreads)
+{
+    PlugB* b = (PlugB*)h;                         /* EBUr128 ports: 2 inL 3 outL 4 inR 5 outR (src/ebulv2.cc:31-38) */
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            float* l = const_cast<float*> (in + (size_t)(2 * i) * stride); float* r = l + stride;
+            refplug_connect (b->p[i], 2, l); refplug_connect (b->p[i], 3, l); refplug_connect (b->p[i], 4, r); refplug_connect (b->p[i], 5, r);
+            refplug_run (b->p[i], (uint32_t)nfram);
+        }
+    });
+}
+void  orc_ebuplug_read (void* h, float* out) { PlugB* b = (PlugB*)h; for (int i = 0; i < b->n; ++i) refebu_snapshot (b->p[i], out + 10 * i); }
 void* orc_bim_create (int n, float rate) { return plug_create (n, "bitmeter", rate); }
 void  orc_bim_destroy (void* h) { PlugB* b = (PlugB*)h; for (auto p : b->p) refplug_free (p); delete b; }
 void  orc_bim_mode (void* h, int average, int integrating) { PlugB* b = (PlugB*)h; for (auto p : b->p) refbim_mode (p, average, integrating); }
@@ -362,6 +382,7 @@ void  orc_bim_process (void* h, const float* in, size_t stride, int nfram, int n
 void  orc_bim_read (void* h, int inst, int32_t* hist, int32_t* cnt5, float* mm, int64_t* it) { refbim_snapshot (((PlugB*)h)->p[inst], hist, cnt5, mm, it); }
 void* orc_sdh_create (int n, float rate) { return plug_create (n, "SigDistHist", rate); }
 void  orc_sdh_destroy (void* h) { orc_bim_destroy (h); }
+void  orc_ebuplug_destroy (void* h) { orc_bim_destroy (h); }
 void  orc_sdh_integrate (void* h, int on) { PlugB* b = (PlugB*)h; for (auto p : b->p) refsdh_integrate (p, on); }
 void  orc_sdh_process (void* h, const float* in, size_t stride, int nfram, int nthreads) { plug_process (h, in, stride, nfram, nthreads); }
 void  orc_sdh_read (void* h, int inst, int32_t* hist, int32_t* mp, double* av, int64_t* it) { refsdh_snapshot (((PlugB*)h)->p[inst], hist, mp, av, it); }

@@ -59,6 +59,10 @@ def _proto(lib):
         "orc_ppm_peek": (None, [_v, _v]),
         "orc_ppm_set_gain": (None, [_v, C.c_float, C.c_float]),
         "orc_ppm_coeffs": (None, [_v, _v]),
+        "orc_ebuplug_create": (_v, [C.c_int, C.c_float, C.c_int]),
+        "orc_ebuplug_destroy": (None, [_v]),
+        "orc_ebuplug_run": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int]),
+        "orc_ebuplug_read": (None, [_v, _v]),
         "orc_bim_create": (_v, [C.c_int, C.c_float]),
         "orc_bim_destroy": (None, [_v]),
         "orc_bim_mode": (None, [_v, C.c_int, C.c_int]),
@@ -277,6 +281,29 @@ class Needle:
         w = np.empty(4, np.float32)
         self.L.orc_ppm_coeffs(self.h, ptr(w))
         return w
+
+
+class EbuPlugin:
+    """the reference's EBUr128 plugin run through its own ebur128_run (reference build only)"""
+
+    def __init__(self, n, rate=48000.0, dbtp=True):
+        self.L = load("reference"); self.n = n
+        self.h = self.L.orc_ebuplug_create(n, rate, int(dbtp))
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_ebuplug_destroy(self.h); self.h = None
+
+    def run(self, x, nthreads=1):
+        p, s = planar(x)
+        assert x.shape[0] == 2 * self.n
+        self.L.orc_ebuplug_run(self.h, p, s, x.shape[1], nthreads)
+
+    def read(self):
+        o = np.empty((self.n, 10), np.float32)
+        self.L.orc_ebuplug_read(self.h, ptr(o))
+        return o
 
 
 class Bitmeter:
