@@ -78,7 +78,7 @@ class ClockSampler(threading.Thread):
                         self.reasons.add(k)
             except Exception:
                 pass
-            time.sleep(0.02)
+            time.sleep(0.004)
 
     def summary(self):
         if not self.sm:
