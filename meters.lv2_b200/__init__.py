@@ -225,6 +225,19 @@ def design_spec(rate):
     return W
 
 
+def host_alloc(rows, cols):
+    """[rows, cols] float32 numpy array in pinned host memory from b200m_host_alloc (placed on the GPU-local NUMA node);
+    freed with b200m_host_free when the array is garbage-collected."""
+    import weakref
+    p = _v()
+    nbytes = int(rows) * int(cols) * 4
+    _ck(lib().b200m_host_alloc(C.byref(p), nbytes))
+    buf = (C.c_float * (int(rows) * int(cols))).from_address(p.value)
+    a = np.frombuffer(buf, dtype=np.float32).reshape(int(rows), int(cols))
+    weakref.finalize(buf, lib().b200m_host_free, _v(p.value))
+    return a
+
+
 def peak_probe(kind, device=0):
     """kind 0: fp32 unfused mul+add, kind 1: fp64; returns 1e9 lane-ops/s measured on the device."""
     v = C.c_double(0)

@@ -1,5 +1,10 @@
 // host_common.cu — error reporting, launch accounting and pinned-memory helpers of the C ABI.
+#include <ctype.h>
+#include <sched.h>
 #include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
 
 namespace b200m {
@@ -49,10 +54,47 @@ int b200m_device_count (void)
     return n;
 }
 
+// Pinned staging memory should sit on the NUMA node the GPU hangs off: a buffer on the other socket halves the H2D rate
+// (the copy crosses the inter-socket link).  Pages are placed where the allocating thread runs (first touch), so the
+// calling thread is moved onto the GPU-local CPUs for the duration of the allocation.  B200M_NUMA_BIND=0 disables this.
+static bool gpu_local_cpus (cpu_set_t* set)
+{
+    int dev = 0; char bus[32] = {0};
+    if (cudaGetDevice (&dev) != cudaSuccess || cudaDeviceGetPCIBusId (bus, sizeof (bus), dev) != cudaSuccess) return false;
+    for (char* c = bus; *c; ++c) *c = (char)tolower (*c);
+    char path[128]; snprintf (path, sizeof (path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* f = fopen (path, "r");
+    if (!f) return false;
+    char line[1024] = {0};
+    const bool got = fgets (line, sizeof (line), f) != nullptr;
+    fclose (f);
+    if (!got) return false;
+    CPU_ZERO (set);
+    int n = 0;
+    for (char* tok = strtok (line, ",\n"); tok; tok = strtok (nullptr, ",\n")) {      // "0-31,64-95"
+        int a = 0, b = 0;
+        const int k = sscanf (tok, "%d-%d", &a, &b);
+        if (k < 1) continue;
+        if (k == 1) b = a;
+        for (int c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET (c, set); ++n; }
+    }
+    return n > 0;
+}
+
 int b200m_host_alloc (void** p, size_t bytes)
 {
     if (!p) return set_err (B200M_E_INVAL, "NULL out pointer");
-    B200M_CUDA (cudaHostAlloc (p, bytes, cudaHostAllocDefault));
+    cpu_set_t old_set, local;
+    bool moved = false;
+    const char* v = getenv ("B200M_NUMA_BIND");
+    if (!(v && atoi (v) == 0) && sched_getaffinity (0, sizeof (old_set), &old_set) == 0 && gpu_local_cpus (&local)) {
+        cpu_set_t both;
+        CPU_AND (&both, &old_set, &local);                      // never leave the set the caller was confined to
+        if (CPU_COUNT (&both) > 0) moved = sched_setaffinity (0, sizeof (both), &both) == 0;
+    }
+    const cudaError_t e = cudaHostAlloc (p, bytes, cudaHostAllocDefault);
+    if (moved) sched_setaffinity (0, sizeof (old_set), &old_set);
+    B200M_CUDA (e);
     return 0;
 }
 

@@ -168,11 +168,66 @@ B200M_DEV float zita_lit (int i)
 }
 static const float h_zita_lit[120] = {0x1.0e8cc60000000p-65f, -0x1.f4da040000000p-63f, -0x1.1ecee20000000p-64f, -0x1.9d9bde0000000p-62f, 0x1.f84c660000000p-60f, -0x1.5e4cb20000000p-60f, -0x1.9321ea0000000p-60f, -0x1.b534440000000p-59f, 0x1.d2d4d80000000p-57f, -0x1.bb55ce0000000p-58f, -0x1.6e155a0000000p-57f, -0x1.816e140000000p-57f, 0x1.b8ff340000000p-55f, -0x1.28f2680000000p-56f, 0x1.62bccc0000000p-56f, -0x1.9e31840000000p-56f, 0x1.d96a6a0000000p-56f, -0x1.092e9c0000000p-55f, 0x1.237b360000000p-55f, -0x1.3a9ac60000000p-55f, 0x1.4da4960000000p-55f, -0x1.5bd4640000000p-55f, 0x1.6495740000000p-55f, 0x1.0000000000000p+0f, -0x1.d0758c0000000p-20f, 0x1.74f3c80000000p-17f, -0x1.21b2780000000p-15f, 0x1.5cf90e0000000p-14f, -0x1.6c77cc0000000p-13f, 0x1.58b43e0000000p-12f, -0x1.2e2f240000000p-11f, 0x1.f29ba20000000p-11f, -0x1.87672e0000000p-10f, 0x1.26d2d00000000p-9f, -0x1.ad12540000000p-9f, 0x1.2f4f900000000p-8f, -0x1.a293f80000000p-8f, 0x1.1b24ca0000000p-7f, -0x1.7912360000000p-7f, 0x1.f0635e0000000p-7f, -0x1.447e240000000p-6f, 0x1.a7c41a0000000p-6f, -0x1.168e760000000p-5f, 0x1.7511480000000p-5f, -0x1.03d1200000000p-4f, 0x1.88e9740000000p-4f, -0x1.6c09600000000p-3f, 0x1.ccb95c0000000p-1f, -0x1.1c1fd00000000p-20f, 0x1.7106020000000p-17f, -0x1.3e6cae0000000p-15f, 0x1.927a360000000p-14f, -0x1.b144fc0000000p-13f, 0x1.a2f3160000000p-12f, -0x1.75b1180000000p-11f, 0x1.38a6c40000000p-10f, -0x1.f0902a0000000p-10f, 0x1.79a7c20000000p-9f, -0x1.1509ce0000000p-8f, 0x1.8a56220000000p-8f, -0x1.11a21c0000000p-7f, 0x1.73e48e0000000p-7f, -0x1.f1065a0000000p-7f, 0x1.47f5e80000000p-6f, -0x1.ad4f620000000p-6f, 0x1.183a9a0000000p-5f, -0x1.6f76720000000p-5f, 0x1.e924540000000p-5f, -0x1.50663a0000000p-4f, 0x1.ef2dda0000000p-4f, -0x1.aa96140000000p-3f, 0x1.4546e40000000p-1f, -0x1.89a1500000000p-23f, 0x1.5abb860000000p-18f, -0x1.57d15a0000000p-16f, 0x1.cbb6c20000000p-15f, -0x1.ffab940000000p-14f, 0x1.faa5820000000p-13f, -0x1.cc49100000000p-12f, 0x1.86d2e80000000p-11f, -0x1.3a24580000000p-10f, 0x1.e2abfe0000000p-10f, -0x1.65134e0000000p-9f, 0x1.ffdecc0000000p-9f, -0x1.654aee0000000p-8f, 0x1.e7f28c0000000p-8f, -0x1.474f580000000p-7f, 0x1.b124380000000p-7f, -0x1.1bf13a0000000p-6f, 0x1.72b7c40000000p-6f, -0x1.e52f3e0000000p-6f, 0x1.414ca20000000p-5f, -0x1.b5509c0000000p-5f, 0x1.3ad9d40000000p-4f, -0x1.00d0b60000000p-3f, 0x1.31e2140000000p-2f, -0x0.0p+0f, 0x1.0e8cc60000000p-65f, -0x1.f4da040000000p-63f, -0x1.1ecee20000000p-64f, -0x1.9d9bde0000000p-62f, 0x1.f84c660000000p-60f, -0x1.5e4cb20000000p-60f, -0x1.9321ea0000000p-60f, -0x1.b534440000000p-59f, 0x1.d2d4d80000000p-57f, -0x1.bb55ce0000000p-58f, -0x1.6e155a0000000p-57f, -0x1.816e140000000p-57f, 0x1.b8ff340000000p-55f, -0x1.28f2680000000p-56f, 0x1.62bccc0000000p-56f, -0x1.9e31840000000p-56f, 0x1.d96a6a0000000p-56f, -0x1.092e9c0000000p-55f, 0x1.237b360000000p-55f, -0x1.3a9ac60000000p-55f, 0x1.4da4960000000p-55f, -0x1.5bd4640000000p-55f, 0x1.6495740000000p-55f};
 
+// Phase 0 of the zita table is a unit tap (tab[23] = 1.0f) among 46 taps of magnitude <= 1.73 * 2^-55 (plus one -0.0f);
+// the 46 magnitudes sum to S = 7.7035e-16.  Its output is therefore x[k-24] itself whenever the tiny products and the
+// +-1e-20f bias are too small to move any partial sum off x[k-24].  Sufficient condition used here, for the window
+// maximum M >= max |w[j]| (NaN-propagating; taken over the whole chunk row, see row_absmax):
+//     |x| > 1.25e-7 * M + 1e-12        (then x is normal and M finite)       or       M == 0 (silent row: output +0)
+// Proof: the unit tap is the last pair (i = 23).  Every partial sum before it is bounded by
+// A = (1e-20 + S * M) * (1 + 2^-18) < 1.0001e-20 + 7.71e-16 * M, and so is the other product of the last pair.  With
+// 2^e <= |x| < 2^(e+1): A < |x| * 2^-26 < 2^(e-25) = half of the smallest gap next to x, so fl(x + tiny) = x,
+// fl(acc + x) = x and fl(x - 1e-20f) = x under round-to-nearest.  |x| * 2^-26 > A  <=>  |x| > 6.72e-13 + 5.18e-8 * M;
+// the guard's constants leave 2.4x / 1.5x of margin over that, far more than the rounding of the guard itself.
+// Non-finite samples make M NaN/Inf and fail the test, so such windows take the full evaluation (NaN/Inf propagate
+// exactly as in the reference).  b200m_tpk_create enables the shortcut only after checking tab[23] == 1 and S against
+// the table it actually computed.  Checked offline on 2e8 random / adversarial windows (0 mismatches) and by
+// tests/test_tpk_gpu.py::test_phase0_guard_* on both sides of the guard.
+B200M_DEV float max3_abs_nan (float a, float b, float c)
+{
+    float d;
+    asm ("max.NaN.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(fabsf (a)), "f"(fabsf (b)), "f"(fabsf (c)));   // FMNMX3.NAN |a|,|b|,|c|
+    return d;
+}
+
+// |x| maximum (NaN-propagating) of one shared-memory row of NV float4, computed by the SEG lanes of the warp that work on
+// that row; every lane of the segment returns the same M.  M covers more than the 48 taps a sample needs (the whole
+// chunk + its 48-sample prefix), which only makes the guard more conservative.
+template <int SEG, int NV>
+B200M_DEV float row_absmax (const float4* __restrict__ row, int lane)
+{
+    float mx = 0.0f;
+#pragma unroll
+    for (int j0 = 0; j0 < NV; j0 += SEG) {
+        const int j = j0 + (lane & (SEG - 1));
+        if (j0 + SEG <= NV || j < NV) { const float4 v = row[j]; mx = max3_abs_nan (max3_abs_nan (v.x, v.y, v.z), v.w, mx); }
+    }
+    // mx >= +0 or NaN (0x7fffffff): unsigned order == float order with NaN on top
+    const unsigned segmask = SEG == 32 ? 0xffffffffu : (((1u << SEG) - 1u) << (lane & ~(SEG - 1)));
+    return __uint_as_float (__reduce_max_sync (segmask, __float_as_uint (mx)));
+}
+
+B200M_DEV bool phase0_is_delay (const float4 x, const float M)
+{
+    // M == 0: the whole row is +-0 and the full evaluation yields (1e-20f + 0) - 1e-20f = +0 (digital silence stays fast)
+    const float thr = __fadd_rn (__fmul_rn (M, 1.25e-7f), 1e-12f);
+    return (fabsf (x.x) > thr && fabsf (x.y) > thr && fabsf (x.z) > thr && fabsf (x.w) > thr) || M == 0.0f;
+}
+
 // 16 outputs (4 input positions x 4 phases) from a 52-sample window; w[j] = x[kb-48+j].
 // out[4k+ph] = (1e-20f + sum_i (x[k-47+i]*c1[i] + x[k-i]*c2[i])) - 1e-20f, pair-sum first, i ascending
 // (resampler.cc:213-230 with c1 = ctab + hl*ph, c2 = ctab + hl*(np-ph)).
+// `full0` (warp-uniform) = evaluate phase 0 as well; otherwise phase 0 is the proven pure delay (see above).  The
+// full evaluation re-reads its window from shared memory (`xw`, volatile so that the loads are not merged with the
+// ones feeding `w`): keeping `w` alive across the branch instead costs ~40 registers and a third of the occupancy.
+B200M_DEV float lds_volatile (const float* p)
+{
+    float v;
+    asm volatile ("ld.volatile.shared.f32 %0, [%1];" : "=f"(v) : "r"((unsigned)__cvta_generic_to_shared (p)));
+    return v;
+}
+
 template <bool IMM>
-B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
+B200M_DEV void fir16 (const float (&w)[52], const float* xw, float (&o)[16], const bool full0)
 {
     float acc[16];
 #pragma unroll
@@ -180,7 +235,7 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
 #pragma unroll
-        for (int ph = 0; ph < 4; ++ph) {
+        for (int ph = 1; ph < 4; ++ph) {
             const float c1 = IMM ? zita_lit (24 * ph + i) : c_tp_tab[24 * ph + i];
             const float c2 = IMM ? zita_lit (24 * (4 - ph) + i) : c_tp_tab[24 * (4 - ph) + i];
 #pragma unroll
@@ -190,6 +245,28 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
     }
 #pragma unroll
     for (int a = 0; a < 16; ++a) o[a] = __fsub_rn (acc[a], 1e-20f);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) o[4 * r] = __fadd_rn (w[r + 24], 0.0f);      // x for x != 0; +0 for the all-zero row (-0 + 0 = +0)
+    if (full0) {
+        // two sliding 4-sample windows: lo = x[i+1 .. i+4], hi = x[48-i .. 51-i]; one new sample each per tap pair
+        float a0[4] = {1e-20f, 1e-20f, 1e-20f, 1e-20f};
+        float lo[4], hi[4];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) { lo[r + 1] = lds_volatile (xw + r + 1); hi[r] = lds_volatile (xw + 49 + r); }
+#pragma unroll
+        for (int i = 0; i < 24; ++i) {
+            const float c1 = IMM ? zita_lit (i) : c_tp_tab[i];
+            const float c2 = IMM ? zita_lit (96 + i) : c_tp_tab[96 + i];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) { lo[r] = lo[r + 1]; hi[3 - r] = hi[2 - r]; }
+            lo[3] = lds_volatile (xw + i + 4); hi[0] = lds_volatile (xw + 48 - i);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                a0[r] = __fadd_rn (a0[r], __fadd_rn (__fmul_rn (lo[r], c1), __fmul_rn (hi[r], c2)));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) o[4 * r] = __fsub_rn (a0[r], 1e-20f);
+    }
 }
 
 // Note on Blackwell's packed fp32x2 instructions (FMUL2 / FADD2): tried and dropped.  b200m_peak_probe(2) measures
@@ -205,8 +282,8 @@ B200M_DEV void fir16 (const float (&w)[52], float (&o)[16])
 // instructions it would with one channel per lane.
 template <int CH, int TC, bool TP, bool TPMAX, bool KM, bool IMM>
 __global__ void __launch_bounds__ (TPK_THREADS)
-tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st,
-            float* __restrict__ dbg)
+tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, int elide0, TpkParams prm,
+            TpkState st, float* __restrict__ dbg)
 {
     // processes channels [c_first, n_chan): `n_chan` is the END of the slice (absolute channel index)
     constexpr int XP = 48 + TC + 4;               // x row pitch (floats): 16-byte multiple
@@ -214,10 +291,10 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     constexpr int GPC = TC / 4;                   // 4-sample groups per channel per chunk
     constexpr bool BAL = TP && !TPMAX;
     static_assert (!BAL || CH == 16, "split ballistics lanes assume 16 channels per CTA");
-    static_assert (CH <= 32 && (CH * GPC) % TPK_THREADS == 0, "tile geometry");
+    constexpr int LPR = TPK_THREADS / CH;         // lanes that share one channel row in the FIR phase (an aligned lane group)
+    static_assert (CH <= 32 && TPK_THREADS % CH == 0 && LPR <= 32 && GPC % LPR == 0, "tile geometry");
     __shared__ __align__ (16) float xs[2][CH][XP];
     __shared__ __align__ (16) float ob[BAL ? CH : 1][BAL ? OP : 4];
-    __shared__ float smax[CH];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c0 = c_first + blockIdx.x * CH;
     const int nchunks = (nfram + TC - 1) / TC;
@@ -253,10 +330,13 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     }
     load_chunk (0, 0);
 
-    // serial lanes.  warp 0: true-peak ballistics, lane = filter * 16 + channel.  warp 1: K-meter, lane = channel.
-    const bool is_tp = BAL && warp == 0;
+    // serial lanes.  role 0: true-peak ballistics, lane = filter * 16 + channel.  role 1: K-meter, lane = channel.
+    // the serial roles rotate over the CTA's warps with blockIdx: warp w of every CTA lives on SM sub-partition w % 4, so a
+    // fixed role assignment would pile all ballistics work (18 % of the instructions) onto sub-partition 0
+    const int wrole = (warp + blockIdx.x) & 3;
+    const bool is_tp = BAL && wrole == 0;
     const int tch = lane & 15, filt = lane >> 4;
-    const bool is_km = KM && warp == 1 && lane < CH;
+    const bool is_km = KM && wrole == 1 && lane < CH;
     const int chs = min (c0 + (is_tp ? tch : lane), n_chan - 1);
     const bool live = (c0 + (is_tp ? tch : lane)) < n_chan;
     float z = 0, m = 0, p = 0, wf = 0; int res = 0;
@@ -274,7 +354,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
         kz1 = a > 50 ? 50 : (a < 0 ? 0 : a);
         kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
     }
-    if (tid < CH) smax[tid] = 0.0f;                                       // process_max: plain max (:109-122)
+    float vmax = 0.0f;                                                    // process_max: plain running max (:109-122), per FIR lane
     const int km_n = (nfram / 4) * 4;                                     // "n /= 4" drops n mod 4 samples (:79)
 
     for (int c = 0; c < nchunks; ++c) {
@@ -291,31 +371,40 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
         load_chunk (c + 1, buf ^ 1);
 
         if (TP) {
-            // FIR phase: item = (channel r, group q of 4 consecutive inputs); consecutive lanes take consecutive groups
+            // FIR phase: a thread stays on channel row r = tid / LPR for the whole block and takes the groups q = ql + k * LPR
+            // of 4 consecutive inputs (consecutive lanes -> consecutive 16-byte groups: conflict-free LDS.128)
+            const int r = tid / LPR, ql = tid % LPR;
+            float M = 0.0f;
+            if (elide0) M = row_absmax<LPR, 12 + GPC> (reinterpret_cast<const float4*> (&xs[buf][r][0]), lane);
 #pragma unroll 1
-            for (int item = tid; item < CH * GPC; item += TPK_THREADS) {
-                const int r = item / GPC, q = item % GPC;
-                float vmax = 0.0f;
-                if (4 * q < len) {
+            for (int q = ql; q < GPC; q += LPR) {
+                const bool act = 4 * q < len;
+                // phase 0 degenerates to a delay for every lane of the warp?  (one vote keeps the branch warp-uniform;
+                // lanes beyond a short block's end vote yes)
+                bool full0 = true;
+                if (elide0) {
+                    const float4 xm = *reinterpret_cast<const float4*> (&xs[buf][r][act ? 4 * q + 24 : 0]);   // the 4 unit-tap samples
+                    full0 = !__all_sync (0xffffffffu, !act || phase0_is_delay (xm, M));
+                }
+                if (act) {
                     float w[52];
                     const float4* xr = reinterpret_cast<const float4*> (&xs[buf][r][4 * q]);
 #pragma unroll
                     for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
                     float o[16];
-                    fir16<IMM> (w, o);
+                    fir16<IMM> (w, &xs[buf][r][4 * q], o, full0);
                     if (dbg && (c0 + r) < n_chan) {
                         float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
 #pragma unroll
                         for (int i = 0; i < 4; ++i) d[i] = make_float4 (o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
                     }
                     if (TPMAX) {
-                        // positions beyond len inside the last group come from zero-filled input: exclude them
+                        // positions beyond len inside the last group come from zero-filled input: exclude them.
+                        // fmaxf == the reference's `if (v > m) m = v` here: m is never NaN and a NaN v leaves it unchanged
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (4 * q + i < len) {
-#pragma unroll
-                                for (int ph = 0; ph < 4; ++ph) { const float v = fabsf (o[4 * i + ph]); if (v > vmax) vmax = v; }
-                            }
+                            if (4 * q + i < len)
+                                vmax = fmaxf (fmaxf (vmax, fmaxf (fabsf (o[4 * i]), fabsf (o[4 * i + 1]))), fmaxf (fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3])));
                     } else {
                         // the 4 outputs of input sample 4q+i live at float4 slot i*GPC + q: consecutive lanes (q) store
                         // consecutive float4 -> conflict-free STS.128; the ballistics lane un-swizzles when it reads
@@ -324,14 +413,6 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
                         for (int i = 0; i < 4; ++i)
                             d[BAL ? i * GPC + q : 0] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
                     }
-                }
-                if (TPMAX) {
-                    // the lanes that share channel r are GPC consecutive lanes of this warp: segmented max, one atomic-free
-                    // writer per (warp, channel) because a channel's groups never straddle two warps (GPC divides 32 or 32 | GPC)
-                    constexpr int SEG = GPC < 32 ? GPC : 32;
-#pragma unroll
-                    for (int o = SEG / 2; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));
-                    if ((lane & (SEG - 1)) == 0) atomicMax (reinterpret_cast<int*> (&smax[r]), __float_as_int (vmax));   // vmax >= +0: int order == float order
                 }
             }
         }
@@ -349,7 +430,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
                 for (int i = 0; i < 4; ++i) {
                     const float v = vv[i];
                     if (v > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v, z)));
-                    if (v > p) p = v;
+                    p = fmaxf (p, v);                       // == `if (v > p) p = v`: p is never NaN, a NaN v leaves it unchanged
                 }
                 const float t = __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16));    // z1 + z2
                 if (t > m) m = t;
@@ -385,12 +466,16 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
             if (c0 + r < n_chan) st.hist[(size_t)(c0 + r) * 48 + j] = xs[hb][r][j];
         }
     }
-    if (TP && TPMAX && tid < CH && (c0 + tid) < n_chan) {
+    if (TP && TPMAX) {
         // process_max (:108-123): m = _res ? 0 : _m; running max; _m = m.  _res, _p, _z1, _z2 untouched.
-        const int ch = c0 + tid;
-        float mm = st.tp_res[ch] ? 0.0f : st.tp_m[ch];
-        if (smax[tid] > mm) mm = smax[tid];
-        st.tp_m[ch] = mm;
+#pragma unroll
+        for (int o = LPR / 2; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));     // the LPR lanes of row r
+        const int ch = c0 + tid / LPR;
+        if (tid % LPR == 0 && ch < n_chan) {
+            float mm = st.tp_res[ch] ? 0.0f : st.tp_m[ch];
+            if (vmax > mm) mm = vmax;
+            st.tp_m[ch] = mm;
+        }
     }
     if (is_tp && live) {
         if (filt) st.tp_z2[chs] = __fadd_rn (z, 1e-20f);    // :86-87
@@ -457,6 +542,7 @@ struct b200m_tpk {
     TpkParams prm; float ctab[120];
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
     int imm = 0;                            // host table == literal table: use the immediate-coefficient kernels
+    int elide0 = 0;                         // phase 0 of the table is the unit-tap delay fir16's guard assumes
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 
@@ -512,11 +598,11 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
         const int cf = (int)bounds[sl], ce = (int)bounds[sl + 1];
         if (ce <= cf) continue;
         if (ready) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
-#define TPK_GO(CH, TC, TP, MX, KM) do { if (h->imm) tpk_kernel<CH, TC, TP, MX, KM, true><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg); \
-                                        else tpk_kernel<CH, TC, TP, MX, KM, false><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg); } while (0)
+#define TPK_GO(CH, TC, TP, MX, KM) do { if (h->imm) tpk_kernel<CH, TC, TP, MX, KM, true><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg); \
+                                        else tpk_kernel<CH, TC, TP, MX, KM, false><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg); } while (0)
         if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true); else TPK_GO (8, 256, true, true, false); }
         else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
-        else tpk_kernel<16, 64, false, false, true, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st, h->d_dbg);
+        else tpk_kernel<16, 64, false, false, true, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg);
 #undef TPK_GO
         B200M_LAUNCHED (1);
     }
@@ -556,6 +642,13 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     tpk_design (fsamp, h->prm, h->ctab);
     h->imm = memcmp (h->ctab, h_zita_lit, sizeof (h->ctab)) == 0;
     if (const char* v = getenv ("B200M_TPK_IMM")) h->imm = h->imm && atoi (v);
+    // the phase-0 guard's bound (see phase0_is_delay) holds for this table: unit tap at [23], the other 46 taps sum to <= 7.71e-16
+    {
+        double S = 0.0;
+        for (int i = 0; i < 24; ++i) S += (i == 23 ? 0.0 : fabs ((double)h->ctab[i])) + fabs ((double)h->ctab[96 + i]);
+        h->elide0 = h->ctab[23] == 1.0f && S <= 7.71e-16;
+    }
+    if (const char* v = getenv ("B200M_TPK_ELIDE0")) h->elide0 = h->elide0 && atoi (v);      // 0: always evaluate phase 0 (tests, worst-case timing)
     cudaError_t e = cudaMemcpyToSymbol (c_tp_tab, h->ctab, sizeof (h->ctab));
     auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
     const size_t n = n_chan;

@@ -8,6 +8,16 @@ import _signals as S
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["shortcut", "full"])
+def phase0_mode(request, monkeypatch):
+    """every test runs twice: with the exact phase-0 shortcut of the FIR (default) and with phase 0 always evaluated."""
+    if request.param == "full":
+        monkeypatch.setenv("B200M_TPK_ELIDE0", "0")
+    else:
+        monkeypatch.delenv("B200M_TPK_ELIDE0", raising=False)
+    return request.param
+
+
 def u32(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
@@ -134,3 +144,73 @@ def test_reset():
     assert np.array_equal(u32(s["m"]), u32(m)) and np.array_equal(u32(s["p"]), u32(p))
     assert np.array_equal(u32(s["km"]), u32(ok.peek()))
 
+
+
+def _guard_signals(n, seed=3):
+    """rows built to sit on both sides of the phase-0 guard (csrc/tpk.cu: |x| > 1.25e-7*M + 1e-12)."""
+    rng = np.random.default_rng(seed)
+    rows = []
+    base = rng.uniform(-1, 1, n).astype(np.float32)
+    rows.append(base.copy())                                                  # plain noise: fast path
+    r = base.copy(); r[rng.random(n) < 0.9] = 0; rows.append(r)               # sparse impulses: x == 0 next to large neighbours
+    e = rng.integers(-40, 1, n); rows.append((base * np.exp2(e)).astype(np.float32))     # 40 octaves of dynamic range
+    e = rng.integers(-30, -18, n); r = base.copy(); k = rng.random(n) < 0.3
+    r[k] = (base[k] * np.exp2(e[k])).astype(np.float32); rows.append(r)       # main taps right around 2^-23 * M
+    r = base.copy(); r[::5] *= np.float32(1.25e-7); r[1::5] *= np.float32(1.19e-7); r[2::5] *= np.float32(1.3e-7); rows.append(r)
+    rows.append((base * np.float32(1e-12)).astype(np.float32))                # around the absolute floor of the guard
+    rows.append((base * np.float32(4e-13)).astype(np.float32))
+    r = (base * np.float32(1e-38)).astype(np.float32); rows.append(r)         # denormal products
+    r = base.copy(); r[100] = np.inf; r[400] = np.nan; r[700] = -np.inf; rows.append(r)
+    r = np.zeros(n, np.float32); r[n // 2] = 1.0; rows.append(r)              # unit impulse: reads the table itself
+    r = np.full(n, 0.5, np.float32); rows.append(r)                           # DC
+    rows.append(np.zeros(n, np.float32)); rows.append(np.full(n, -0.0, np.float32))          # digital silence, either sign
+    r = np.zeros(n, np.float32); r[n // 3:] = base[n // 3:]; r[2 * n // 3:] = -0.0; rows.append(r)   # silence -> signal -> silence
+    r = np.where(np.arange(n) % 2 == 0, 1.0, -1.0).astype(np.float32) * 0.9; rows.append(r)   # fs/2
+    return np.stack(rows)
+
+
+@pytest.mark.parametrize("block", [1024, 333])
+def test_phase0_guard_fir_stream(block):
+    """the phase-0 shortcut never changes a bit of the oversampled stream, whichever side of the guard a sample is on."""
+    import torch
+    import meters_lv2_b200 as B
+    n = 4096
+    x = _guard_signals(n)
+    g = B.TruePeakKmeter(x.shape[0]); g.debug_capture(True)
+    xd = torch.from_numpy(x).cuda()
+    outs = [[] for _ in range(x.shape[0])]
+    for o in range(0, n, block):
+        k = min(block, n - o)
+        g.process(xd[:, o:o + k])
+        for ch in range(x.shape[0]):
+            outs[ch].append(g.debug_upsampled(ch, 4 * k))
+    for ch in range(x.shape[0]):
+        ref = O.tp_upsample(x[ch], block=block)
+        got = np.concatenate(outs[ch])
+        nan = np.isnan(ref)                                                   # NaN payloads are not part of the contract
+        assert np.array_equal(np.isnan(got), nan), ch
+        assert np.array_equal(u32(got)[~nan], u32(ref)[~nan]), (ch, int((u32(got)[~nan] != u32(ref)[~nan]).sum()))
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_phase0_guard_meters(mode):
+    x = _guard_signals(6000, seed=9)
+    x = np.concatenate([x, _guard_signals(6000, seed=10)], axis=0)           # 24 rows: spans two process() tiles
+    _drive(x, [1024, 1024, 1000, 24, 1024, 1904], read_every=2, mode=mode, flags=1 if mode else 3)
+
+
+def test_phase0_guard_off_matches(monkeypatch):
+    """B200M_TPK_ELIDE0=0 (full evaluation) and the default produce identical state on noise."""
+    import torch
+    import meters_lv2_b200 as B
+    x = S.white(40, 4096, seed=21)
+    xd = torch.from_numpy(x).cuda()
+    res = []
+    for v in ("1", "0"):
+        monkeypatch.setenv("B200M_TPK_ELIDE0", v)
+        g = B.TruePeakKmeter(40)
+        for o in range(0, 4096, 1024):
+            g.process(xd[:, o:o + 1024])
+        res.append(g.state())
+    for k in ("m", "p", "z1", "z2"):
+        assert np.array_equal(u32(res[0][k]), u32(res[1][k])), k
