@@ -64,8 +64,11 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k
 {
     // channels [k_first, k_end) of the bank's nchans (a slice: *_run_host overlaps the copy of slice s+1 with slice s)
     extern __shared__ __align__ (16) float ebu_smem[];
+    // programmatic dependent launch: a kernel launched behind this one with the programmatic-serialization attribute (the
+    // true-peak kernel of the EBUr128 cycle, r128.cu) may start as soon as every CTA of this grid is running
+    asm volatile ("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k0 = k_first + (blockIdx.x * EBU_WARPS + warp) * 32;
+    const int k0 = k_first + (blockIdx.x * (blockDim.x >> 5) + warp) * 32;      // 1, 2 or 4 warps per CTA (host's choice)
     if (k0 >= k_end) return;                           // warp-uniform; warps never synchronise with each other
     float* tile = ebu_smem + warp * EBU_WARP_FLOATS;
     const int k = min (k0 + lane, k_end - 1);        // tail lanes shadow the last channel (no stores)
@@ -432,6 +435,7 @@ struct b200m_ebu {
     EbuCtl* d_ctl = nullptr; b200m_ebu_result* d_res = nullptr;
     int *d_histM = nullptr, *d_histS = nullptr, *d_cnt = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
+    int k1_warps = EBU_WARPS;            // warps per K1 CTA (1, 2 or 4)
     // Host mirror of every instance's S-histogram period (_div2, :234-241), kept in O(1) per fragment: an
     // integrating instance has div2 = (G - base) mod 10 where G counts fragments; cnt10[r] = number of integrating
     // instances with base = r.  The gated-statistics kernel (K2b) is launched only for fragments where some
@@ -571,7 +575,7 @@ int b200m_ebu_integr_reset (b200m_ebu* h, int32_t inst, void* stream) { return e
 // separately, slice s after event ready[s] (the host->device copy of its rows) when `ready` is given; the
 // fragment/gating kernels run once, after the last slice.
 int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st,
-                        int nsl, const uint32_t* bounds, cudaEvent_t* ready)
+                        int nsl, const uint32_t* bounds, cudaEvent_t* ready, int (*after_k1) (void*), void* after_arg)
 {
     const int nch = (int)(h->n_inst * h->nchan);
     const bool aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
@@ -595,13 +599,15 @@ int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
             if (ke <= kf) continue;
             if (ready && done == 0) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
             const int nwarps = (ke - kf + 31) / 32;
-            dim3 grid ((nwarps + EBU_WARPS - 1) / EBU_WARPS), blk (EBU_WARPS * 32);
-#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, EBU_SMEM_BYTES, st>>> (src, stride, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
+            const int wpc = h->k1_warps;
+            dim3 grid ((nwarps + wpc - 1) / wpc), blk (wpc * 32);
+#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, (size_t)wpc * EBU_WARP_FLOATS * 4, st>>> (src, stride, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
             if (h->nchan == 1) { if (al) EBU_K1 (1, true); else EBU_K1 (1, false); }
             else               { if (al) EBU_K1 (2, true); else EBU_K1 (2, false); }
 #undef EBU_K1
             B200M_LAUNCHED (1);
         }
+        if (after_k1 && done == 0) { if (int rc = after_k1 (after_arg)) return rc; }      // work to enqueue right behind the first K1
         for (int f = 0; f < nfrag; ++f) {                    // fragments complete in order; each may trigger gating
             ebu_fragment_kernel<<<(h->n_inst + K2A_THREADS - 1) / K2A_THREADS, K2A_THREADS, 0, st>>> (
                 (int)h->n_inst, f, h->wrind, h->d_fragpw, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt);
@@ -619,10 +625,13 @@ int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
     return 0;
 }
 
+// K1 CTA shape (r128.cu: single-warp CTAs slot in beside the true-peak kernel's CTAs whichever kernel reaches the SMs first)
+extern "C" void ebu_set_k1_warps (b200m_ebu* h, int w) { h->k1_warps = (w == 1 || w == 2) ? w : EBU_WARPS; }
+
 static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
 {
     const uint32_t bounds[2] = {0, h->n_inst};
-    return ebu_process_sliced (h, d_in, stride, nfram, st, 1, bounds, nullptr);
+    return ebu_process_sliced (h, d_in, stride, nfram, st, 1, bounds, nullptr, nullptr, nullptr);
 }
 
 int b200m_ebu_process_device (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, void* stream)

@@ -10,27 +10,17 @@
 
 namespace b200m {
 
-// coef_to_db (src/ebulv2.cc:227-230) and the tp_max hold (:360-367); one thread per instance
-__global__ void r128_tp_kernel (int n_inst, const float* __restrict__ tp_m, int* __restrict__ tp_res, float* __restrict__ tp_max)
-{
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_inst) return;
-    const float a = tp_m[2 * i], b = tp_m[2 * i + 1];           // TruePeakdsp::read(): returns _m, sets _res
-    tp_res[2 * i] = 1; tp_res[2 * i + 1] = 1;
-    const float v = a > b ? a : b;
-    const float tp = (v == 0) ? -INFINITY : __double2float_rn (__dmul_rn (20.0, (double)log10f_glibc (v)));
-    if (tp > tp_max[i]) tp_max[i] = tp;
-}
+// coef_to_db (src/ebulv2.cc:227-230) and the tp_max hold (:360-367) run in the epilogue of tpk_kernel<TPMAX> (tpk.cu)
 __global__ void r128_fill_kernel (int n, float* p, float v) { const int i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) p[i] = v; }
-
-// accessors implemented in tpk.cu (internal linkage across the library, hidden visibility)
-void tpk_raw_pointers (b200m_tpk* h, float** tp_m, int** tp_res);
 
 }  // namespace b200m
 
 // sliced process entry points of the two banks (ebu.cu, tpk.cu)
-extern "C" int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready);
-int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready);
+extern "C" void ebu_set_k1_warps (b200m_ebu* h, int w);
+extern "C" int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready,
+                                   int (*after_k1) (void*), void* after_arg);
+int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready,
+                        float* r128_tpmax, bool pdl);
 
 using namespace b200m;
 
@@ -49,24 +39,38 @@ struct b200m_r128 {
 
 static int env_int (const char* name, int dflt) { const char* v = getenv (name); return v ? atoi (v) : dflt; }
 
+struct R128Step { b200m_r128* h; const float* d_in; size_t stride; uint32_t nfram; cudaStream_t st; const uint32_t* bc; };
+
+// device path: the true-peak kernel goes onto the caller's stream right behind the first K-weighting launch, with
+// programmatic dependent launch, so that the two kernels share the SMs (see r128_run)
+static int r128_tp_behind_k1 (void* p)
+{
+    R128Step* a = (R128Step*)p;
+    return tpk_process_sliced (a->h->tpk, a->d_in, a->stride, a->nfram, B200M_TP_MODE_MAX, a->st, 1, a->bc, nullptr, a->h->d_tpmax, true);
+}
+
 static int r128_run (b200m_r128* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, cudaEvent_t* ready)
 {
     uint32_t bi[R128_SLICES + 1], bc[R128_SLICES + 1];
     for (int s = 0; s <= nsl; ++s) { bi[s] = (uint32_t)((uint64_t)h->n_inst * s / nsl); bc[s] = 2 * bi[s]; }
-    // The EBU kernel is latency bound on 4 warps per SM; launched FIRST it leaves most of every SM to the true-peak
-    // kernel, which then runs concurrently on the side stream (tuning knob: B200M_R128_CONCURRENT=0 serialises them).
-    const bool conc = h->dbtp && h->concurrent && ready;     // measured: concurrency helps the sliced host path (12.2 vs 9.0 G
-                                                             // samples/s) and costs 6 % on the device-resident path
-    cudaStream_t tps = conc ? h->side : st;
-    if (conc && !ready) { B200M_CUDA (cudaEventRecord (h->ev_in, st)); B200M_CUDA (cudaStreamWaitEvent (h->side, h->ev_in, 0)); }
-    if (int rc = ebu_process_sliced (h->ebu, d_in, stride, nfram, st, nsl, bi, ready)) return rc;
+    // The K-weighting kernel is latency bound on 4 warps per SM and the true-peak kernel issue bound: run together they
+    // cost little more than the true-peak kernel alone, PROVIDED the K-weighting CTAs are resident first (104 KB of shared
+    // memory each: they do not fit once the true-peak CTAs fill an SM).
+    //  * device path (B200M_R128_CONCURRENT >= 2): same stream; the K-weighting kernel triggers programmatic launch
+    //    completion at its start and the true-peak kernel is launched behind it with the programmatic-serialization
+    //    attribute -> deterministic order, no events.  The true-peak kernel's epilogue does read() x 2 + coef_to_db + the
+    //    tp_max hold per instance and ends with griddepcontrol.wait, so everything queued behind it is ordered after both.
+    //  * sliced host path (>= 1): true-peak kernels on the side stream, each slice behind its copy event.
+    // B200M_R128_CONCURRENT=0 serialises everything on one stream.
+    const bool pdl = h->dbtp && h->concurrent >= 2 && !ready;
+    const bool conc = h->dbtp && h->concurrent >= 1 && ready;
+    R128Step step = {h, d_in, stride, nfram, st, bc};
+    if (int rc = ebu_process_sliced (h->ebu, d_in, stride, nfram, st, nsl, bi, ready, pdl ? r128_tp_behind_k1 : nullptr, &step)) return rc;
     if (h->dbtp) {
-        if (int rc = tpk_process_sliced (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, tps, nsl, bc, conc ? ready : nullptr)) return rc;
-        if (conc) { B200M_CUDA (cudaEventRecord (h->ev_tp, h->side)); B200M_CUDA (cudaStreamWaitEvent (st, h->ev_tp, 0)); }
-        float* tp_m; int* tp_res;
-        tpk_raw_pointers (h->tpk, &tp_m, &tp_res);
-        r128_tp_kernel<<<(h->n_inst + 255) / 256, 256, 0, st>>> ((int)h->n_inst, tp_m, tp_res, h->d_tpmax);
-        B200M_LAUNCHED (1);
+        if (!pdl) {
+            if (int rc = tpk_process_sliced (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, conc ? h->side : st, nsl, bc, conc ? ready : nullptr, h->d_tpmax, false)) return rc;
+            if (conc) { B200M_CUDA (cudaEventRecord (h->ev_tp, h->side)); B200M_CUDA (cudaStreamWaitEvent (st, h->ev_tp, 0)); }
+        }
     } else {
         r128_fill_kernel<<<(h->n_inst + 255) / 256, 256, 0, st>>> ((int)h->n_inst, h->d_tpmax, -INFINITY);   // :365-366
         B200M_LAUNCHED (1);
@@ -84,12 +88,13 @@ int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsam
     b200m_r128* h = new (std::nothrow) b200m_r128;
     if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
     h->device = device; h->n_inst = n_inst; h->dbtp = dbtp_enable ? 1 : 0;
-    h->concurrent = env_int ("B200M_R128_CONCURRENT", 1);
+    h->concurrent = env_int ("B200M_R128_CONCURRENT", 2);      // 0: serial, 1: sliced host path only, 2: device path too
     h->slices = env_int ("B200M_R128_SLICES", 4);
     if (h->slices < 1) h->slices = 1;
     if (h->slices > R128_SLICES) h->slices = R128_SLICES;
     int rc = b200m_ebu_create (&h->ebu, device, n_inst, 2, fsamp);                 // ebu->init (2, rate), src/ebulv2.cc:190
     if (!rc) rc = b200m_tpk_create (&h->tpk, device, 2 * n_inst, fsamp, B200M_TPK_TRUEPEAK);   // 2 x TruePeakdsp, :192-196
+    if (!rc) ebu_set_k1_warps (h->ebu, env_int ("B200M_R128_K1_WARPS", 4));
     if (!rc) {
         DeviceGuard g (device);
         cudaError_t e = cudaMalloc ((void**)&h->d_tpmax, n_inst * sizeof (float));

@@ -283,7 +283,7 @@ B200M_DEV void fir16 (const float (&w)[52], const float* xw, float (&o)[16], con
 template <int CH, int TC, bool TP, bool TPMAX, bool KM, bool IMM>
 __global__ void __launch_bounds__ (TPK_THREADS)
 tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, int elide0, TpkParams prm,
-            TpkState st, float* __restrict__ dbg)
+            TpkState st, float* __restrict__ dbg, float* __restrict__ r128_tpmax)
 {
     // processes channels [c_first, n_chan): `n_chan` is the END of the slice (absolute channel index)
     constexpr int XP = 48 + TC + 4;               // x row pitch (floats): 16-byte multiple
@@ -471,10 +471,27 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
 #pragma unroll
         for (int o = LPR / 2; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));     // the LPR lanes of row r
         const int ch = c0 + tid / LPR;
-        if (tid % LPR == 0 && ch < n_chan) {
-            float mm = st.tp_res[ch] ? 0.0f : st.tp_m[ch];
+        const bool lead = (tid % LPR) == 0 && ch < n_chan;
+        float mm = 0.0f;
+        if (lead) {
+            mm = st.tp_res[ch] ? 0.0f : st.tp_m[ch];
             if (vmax > mm) mm = vmax;
             st.tp_m[ch] = mm;
+        }
+        if (r128_tpmax) {
+            // EBUr128 epilogue (src/ebulv2.cc:227-230,360-367), one lane per stereo instance: read() both meters (returns _m,
+            // sets _res), tp = coef_to_db (max), tp_max hold.  The instance's channels are rows r, r+1 of this warp.
+            static_assert (!TPMAX || 2 * LPR <= 32, "a stereo pair must live in one warp");
+            const float b = __shfl_xor_sync (0xffffffffu, mm, LPR);
+            if (lead && ((tid / LPR) & 1) == 0 && ch + 1 < n_chan) {
+                const float v = mm > b ? mm : b;
+                const float tp = (v == 0) ? -INFINITY : __double2float_rn (__dmul_rn (20.0, (double)log10f_glibc (v)));
+                if (tp > r128_tpmax[ch >> 1]) r128_tpmax[ch >> 1] = tp;
+                st.tp_res[ch] = 1; st.tp_res[ch + 1] = 1;
+            }
+            // launched with programmatic serialization behind the K-weighting kernel (r128.cu): this grid must not complete
+            // before that one has, so that the kernels queued behind it see its results (no-op in a plain launch)
+            asm volatile ("griddepcontrol.wait;" ::: "memory");
         }
     }
     if (is_tp && live) {
@@ -577,16 +594,12 @@ static void tpk_design (float fsamp, TpkParams& prm, float* ctab)
     zita_table (ctab, 24, 4, 1.0);                  // setup (fsamp, fsamp * 4.0, 1, 24, 1.0): np = 4, ratio-only
 }
 
-namespace b200m {
-void tpk_raw_pointers (b200m_tpk* h, float** tp_m, int** tp_res) { *tp_m = h->st.tp_m; *tp_res = h->st.tp_res; }
-}
-
 static cudaStream_t tpk_stream (b200m_tpk* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
 
 // process()/process_max() of every meter; channel slices [bounds[s], bounds[s+1]) are launched separately, slice s
 // after event ready[s] when `ready` is given (see ebu_process_sliced).
 int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st,
-                        int nsl, const uint32_t* bounds, cudaEvent_t* ready)
+                        int nsl, const uint32_t* bounds, cudaEvent_t* ready, float* r128_tpmax, bool pdl)
 {
     const bool tp = h->flags & B200M_TPK_TRUEPEAK, km = h->flags & B200M_TPK_KMETER;
     TpkParams prm = h->prm;
@@ -598,11 +611,18 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
         const int cf = (int)bounds[sl], ce = (int)bounds[sl + 1];
         if (ce <= cf) continue;
         if (ready) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
-#define TPK_GO(CH, TC, TP, MX, KM) do { if (h->imm) tpk_kernel<CH, TC, TP, MX, KM, true><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg); \
-                                        else tpk_kernel<CH, TC, TP, MX, KM, false><<<(ce - cf + CH - 1) / CH, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg); } while (0)
+        // cudaLaunchKernelEx so that the EBUr128 cycle can attach the programmatic-serialization attribute (pdl): the kernel
+        // may then start while the K-weighting kernel launched just before it on `st` is still running (r128.cu)
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
+        cudaLaunchConfig_t cfg = {};
+        cfg.blockDim = blk; cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+#define TPK_GO(CH, TC, TP, MX, KM) do { cfg.gridDim = dim3 ((ce - cf + CH - 1) / CH); \
+            if (h->imm) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax)); \
+            else B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, false>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax)); } while (0)
         if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true); else TPK_GO (8, 256, true, true, false); }
         else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
-        else tpk_kernel<16, 64, false, false, true, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg);
+        else tpk_kernel<16, 64, false, false, true, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax);
 #undef TPK_GO
         B200M_LAUNCHED (1);
     }
@@ -613,7 +633,7 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
 static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st)
 {
     const uint32_t bounds[2] = {0, h->n_chan};
-    return tpk_process_sliced (h, d_in, stride, nfram, tp_mode, st, 1, bounds, nullptr);
+    return tpk_process_sliced (h, d_in, stride, nfram, tp_mode, st, 1, bounds, nullptr, nullptr, false);
 }
 
 extern "C" {
