@@ -60,20 +60,22 @@ B200M_DEV void kw_step (float p, const EbuCoef& c, float& z1, float& z2, float& 
 template <int NCHAN, bool ALIGNED>
 __global__ void __launch_bounds__ (EBU_WARPS * 32)
 ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k_first, int k_end, int nfram, EbuCoef cf, EbuChunks ck,
-                  float fragm_f, float* __restrict__ zst, float* __restrict__ frpwr, float* __restrict__ fragpw, int n_inst)
+                  float fragm_f, float* __restrict__ zst, float* __restrict__ frpwr, float* __restrict__ fragpw, int n_inst, int pdl_trigger)
 {
     // channels [k_first, k_end) of the bank's nchans (a slice: *_run_host overlaps the copy of slice s+1 with slice s)
     extern __shared__ __align__ (16) float ebu_smem[];
     // programmatic dependent launch: a kernel launched behind this one with the programmatic-serialization attribute (the
     // true-peak kernel of the EBUr128 cycle, r128.cu) may start as soon as every CTA of this grid is running
-    asm volatile ("griddepcontrol.launch_dependents;");
+    if (pdl_trigger) asm volatile ("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k0 = k_first + (blockIdx.x * (blockDim.x >> 5) + warp) * 32;      // 1, 2 or 4 warps per CTA (host's choice)
+    const int k0 = k_first + (blockIdx.x * EBU_WARPS + warp) * 32;
     if (k0 >= k_end) return;                           // warp-uniform; warps never synchronise with each other
     float* tile = ebu_smem + warp * EBU_WARP_FLOATS;
     const int k = min (k0 + lane, k_end - 1);        // tail lanes shadow the last channel (no stores)
     const bool live = (k0 + lane) < k_end;
     const int ntiles = (nfram + EBU_TILE - 1) / EBU_TILE;
+    const bool full_warp = k0 + 32 <= k_end;
+    const float* src_base = in + (size_t)min (k0 + (lane >> 4), k_end - 1) * stride + (lane & 15) * 4;
 
     auto issue = [&] (int t) {
         if (t < ntiles) {
@@ -83,12 +85,21 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k
                 const int c4 = (lane & 15) * 4;                  // column of this lane's 16-byte piece
                 const int left = (nfram - (s0 + c4)) * 4;        // bytes still inside the block
                 const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+                if (full_warp) {
+                    // rows 2i + (lane >> 4): one base pointer per lane, a constant 2-row step (all 32 channels exist)
+                    const float* sp = nb ? src_base + s0 : in;
+                    const size_t step = nb ? 2 * stride : 0;
+                    float* d = dst + (lane >> 4) * EBU_ROWP + c4;
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int r = 2 * i + (lane >> 4);
-                    const int kr = min (k0 + r, k_end - 1);
-                    const float* src = in + (size_t)kr * stride + s0 + c4;
-                    cp_async16 (dst + r * EBU_ROWP + c4, nb ? src : in, nb);
+                    for (int i = 0; i < 16; ++i) cp_async16 (d + i * 2 * EBU_ROWP, sp + i * step, nb);
+                } else {
+#pragma unroll 4
+                    for (int i = 0; i < 16; ++i) {
+                        const int r = 2 * i + (lane >> 4);
+                        const int kr = min (k0 + r, k_end - 1);
+                        const float* src = in + (size_t)kr * stride + s0 + c4;
+                        cp_async16 (dst + r * EBU_ROWP + c4, nb ? src : in, nb);
+                    }
                 }
             } else {
 #pragma unroll 4
@@ -435,7 +446,6 @@ struct b200m_ebu {
     EbuCtl* d_ctl = nullptr; b200m_ebu_result* d_res = nullptr;
     int *d_histM = nullptr, *d_histS = nullptr, *d_cnt = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
-    int k1_warps = EBU_WARPS;            // warps per K1 CTA (1, 2 or 4)
     // Host mirror of every instance's S-histogram period (_div2, :234-241), kept in O(1) per fragment: an
     // integrating instance has div2 = (G - base) mod 10 where G counts fragments; cnt10[r] = number of integrating
     // instances with base = r.  The gated-statistics kernel (K2b) is launched only for fragments where some
@@ -599,9 +609,8 @@ int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
             if (ke <= kf) continue;
             if (ready && done == 0) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
             const int nwarps = (ke - kf + 31) / 32;
-            const int wpc = h->k1_warps;
-            dim3 grid ((nwarps + wpc - 1) / wpc), blk (wpc * 32);
-#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, (size_t)wpc * EBU_WARP_FLOATS * 4, st>>> (src, stride, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst)
+            dim3 grid ((nwarps + EBU_WARPS - 1) / EBU_WARPS), blk (EBU_WARPS * 32);
+#define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, EBU_SMEM_BYTES, st>>> (src, stride, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst, (after_k1 && done == 0) ? 1 : 0)
             if (h->nchan == 1) { if (al) EBU_K1 (1, true); else EBU_K1 (1, false); }
             else               { if (al) EBU_K1 (2, true); else EBU_K1 (2, false); }
 #undef EBU_K1
@@ -624,9 +633,6 @@ int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
     B200M_CUDA (cudaGetLastError ());
     return 0;
 }
-
-// K1 CTA shape (r128.cu: single-warp CTAs slot in beside the true-peak kernel's CTAs whichever kernel reaches the SMs first)
-extern "C" void ebu_set_k1_warps (b200m_ebu* h, int w) { h->k1_warps = (w == 1 || w == 2) ? w : EBU_WARPS; }
 
 static int ebu_process (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
 {

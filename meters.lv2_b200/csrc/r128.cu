@@ -16,7 +16,6 @@ __global__ void r128_fill_kernel (int n, float* p, float v) { const int i = bloc
 }  // namespace b200m
 
 // sliced process entry points of the two banks (ebu.cu, tpk.cu)
-extern "C" void ebu_set_k1_warps (b200m_ebu* h, int w);
 extern "C" int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready,
                                    int (*after_k1) (void*), void* after_arg);
 int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready,
@@ -94,7 +93,6 @@ int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsam
     if (h->slices > R128_SLICES) h->slices = R128_SLICES;
     int rc = b200m_ebu_create (&h->ebu, device, n_inst, 2, fsamp);                 // ebu->init (2, rate), src/ebulv2.cc:190
     if (!rc) rc = b200m_tpk_create (&h->tpk, device, 2 * n_inst, fsamp, B200M_TPK_TRUEPEAK);   // 2 x TruePeakdsp, :192-196
-    if (!rc) ebu_set_k1_warps (h->ebu, env_int ("B200M_R128_K1_WARPS", 4));
     if (!rc) {
         DeviceGuard g (device);
         cudaError_t e = cudaMalloc ((void**)&h->d_tpmax, n_inst * sizeof (float));
