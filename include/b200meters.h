@@ -168,7 +168,8 @@ int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t
  * One host->device copy per block feeds both meters.  Atom/radar/GUI messaging is out of scope.
  * ====================================================================================== */
 typedef struct b200m_r128 b200m_r128;
-enum { B200M_R128_START = 1, B200M_R128_PAUSE = 2, B200M_R128_RESET = 3 };   /* CTL_START/PAUSE/RESET, src/uris.h:187-203 */
+enum { B200M_R128_START = 1, B200M_R128_PAUSE = 2, B200M_R128_RESET = 3 };   /* CTL_START/PAUSE/RESET, src/uris.h:187-203; RESET = ebu_reset
+                                                                                * (src/ebulv2.cc:45-61): integr_reset + tp_max hold cleared */
 int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsamp, int dbtp_enable);
 int b200m_r128_destroy (b200m_r128* h);
 int b200m_r128_control (b200m_r128* h, int32_t inst, int cmd, void* stream);      /* inst = -1: all */
@@ -176,6 +177,11 @@ int b200m_r128_run_device (b200m_r128* h, const float* d_in, size_t stride, uint
 int b200m_r128_run_host (b200m_r128* h, const float* in, size_t stride, uint32_t nfram);
 /* ebu_out: n_inst getter blocks (may be NULL); tp_max_db: n_inst floats, -inf when dBTP is disabled (may be NULL) */
 int b200m_r128_results (b200m_r128* h, b200m_ebu_result* ebu_out, float* tp_max_db, void* stream);
+/* self->dbtp_enable (CTL_UISETTINGS bit 64, src/ebulv2.cc:316-317): the true-peak meters only run while enabled; while
+ * disabled tp_max is -inf every cycle (:365-366).  Takes effect with the next run. */
+int b200m_r128_set_dbtp (b200m_r128* h, int enable);
+/* histogram_M() / histogram_S() of one instance (src/ebulv2.cc:425-429), ordered after the bank's last run */
+int b200m_r128_histogram (b200m_r128* h, uint32_t inst, int32_t* hist_M, int32_t* hist_S, void* stream);
 b200m_ebu* b200m_r128_ebu (b200m_r128* h);     /* the underlying banks (histograms, state, coefficients) */
 b200m_tpk* b200m_r128_tpk (b200m_r128* h);
 

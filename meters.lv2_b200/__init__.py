@@ -82,6 +82,8 @@ _PROTOS = {
     "b200m_r128_run_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
     "b200m_r128_run_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
     "b200m_r128_results": (C.c_int, [_v, _v, _v, _v]),
+    "b200m_r128_set_dbtp": (C.c_int, [_v, C.c_int]),
+    "b200m_r128_histogram": (C.c_int, [_v, C.c_uint32, _v, _v, _v]),
     "b200m_r128_ebu": (_v, [_v]),
     "b200m_r128_tpk": (_v, [_v]),
     # Stcorr
@@ -650,3 +652,12 @@ class EBUr128(_Bank):
         tp = np.empty(self.n_inst, np.float32) if tp is None else tp
         _ck(lib().b200m_r128_results(self.h, _np_ptr(out), _np_ptr(tp), _stream_ptr(stream)))
         return out, tp
+
+    def set_dbtp(self, enable):
+        """self->dbtp_enable (src/ebulv2.cc:316-317): takes effect with the next run"""
+        _ck(lib().b200m_r128_set_dbtp(self.h, int(bool(enable))))
+
+    def histogram(self, inst, stream=None):
+        m = np.empty(751, np.int32); s = np.empty(751, np.int32)
+        _ck(lib().b200m_r128_histogram(self.h, int(inst), _np_ptr(m), _np_ptr(s), _stream_ptr(stream)))
+        return m, s

@@ -1,13 +1,13 @@
 // lv2_shim.cu — per-instance LV2 façade over the batched engine: `lv2_descriptor()` with the reference's URIs,
 // port indices and run() semantics, so that an LV2 host can load this library where it loaded meters.so.
 //
-// Covers the 24 control-port plugins (src/meters.cc:745-792 lists all 38 descriptors):
+// Covers the 24 control-port plugins (src/meters.cc:745-792 lists all 38 descriptors) and, in lv2_ebur128.cu, EBUr128:
 //   VU / BBC / EBU / DIN / NOR mono+stereo (run :298-331), BBCM6 (bbcm_run :552-589),
 //   COR (cor_run :511-536), dBTPmono/stereo (dbtp_run :438-508), K12/K14/K20 mono/stereo (kmeter_run :333-418),
 //   spectr30mono/stereo (spectrum_run, src/spectrumlv2.c:159-257), TPnRMSmono/stereo (dr14_run without DR mode,
 //   src/dr14.c:354-482; its float control ports carry all results, the atom control port is ignored).
-// EBUr128, DR14, phasewheel, stereoscope, goniometer, bitmeter and SigDistHist publish their results only
-// through LV2 atom messages (src/uris.h:279-318), which is out of scope: use the batch API.
+// DR14, phasewheel, stereoscope, goniometer, bitmeter and SigDistHist publish their results only through LV2 atom
+// messages (src/uris.h:279-318) and are not wrapped yet: use the batch API.
 // Each LV2 instance owns a bank of one instance; run() is synchronous (host buffers in, ports out), exactly the
 // reference's calling convention (robtk/jackwrap.c:531-544).  LV2 core types are restated from the LV2
 // specification (the SDK is not installed); the struct layout is the stable public C ABI.
@@ -15,23 +15,9 @@
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
+#include "lv2_abi.cuh"
 
-extern "C" {
-typedef void* LV2_Handle;
-typedef struct { const char* URI; void* data; } LV2_Feature;
-typedef struct LV2_Descriptor_s {
-    const char* URI;
-    LV2_Handle (*instantiate) (const struct LV2_Descriptor_s*, double, const char*, const LV2_Feature* const*);
-    void (*connect_port) (LV2_Handle, uint32_t, void*);
-    void (*activate) (LV2_Handle);
-    void (*run) (LV2_Handle, uint32_t);
-    void (*deactivate) (LV2_Handle);
-    void (*cleanup) (LV2_Handle);
-    const void* (*extension_data) (const char*);
-} LV2_Descriptor;
-}
-
-#define MTR_URI "http://gareus.org/oss/lv2/meters#"      /* src/uris.h:37 */
+namespace b200m { const LV2_Descriptor* lv2_ebur128_descriptor (); }     // lv2_ebur128.cu
 
 namespace {
 
@@ -267,5 +253,8 @@ const LV2_Descriptor g_desc[] = {
 // the covered subset in the reference's order.
 extern "C" __attribute__ ((visibility ("default"))) const LV2_Descriptor* lv2_descriptor (uint32_t index)
 {
-    return index < sizeof (g_desc) / sizeof (g_desc[0]) ? &g_desc[index] : nullptr;
+    constexpr uint32_t n = sizeof (g_desc) / sizeof (g_desc[0]);
+    if (index < n) return &g_desc[index];
+    if (index == n) return b200m::lv2_ebur128_descriptor ();       // the atom-port plugins follow the control-port ones
+    return nullptr;
 }

@@ -132,7 +132,15 @@ int b200m_r128_control (b200m_r128* h, int32_t inst, int cmd, void* stream)
     switch (cmd) {
     case B200M_R128_START: return b200m_ebu_integr_start (h->ebu, inst, st);
     case B200M_R128_PAUSE: return b200m_ebu_integr_pause (h->ebu, inst, st);
-    case B200M_R128_RESET: return b200m_ebu_integr_reset (h->ebu, inst, st);
+    case B200M_R128_RESET: {                                // ebu_reset (src/ebulv2.cc:45-61): integr_reset + tp_max = -inf
+        if (inst >= (int32_t)h->n_inst) return set_err (B200M_E_INVAL, "bad instance %d", inst);
+        DeviceGuard g (h->device);
+        const int first = inst < 0 ? 0 : inst, cnt = inst < 0 ? (int)h->n_inst : 1;
+        r128_fill_kernel<<<(cnt + 255) / 256, 256, 0, (cudaStream_t)st>>> (cnt, h->d_tpmax + first, -INFINITY);
+        B200M_LAUNCHED (1);
+        B200M_CUDA (cudaGetLastError ());
+        return b200m_ebu_integr_reset (h->ebu, inst, st);
+    }
     default: return set_err (B200M_E_INVAL, "unknown control %d", cmd);
     }
 }
@@ -175,6 +183,19 @@ int b200m_r128_results (b200m_r128* h, b200m_ebu_result* ebu_out, float* tp_max_
     if (ebu_out) return b200m_ebu_results (h->ebu, ebu_out, st);
     B200M_CUDA (cudaStreamSynchronize (st));
     return 0;
+}
+
+int b200m_r128_set_dbtp (b200m_r128* h, int enable)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    h->dbtp = enable ? 1 : 0;                              // takes effect with the next run: self->dbtp_enable (src/ebulv2.cc:316-317,344-347)
+    return 0;
+}
+
+int b200m_r128_histogram (b200m_r128* h, uint32_t inst, int32_t* hist_M, int32_t* hist_S, void* stream)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    return b200m_ebu_histogram (h->ebu, inst, hist_M, hist_S, h->last_host ? (void*)h->own : stream);
 }
 
 b200m_ebu* b200m_r128_ebu (b200m_r128* h) { return h ? h->ebu : nullptr; }

@@ -1,0 +1,131 @@
+"""GPU: the EBUr128 LV2 plugin of libb200meters.so (csrc/lv2_ebur128.cu) against the REFERENCE plugin (src/ebulv2.cc
+compiled unmodified into oracle/_ref, -DHAVE_LV2_1_8 as every LV2 >= 1.8.1 build defines), both driven like an LV2 host
+drives them: the same URID map, the same control-port atom sequences (meteron, metercfg key/value, time:Position), the
+same audio.  After every run() the notify-port buffers must be IDENTICAL BYTES: every radar point, histogram delta,
+ebulevels float and control reply.  The atom wire format itself is restated from the LV2 specification on both sides
+(the SDK is not installed; oracle/lv2stub is the stand-in the reference is compiled against)."""
+import ctypes as C
+import struct
+
+import numpy as np
+import pytest
+
+import _oracle as O
+import _signals as S
+from test_lv2_shim_gpu import Feature, _map, descriptors, Plugin
+
+pytestmark = pytest.mark.gpu
+ATOM = b"http://lv2plug.in/ns/ext/atom#"
+TIME = b"http://lv2plug.in/ns/ext/time#"
+MTR = b"http://gareus.org/oss/lv2/meters#"
+CTL = dict(START=1, PAUSE=2, RESET=3, TRANSPORTSYNC=4, AUTORESET=5, RADARTIME=6, UISETTINGS=7)      # src/uris.h:187-203
+CAP = 8192
+
+
+def urid(uri):
+    return _map(None, uri)
+
+
+def obj(otype, props=()):
+    """one event at frame 0 holding an atom:Object {otype; (key, type, packed 4-byte value)...}"""
+    body = struct.pack("<II", 0, urid(otype))
+    for key, typ, val in props:
+        body += struct.pack("<IIII", urid(key), 0, 4, urid(typ)) + val + b"\0\0\0\0"
+    return struct.pack("<q", 0) + struct.pack("<II", len(body), urid(ATOM + b"Object")) + body
+
+
+def cfg(key, value):
+    return obj(MTR + b"metercfg", [(MTR + b"controlkey", ATOM + b"Int", struct.pack("<i", CTL[key])),
+                                   (MTR + b"controlval", ATOM + b"Float", struct.pack("<f", value))])
+
+
+def position(speed):
+    return obj(TIME + b"Position", [(TIME + b"speed", ATOM + b"Float", struct.pack("<f", speed))])
+
+
+def sequence(events):
+    body = struct.pack("<II", 0, 0) + b"".join(events)
+    raw = struct.pack("<II", len(body), urid(ATOM + b"Sequence")) + body
+    a = np.zeros(max(64, (len(raw) + 7) // 8 * 8), np.uint8)
+    a[:len(raw)] = np.frombuffer(raw, np.uint8)
+    return a
+
+
+def drive(script, nblocks, block=1024, x=None, cap=CAP, rate=48000.0):
+    """script: {block index: [events]} fed to the control port of both plugins; returns nothing, asserts byte parity"""
+    import meters_lv2_b200 as B
+    mine, l1 = descriptors(B.LIB_PATH)
+    ref, l2 = descriptors(O.PATHS["reference"])
+    g, r = Plugin(mine["EBUr128"], rate), Plugin(ref["EBUr128"], rate)
+    if x is None:
+        x = S.white(2, block * nblocks, seed=17) * np.float32(4.0)
+    empty = sequence([])
+    notes = [np.zeros(cap, np.uint8), np.zeros(cap, np.uint8)]
+    sizes = []
+    for b in range(nblocks):
+        ctl = sequence(script[b]) if b in script else empty
+        outs = []
+        for p, note in ((g, notes[0]), (r, notes[1])):
+            note[:] = 0xA5                                                # stale bytes must not leak into the comparison
+            note[:8] = np.frombuffer(struct.pack("<II", cap - 8, 0), np.uint8)   # host convention: capacity, type 0
+            bufs = [np.ascontiguousarray(x[c, b * block:(b + 1) * block]) for c in range(2)]
+            p.port(0, ctl); p.port(1, note)
+            p.port(2, bufs[0]); p.port(3, bufs[0]); p.port(4, bufs[1]); p.port(5, bufs[1])
+            p.run(block)
+            size = struct.unpack("<I", note[:4].tobytes())[0]
+            outs.append(note[:8 + size].tobytes())
+        assert len(outs[0]) == len(outs[1]), (b, len(outs[0]), len(outs[1]))
+        assert outs[0] == outs[1], (b, next(i for i in range(len(outs[0])) if outs[0][i] != outs[1][i]))
+        sizes.append(len(outs[0]))
+    g.close(); r.close()
+    return sizes
+
+
+def test_descriptor_and_missing_urid_map():
+    import meters_lv2_b200 as B
+    mine, lib = descriptors(B.LIB_PATH)
+    assert "EBUr128" in mine
+    d = mine["EBUr128"]
+    none = (C.POINTER(Feature) * 1)(None)
+    assert not d.contents.instantiate(d, 48000.0, b"", none)               # no urid:map feature -> NULL (:140-144)
+
+
+def test_silent_ui_no_messages():
+    sizes = drive({}, 6)
+    assert set(sizes) == {16}                                               # bare sequence header while the UI is off
+
+
+def test_gui_session_byte_parity():
+    """UI connects, starts integration with dBTP on, changes radar time, pauses, resets, disconnects."""
+    script = {
+        1: [obj(MTR + b"meteron")],
+        2: [cfg("UISETTINGS", 8 + 64), cfg("START", 0)],
+        40: [cfg("RADARTIME", 30.0)],
+        90: [cfg("PAUSE", 0)],
+        95: [cfg("START", 0), cfg("RADARTIME", 10.0), cfg("RADARTIME", 700.0)],     # out-of-range: reply only
+        140: [cfg("UISETTINGS", 8)],                                                   # dBTP off: tp_max -> -inf
+        150: [cfg("RESET", 0)],
+        170: [obj(MTR + b"meteroff")],
+        175: [obj(MTR + b"meteron")],                                                  # resync of the stored radar, 16 points per cycle
+    }
+    sizes = drive(script, 210)
+    assert max(sizes) > 1500 and sizes[0] == 16
+
+
+def test_transport_follow_and_autoreset():
+    script = {
+        0: [obj(MTR + b"meteron"), cfg("TRANSPORTSYNC", 1.0), cfg("AUTORESET", 1.0)],
+        5: [position(1.0)],
+        30: [position(0.0)],
+        33: [position(1.0)],                                                            # restart: auto reset -> RESETRADAR message
+        50: [cfg("TRANSPORTSYNC", 0.0), position(0.0)],
+        60: [cfg("AUTORESET", 0.0), cfg("START", 0)],
+    }
+    drive(script, 80)
+
+
+def test_small_notify_buffer_and_odd_blocks():
+    """capacity just above the reference's floor: histogram messages are rationed by the space left (:433)"""
+    script = {0: [obj(MTR + b"meteron"), cfg("START", 0)]}
+    drive(script, 120, block=1000, cap=1100)
+    drive(script, 40, block=333, cap=4096, rate=44100.0)
