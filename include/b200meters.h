@@ -234,6 +234,11 @@ int b200m_bim_control (b200m_bim* h, int cmd, void* stream);
 int b200m_bim_run_device (b200m_bim* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
 int b200m_bim_run_host (b200m_bim* h, const float* in, size_t stride, uint32_t nfram);
 int b200m_bim_results (b200m_bim* h, uint32_t inst, int32_t* hist584, int32_t* cnt5, float* minmax2, int64_t* integration_time, void* stream);
+/* 1 if the last run closed a ~5 fps window (self->radar_resync >= fps_limit, src/bitmeter.c:264-267,293); the statistics
+ * as they stood at that moment -- what bim_run publishes in its bim_stats message before the windowed-mode bim_clear
+ * (:269-291,323-325) -- stay readable through b200m_bim_published until the next window closes */
+int b200m_bim_window_closed (const b200m_bim* h);
+int b200m_bim_published (b200m_bim* h, uint32_t inst, int32_t* hist584, int32_t* cnt5, float* minmax2, int64_t* integration_time, void* stream);
 int b200m_sdh_create (b200m_sdh** out, int device, uint32_t n_inst, double rate);
 int b200m_sdh_destroy (b200m_sdh* h);
 int b200m_sdh_control (b200m_sdh* h, int cmd, void* stream);

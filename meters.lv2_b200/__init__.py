@@ -111,6 +111,8 @@ _PROTOS = {
     "b200m_bim_run_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
     "b200m_bim_run_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
     "b200m_bim_results": (C.c_int, [_v, C.c_uint32, _v, _v, _v, _v, _v]),
+    "b200m_bim_window_closed": (C.c_int, [_v]),
+    "b200m_bim_published": (C.c_int, [_v, C.c_uint32, _v, _v, _v, _v, _v]),
     "b200m_sdh_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_double]),
     "b200m_sdh_destroy": (C.c_int, [_v]),
     "b200m_sdh_control": (C.c_int, [_v, C.c_int, _v]),

@@ -51,7 +51,7 @@ inline uint32_t atom_pad (uint32_t n) { return (n + 7u) & ~7u; }
 // (the reference reads notify->atom.size mid-way to ration its histogram messages, src/ebulv2.cc:433).
 class AtomWriter {
 public:
-    LV2_URID t_sequence = 0, t_object = 0, t_int = 0, t_float = 0, t_bool = 0;
+    LV2_URID t_sequence = 0, t_object = 0, t_int = 0, t_float = 0, t_bool = 0, t_long = 0, t_double = 0, t_vector = 0;
 
     void begin_sequence (void* buf, uint32_t capacity)
     {
@@ -73,6 +73,16 @@ public:
     void prop_int (LV2_URID key, int32_t v) { prop (key, t_int, &v); }
     void prop_float (LV2_URID key, float v) { prop (key, t_float, &v); }
     void prop_bool (LV2_URID key, bool v) { const int32_t b = v ? 1 : 0; prop (key, t_bool, &b); }
+    void prop_long (LV2_URID key, int64_t v) { prop8 (key, t_long, &v); }
+    void prop_double (LV2_URID key, double v) { prop8 (key, t_double, &v); }
+    // atom:Vector of n int32 (child_size 4, child_type Int); the data is padded to 8 bytes like every atom body
+    void prop_vector_i32 (LV2_URID key, const int32_t* v, uint32_t n)
+    {
+        const uint32_t head[6] = {key, 0u, 8u + 4u * n, t_vector, 4u, t_int};
+        if (!put (head, sizeof (head))) return;
+        if (!put (v, 4u * (n & ~1u))) return;
+        if (n & 1u) { const uint32_t tail[2] = {(uint32_t)v[n - 1], 0u}; put (tail, sizeof (tail)); }
+    }
     uint32_t sequence_size () const { return base_ ? ((const AtomHead*)base_)->size : 0; }
     bool ok () const { return ok_; }
 
@@ -86,6 +96,12 @@ private:
         off_ += n;
         for (int d = 0; d < depth_; ++d) ((AtomHead*)(base_ + open_[d]))->size += n;
         return true;
+    }
+    void prop8 (LV2_URID key, LV2_URID type, const void* v8)
+    {
+        uint32_t w[6] = {key, 0u, 8u, type, 0u, 0u};          // 8-byte body: no padding
+        memcpy (&w[4], v8, 8);
+        put (w, sizeof (w));
     }
     void prop (LV2_URID key, LV2_URID type, const void* v4)
     {

@@ -17,7 +17,11 @@
 #include "common.cuh"
 #include "lv2_abi.cuh"
 
-namespace b200m { const LV2_Descriptor* lv2_ebur128_descriptor (); }     // lv2_ebur128.cu
+namespace b200m {
+const LV2_Descriptor* lv2_ebur128_descriptor ();        // lv2_ebur128.cu
+const LV2_Descriptor* lv2_sigdisthist_descriptor ();    // lv2_stats.cu
+const LV2_Descriptor* lv2_bitmeter_descriptor ();
+}
 
 namespace {
 
@@ -256,5 +260,7 @@ extern "C" __attribute__ ((visibility ("default"))) const LV2_Descriptor* lv2_de
     constexpr uint32_t n = sizeof (g_desc) / sizeof (g_desc[0]);
     if (index < n) return &g_desc[index];
     if (index == n) return b200m::lv2_ebur128_descriptor ();       // the atom-port plugins follow the control-port ones
+    if (index == n + 1) return b200m::lv2_sigdisthist_descriptor ();
+    if (index == n + 2) return b200m::lv2_bitmeter_descriptor ();
     return nullptr;
 }

@@ -198,6 +198,8 @@ struct b200m_bim {
     int device; uint32_t n_inst; double rate;
     bool average = false, integrating = true; uint64_t itime = 0; int resync = 0;    // uniform host-side control (:146-157)
     int32_t *d_hist = nullptr, *d_cnt = nullptr; float* d_mm = nullptr;
+    // the statistics as they stood when the last ~5 fps window closed, i.e. what bim_run publishes before bim_clear (:267-326)
+    int32_t *d_pub_hist = nullptr, *d_pub_cnt = nullptr; float* d_pub_mm = nullptr; uint64_t pub_itime = 0; bool window_closed = false;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 struct b200m_sdh {
@@ -230,7 +232,15 @@ static int bim_run (b200m_bim* h, const float* d_in, size_t stride, uint32_t n, 
     // ~5 fps window (:264-327): in windowed mode the statistics are cleared after they were published
     const int fps_limit = n * ceil (h->rate / (5.f * n));
     h->resync += n;
-    if (h->resync >= fps_limit) { h->resync = h->resync % fps_limit; if (!h->average) bim_clear (h, 0, st); }
+    h->window_closed = h->resync >= fps_limit;
+    if (h->window_closed) {
+        h->resync = h->resync % fps_limit;
+        B200M_CUDA (cudaMemcpyAsync (h->d_pub_hist, h->d_hist, (size_t)h->n_inst * BIM_LEN * 4, cudaMemcpyDeviceToDevice, st));
+        B200M_CUDA (cudaMemcpyAsync (h->d_pub_cnt, h->d_cnt, (size_t)h->n_inst * 8 * 4, cudaMemcpyDeviceToDevice, st));
+        B200M_CUDA (cudaMemcpyAsync (h->d_pub_mm, h->d_mm, (size_t)h->n_inst * 2 * 4, cudaMemcpyDeviceToDevice, st));
+        h->pub_itime = h->itime;
+        if (!h->average) bim_clear (h, 0, st);
+    }
     B200M_CUDA (cudaGetLastError ());
     return 0;
 }
@@ -264,6 +274,7 @@ int b200m_bim_create (b200m_bim** out, int device, uint32_t n_inst, double rate)
     cudaError_t e = cudaSuccess;
     auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
     A ((void**)&h->d_hist, (size_t)n_inst * BIM_LEN * 4); A ((void**)&h->d_cnt, (size_t)n_inst * 8 * 4); A ((void**)&h->d_mm, (size_t)n_inst * 2 * 4);
+    A ((void**)&h->d_pub_hist, (size_t)n_inst * BIM_LEN * 4); A ((void**)&h->d_pub_cnt, (size_t)n_inst * 8 * 4); A ((void**)&h->d_pub_mm, (size_t)n_inst * 2 * 4);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
     if (e == cudaSuccess) { bim_clear (h, 1, nullptr); e = cudaDeviceSynchronize (); }           // bim_reset at instantiate (:158)
     if (e != cudaSuccess) { int rc = cuda_fail (e, "bim_create", __FILE__, __LINE__); b200m_bim_destroy (h); return rc; }
@@ -275,7 +286,7 @@ int b200m_bim_destroy (b200m_bim* h)
     if (!h) return 0;
     DeviceGuard g (h->device);
     cudaDeviceSynchronize ();
-    cudaFree (h->d_hist); cudaFree (h->d_cnt); cudaFree (h->d_mm); h->stage.release ();
+    cudaFree (h->d_hist); cudaFree (h->d_cnt); cudaFree (h->d_mm); cudaFree (h->d_pub_hist); cudaFree (h->d_pub_cnt); cudaFree (h->d_pub_mm); h->stage.release ();
     if (h->own) cudaStreamDestroy (h->own);
     delete h;
     return 0;
@@ -322,6 +333,19 @@ int b200m_bim_results (b200m_bim* h, uint32_t inst, int32_t* hist584, int32_t* c
     if (minmax2) B200M_CUDA (cudaMemcpyAsync (minmax2, h->d_mm + (size_t)inst * 2, 2 * 4, cudaMemcpyDeviceToHost, st));
     B200M_CUDA (cudaStreamSynchronize (st));
     if (integration_time) *integration_time = (int64_t)h->itime;
+    return 0;
+}
+int b200m_bim_window_closed (const b200m_bim* h) { return h && h->window_closed ? 1 : 0; }
+int b200m_bim_published (b200m_bim* h, uint32_t inst, int32_t* hist584, int32_t* cnt5, float* minmax2, int64_t* integration_time, void* stream)
+{
+    if (!h || inst >= h->n_inst) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    cudaStream_t st = h->last_host ? h->own : (cudaStream_t)stream;
+    if (hist584) B200M_CUDA (cudaMemcpyAsync (hist584, h->d_pub_hist + (size_t)inst * BIM_LEN, BIM_LEN * 4, cudaMemcpyDeviceToHost, st));
+    if (cnt5) B200M_CUDA (cudaMemcpyAsync (cnt5, h->d_pub_cnt + (size_t)inst * 8, 5 * 4, cudaMemcpyDeviceToHost, st));
+    if (minmax2) B200M_CUDA (cudaMemcpyAsync (minmax2, h->d_pub_mm + (size_t)inst * 2, 2 * 4, cudaMemcpyDeviceToHost, st));
+    B200M_CUDA (cudaStreamSynchronize (st));
+    if (integration_time) *integration_time = (int64_t)h->pub_itime;
     return 0;
 }
 

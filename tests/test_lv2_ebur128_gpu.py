@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ATOM = b"http://lv2plug.in/ns/ext/atom#"
 TIME = b"http://lv2plug.in/ns/ext/time#"
 MTR = b"http://gareus.org/oss/lv2/meters#"
-CTL = dict(START=1, PAUSE=2, RESET=3, TRANSPORTSYNC=4, AUTORESET=5, RADARTIME=6, UISETTINGS=7)      # src/uris.h:187-203
+CTL = dict(START=1, PAUSE=2, RESET=3, TRANSPORTSYNC=4, AUTORESET=5, RADARTIME=6, UISETTINGS=7, WINDOWED=13, AVERAGE=14)   # src/uris.h:187-203
 CAP = 8192
 
 
@@ -51,12 +51,12 @@ def sequence(events):
     return a
 
 
-def drive(script, nblocks, block=1024, x=None, cap=CAP, rate=48000.0):
-    """script: {block index: [events]} fed to the control port of both plugins; returns nothing, asserts byte parity"""
+def drive(script, nblocks, block=1024, x=None, cap=CAP, rate=48000.0, name="EBUr128", nch=2):
+    """script: {block index: [events]} fed to the control port of both plugins; asserts byte parity of the notify port"""
     import meters_lv2_b200 as B
     mine, l1 = descriptors(B.LIB_PATH)
     ref, l2 = descriptors(O.PATHS["reference"])
-    g, r = Plugin(mine["EBUr128"], rate), Plugin(ref["EBUr128"], rate)
+    g, r = Plugin(mine[name], rate), Plugin(ref[name], rate)
     if x is None:
         x = S.white(2, block * nblocks, seed=17) * np.float32(4.0)
     empty = sequence([])
@@ -68,9 +68,10 @@ def drive(script, nblocks, block=1024, x=None, cap=CAP, rate=48000.0):
         for p, note in ((g, notes[0]), (r, notes[1])):
             note[:] = 0xA5                                                # stale bytes must not leak into the comparison
             note[:8] = np.frombuffer(struct.pack("<II", cap - 8, 0), np.uint8)   # host convention: capacity, type 0
-            bufs = [np.ascontiguousarray(x[c, b * block:(b + 1) * block]) for c in range(2)]
+            bufs = [np.ascontiguousarray(x[c, b * block:(b + 1) * block]) for c in range(nch)]
             p.port(0, ctl); p.port(1, note)
-            p.port(2, bufs[0]); p.port(3, bufs[0]); p.port(4, bufs[1]); p.port(5, bufs[1])
+            for c in range(nch):
+                p.port(2 + 2 * c, bufs[c]); p.port(3 + 2 * c, bufs[c])
             p.run(block)
             size = struct.unpack("<I", note[:4].tobytes())[0]
             outs.append(note[:8 + size].tobytes())
