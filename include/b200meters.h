@@ -186,6 +186,28 @@ b200m_ebu* b200m_r128_ebu (b200m_r128* h);     /* the underlying banks (histogra
 b200m_tpk* b200m_r128_tpk (b200m_r128* h);
 
 /* ======================================================================================
+ * DR-14 / TPnRMS bank — replaces dr14_run (src/dr14.c:354-482) for n_inst instances of
+ * n_channels (1 or 2): Kmeterdsp::process + TruePeakdsp::process + read() per channel and, with dr_mode, the 3 s
+ * window statistics of dr14_calc_rms_score (:285-352).  The result block mirrors the plugin's output ports
+ * (DRPortIndex :27-43): all values in dB as the reference writes them.  Every instance shares the 3 s window clock, so
+ * reset_peaks (:241-258) is bank-wide.  dr_mode needs rate >= 2731 Hz (a window longer than the largest block).
+ * ====================================================================================== */
+typedef struct b200m_dr14 b200m_dr14;
+typedef struct b200m_dr14_result {
+    float v_rms[2], v_peak[2];       /* *p_v_rms = coeff_to_db (km rms), *p_v_peak = coeff_to_db (true-peak ballistic m) (:430-431) */
+    float m_peak[2], m_rms[2];       /* coeff_to_db (max true peak) (:432); DR mode: top-20 % RMS score, else coeff_to_db (km peak) (:444-446) */
+    float dr[2], dr_total;           /* DR mode: per channel and averaged, clamped to 1..20; 21 = not yet valid (:436-458) */
+    float block_count;               /* 3.0 * num_fragments (:460) */
+} b200m_dr14_result;
+int b200m_dr14_create (b200m_dr14** out, int device, uint32_t n_inst, uint32_t n_channels, double rate, int dr_mode);
+int b200m_dr14_destroy (b200m_dr14* h);
+int b200m_dr14_run_device (b200m_dr14* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);   /* rows: inst * n_channels + c */
+int b200m_dr14_run_host (b200m_dr14* h, const float* in, size_t stride, uint32_t nfram);
+int b200m_dr14_reset (b200m_dr14* h, void* stream);                                       /* reset_peaks, every instance */
+int b200m_dr14_results (b200m_dr14* h, b200m_dr14_result* out, void* stream);
+int b200m_dr14_histogram (b200m_dr14* h, uint32_t inst, uint32_t chan, uint32_t* hist8000, void* stream);   /* hist[c] (:46,309-311) */
+
+/* ======================================================================================
  * Stereo correlation bank — replaces LV2M::Stcorrdsp (jmeters/stcorrdsp.h:27-55) as driven by
  * cor_run (src/meters.cc:511-536) and xfer_run (src/xfer.c:248-251).
  * ====================================================================================== */

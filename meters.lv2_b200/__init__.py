@@ -87,6 +87,13 @@ _PROTOS = {
     "b200m_r128_ebu": (_v, [_v]),
     "b200m_r128_tpk": (_v, [_v]),
     # Stcorr
+    "b200m_dr14_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_double, C.c_int]),
+    "b200m_dr14_destroy": (C.c_int, [_v]),
+    "b200m_dr14_run_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
+    "b200m_dr14_run_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
+    "b200m_dr14_reset": (C.c_int, [_v, _v]),
+    "b200m_dr14_results": (C.c_int, [_v, _v, _v]),
+    "b200m_dr14_histogram": (C.c_int, [_v, C.c_uint32, C.c_uint32, _v, _v]),
     "b200m_cor_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_int, C.c_float, C.c_float]),
     "b200m_cor_destroy": (C.c_int, [_v]),
     "b200m_cor_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, _v]),
@@ -534,6 +541,46 @@ class SigDistHist(_StatBank):
         h = np.empty(361, np.int32); mp = np.empty(2, np.int32); av = np.empty(3, np.float64); it = C.c_int64(0)
         _ck(lib().b200m_sdh_results(self.h, inst, _np_ptr(h), _np_ptr(mp), _np_ptr(av), C.byref(it), _stream_ptr(stream)))
         return h, mp, av, it.value
+
+
+DR14_RESULT_DTYPE = np.dtype([("v_rms", "<f4", 2), ("v_peak", "<f4", 2), ("m_peak", "<f4", 2), ("m_rms", "<f4", 2), ("dr", "<f4", 2),
+                              ("dr_total", "<f4"), ("block_count", "<f4")])
+
+
+class DR14(_Bank):
+    """N x dr14_run (src/dr14.c:354-482): DR-14 mode (dr_mode=True) or TPnRMS (False); results = the plugin's output ports."""
+    _destroy = "b200m_dr14_destroy"
+
+    def __init__(self, n_inst, n_channels=2, rate=48000.0, dr_mode=True, device=0):
+        super().__init__()
+        self.n_inst, self.nchan = n_inst, n_channels
+        _ck(lib().b200m_dr14_create(C.byref(self.h), device, n_inst, n_channels, rate, int(bool(dr_mode))))
+
+    def run(self, x, stream=None):
+        if isinstance(x, np.ndarray) or not x.is_cuda:
+            p, s, rows, n = _host_planar(x)
+            assert rows == self.n_inst * self.nchan
+            _ck(lib().b200m_dr14_run_host(self.h, p, s, n))
+        else:
+            p, s, rows, n = _dev_ptr(x)
+            assert rows == self.n_inst * self.nchan
+            _ck(lib().b200m_dr14_run_device(self.h, p, s, n, _stream_ptr(stream)))
+
+    def run_ptr(self, ptr, stride, nfram, stream=None):
+        _ck(lib().b200m_dr14_run_device(self.h, C.c_void_p(ptr), stride, nfram, _stream_ptr(stream)))
+
+    def reset(self, stream=None):
+        _ck(lib().b200m_dr14_reset(self.h, _stream_ptr(stream)))
+
+    def results(self, stream=None):
+        out = np.empty(self.n_inst, DR14_RESULT_DTYPE)
+        _ck(lib().b200m_dr14_results(self.h, _np_ptr(out), _stream_ptr(stream)))
+        return out
+
+    def histogram(self, inst, chan, stream=None):
+        h = np.empty(8000, np.uint32)
+        _ck(lib().b200m_dr14_histogram(self.h, inst, chan, _np_ptr(h), _stream_ptr(stream)))
+        return h
 
 
 class Spectr30(_Bank):

@@ -1,13 +1,14 @@
 // lv2_shim.cu — per-instance LV2 façade over the batched engine: `lv2_descriptor()` with the reference's URIs,
 // port indices and run() semantics, so that an LV2 host can load this library where it loaded meters.so.
 //
-// Covers the 24 control-port plugins (src/meters.cc:745-792 lists all 38 descriptors) and, in lv2_ebur128.cu, EBUr128:
+// Covers the 22 pure control-port plugins (src/meters.cc:745-792 lists all 38 descriptors):
 //   VU / BBC / EBU / DIN / NOR mono+stereo (run :298-331), BBCM6 (bbcm_run :552-589),
 //   COR (cor_run :511-536), dBTPmono/stereo (dbtp_run :438-508), K12/K14/K20 mono/stereo (kmeter_run :333-418),
-//   spectr30mono/stereo (spectrum_run, src/spectrumlv2.c:159-257), TPnRMSmono/stereo (dr14_run without DR mode,
-//   src/dr14.c:354-482; its float control ports carry all results, the atom control port is ignored).
-// DR14, phasewheel, stereoscope, goniometer, bitmeter and SigDistHist publish their results only through LV2 atom
-// messages (src/uris.h:279-318) and are not wrapped yet: use the batch API.
+//   spectr30mono/stereo (spectrum_run, src/spectrumlv2.c:159-257);
+// the plugins with atom ports live in lv2_ebur128.cu (EBUr128), lv2_stats.cu (SigDistHist, bitmeter) and lv2_dr14.cu
+// (dr14mono/stereo, TPnRMSmono/stereo).
+// Not wrapped yet: goniometer, phasewheel, stereoscope (their notify ports stream raw audio to the GUI, src/xfer.c) and
+// the surround meters.
 // Each LV2 instance owns a bank of one instance; run() is synchronous (host buffers in, ports out), exactly the
 // reference's calling convention (robtk/jackwrap.c:531-544).  LV2 core types are restated from the LV2
 // specification (the SDK is not installed); the struct layout is the stable public C ABI.
@@ -21,11 +22,12 @@ namespace b200m {
 const LV2_Descriptor* lv2_ebur128_descriptor ();        // lv2_ebur128.cu
 const LV2_Descriptor* lv2_sigdisthist_descriptor ();    // lv2_stats.cu
 const LV2_Descriptor* lv2_bitmeter_descriptor ();
+const LV2_Descriptor* lv2_dr14_descriptor (uint32_t i);   // lv2_dr14.cu: dr14mono, dr14stereo, TPnRMSmono, TPnRMSstereo
 }
 
 namespace {
 
-enum Kind { K_COR, K_DBTP, K_KMETER, K_SPEC, K_TPNRMS, K_NEEDLE, K_BBCM6 };
+enum Kind { K_COR, K_DBTP, K_KMETER, K_SPEC, K_NEEDLE, K_BBCM6 };
 
 struct Shim {
     Kind kind; uint32_t chn;
@@ -34,14 +36,10 @@ struct Shim {
     float* port[68] = {nullptr};          // raw port pointers, indexed as in the reference's enums
     float* stage = nullptr; size_t stage_cap = 0;   // pinned [chn][cap] planar staging
     float p_refl = -9999, peak_max[2] = {0, 0}, peak_hold = 0;   // src/meters.cc:245-251
-    float m_dbtp[2] = {0, 0};                                    // TPnRMS true-peak hold (src/dr14.c:78,430)
 };
 
 // port enums: src/meters.cc:59-70 (MTR_*), src/spectrumlv2.c:35-44 (SA_*)
 enum { MTR_REFLEVEL = 0, MTR_INPUT0, MTR_OUTPUT0, MTR_LEVEL0, MTR_INPUT1, MTR_OUTPUT1, MTR_LEVEL1, MTR_PEAK0, MTR_PEAK1, MTR_HOLD };
-// TPnRMS: DRPortIndex, src/dr14.c:27-43
-enum { DR_CONTROL = 0, DR_HOST_TRANSPORT, DR_RESET, DR_BLKCNT, DR_INPUT0, DR_OUTPUT0, DR_V_PEAK0, DR_M_PEAK0, DR_V_RMS0, DR_M_RMS0, DR_DR0,
-       DR_INPUT1, DR_OUTPUT1, DR_V_PEAK1, DR_M_PEAK1, DR_V_RMS1, DR_M_RMS1, DR_DR1, DR_TOTAL };
 enum { SA_SPEED = 60, SA_RESET = 61, SA_AMP = 62, SA_STATE = 63, SA_INPUT0 = 64, SA_OUTPUT0 = 65, SA_INPUT1 = 66, SA_OUTPUT1 = 67 };
 
 bool stage_in (Shim* s, const float* const* in, uint32_t n)
@@ -70,7 +68,6 @@ LV2_Handle shim_instantiate (const LV2_Descriptor* d, double rate, const char*, 
     int rc = -1;
     if (!strcmp (u, "COR")) { s->kind = K_COR; s->chn = 2; rc = b200m_cor_create (&s->cor, 0, 1, (int)rate, 2e3f, 0.3f); }          // :204-207
     else if (!strncmp (u, "dBTP", 4)) { s->kind = K_DBTP; s->chn = strstr (u, "stereo") ? 2 : 1; rc = b200m_tpk_create (&s->tpk, 0, s->chn, (float)rate, B200M_TPK_TRUEPEAK); }
-    else if (!strncmp (u, "TPnRMS", 6)) { s->kind = K_TPNRMS; s->chn = strstr (u, "stereo") ? 2 : 1; rc = b200m_tpk_create (&s->tpk, 0, s->chn, (float)rate, B200M_TPK_TRUEPEAK | B200M_TPK_KMETER); }
     else if (u[0] == 'K') { s->kind = K_KMETER; s->chn = strstr (u, "stereo") ? 2 : 1; rc = b200m_tpk_create (&s->tpk, 0, s->chn, (float)rate, B200M_TPK_KMETER); }
     else if (!strcmp (u, "BBCM6")) { s->kind = K_BBCM6; s->chn = 2; rc = b200m_ppm_create (&s->ppm, 0, 1, (float)rate, B200M_PPM_MS); }     // :208-214
     else if (!strncmp (u, "VU", 2) || !strncmp (u, "BBC", 3) || !strncmp (u, "EBU", 3) || !strncmp (u, "DIN", 3) || !strncmp (u, "NOR", 3)) {
@@ -170,33 +167,6 @@ void run_tpk (Shim* s, uint32_t n)
     }
 }
 
-// dr14_run in TPnRMS mode (src/dr14.c:354-482 with dr_operation_mode == false).  The atom control port (GUI reset /
-// host transport messages) is not parsed: only the reset-button control port is honoured.
-float coeff_to_db (const float coeff) { if (coeff < .0001) return -80; return 20 * log10f (coeff); }   // src/dr14.c:236-239
-
-void run_tpnrms (Shim* s, uint32_t n)
-{
-    float* in[2] = {s->port[DR_INPUT0], s->port[DR_INPUT1]}; float* out[2] = {s->port[DR_OUTPUT0], s->port[DR_OUTPUT1]};
-    if (s->port[DR_RESET] && *s->port[DR_RESET] != 0) {     // reset_peaks (:241-258): K-meters reset, true-peak hold cleared
-        s->m_dbtp[0] = s->m_dbtp[1] = 0;
-        b200m_tpk_reset_kmeter (s->tpk, nullptr);
-    }
-    if (!stage_in (s, in, n)) return;
-    if (b200m_tpk_process_host (s->tpk, s->stage, s->stage_cap, n, B200M_TP_MODE_PROCESS)) return;
-    b200m_tpk_result r[2];
-    if (b200m_tpk_read_device (s->tpk, nullptr) || b200m_tpk_results (s->tpk, r, nullptr)) return;
-    static const int pv_peak[2] = {DR_V_PEAK0, DR_V_PEAK1}, pm_peak[2] = {DR_M_PEAK0, DR_M_PEAK1}, pv_rms[2] = {DR_V_RMS0, DR_V_RMS1}, pm_rms[2] = {DR_M_RMS0, DR_M_RMS1};
-    for (uint32_t c = 0; c < s->chn; ++c) {                  // :425-450
-        if (s->m_dbtp[c] < r[c].tp_p) s->m_dbtp[c] = r[c].tp_p;
-        if (s->port[pv_rms[c]])  *s->port[pv_rms[c]]  = coeff_to_db (r[c].km_rms);
-        if (s->port[pv_peak[c]]) *s->port[pv_peak[c]] = coeff_to_db (r[c].tp_m);
-        if (s->port[pm_peak[c]]) *s->port[pm_peak[c]] = coeff_to_db (s->m_dbtp[c]);
-        if (s->port[pm_rms[c]])  *s->port[pm_rms[c]]  = coeff_to_db (r[c].km_peak);
-    }
-    if (s->port[DR_BLKCNT]) *s->port[DR_BLKCNT] = 0.0f;      // 3.0 * num_fragments: no 3 s fragments outside DR mode
-    pass_through (in, out, s->chn, n);
-}
-
 // run() and bbcm_run() of the needle meters (src/meters.cc:298-331,552-589)
 void run_needle (Shim* s, uint32_t n)
 {
@@ -237,7 +207,6 @@ void shim_run (LV2_Handle h, uint32_t n)
     case K_COR: run_cor (s, n); break;
     case K_DBTP: case K_KMETER: run_tpk (s, n); break;
     case K_SPEC: run_spec (s, n); break;
-    case K_TPNRMS: run_tpnrms (s, n); break;
     case K_NEEDLE: case K_BBCM6: run_needle (s, n); break;
     }
 }
@@ -248,7 +217,7 @@ const LV2_Descriptor g_desc[] = {
     DESC ("DINmono"), DESC ("DINstereo"), DESC ("NORmono"), DESC ("NORstereo"), DESC ("BBCM6"),
     DESC ("COR"), DESC ("spectr30mono"), DESC ("dBTPmono"), DESC ("dBTPstereo"),
     DESC ("K12mono"), DESC ("K14mono"), DESC ("K20mono"), DESC ("K12stereo"), DESC ("K14stereo"), DESC ("K20stereo"),
-    DESC ("spectr30stereo"), DESC ("TPnRMSmono"), DESC ("TPnRMSstereo"),
+    DESC ("spectr30stereo"),
 };
 
 }  // namespace
@@ -262,5 +231,6 @@ extern "C" __attribute__ ((visibility ("default"))) const LV2_Descriptor* lv2_de
     if (index == n) return b200m::lv2_ebur128_descriptor ();       // the atom-port plugins follow the control-port ones
     if (index == n + 1) return b200m::lv2_sigdisthist_descriptor ();
     if (index == n + 2) return b200m::lv2_bitmeter_descriptor ();
+    if (index < n + 7) return b200m::lv2_dr14_descriptor (index - (n + 3));
     return nullptr;
 }

@@ -19,7 +19,7 @@ __global__ void r128_fill_kernel (int n, float* p, float v) { const int i = bloc
 extern "C" int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready,
                                    int (*after_k1) (void*), void* after_arg);
 int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st, int nsl, const uint32_t* bounds, cudaEvent_t* ready,
-                        float* r128_tpmax, bool pdl);
+                        float* r128_tpmax, bool pdl, const void* dr);
 
 using namespace b200m;
 
@@ -45,7 +45,7 @@ struct R128Step { b200m_r128* h; const float* d_in; size_t stride; uint32_t nfra
 static int r128_tp_behind_k1 (void* p)
 {
     R128Step* a = (R128Step*)p;
-    return tpk_process_sliced (a->h->tpk, a->d_in, a->stride, a->nfram, B200M_TP_MODE_MAX, a->st, 1, a->bc, nullptr, a->h->d_tpmax, true);
+    return tpk_process_sliced (a->h->tpk, a->d_in, a->stride, a->nfram, B200M_TP_MODE_MAX, a->st, 1, a->bc, nullptr, a->h->d_tpmax, true, nullptr);
 }
 
 static int r128_run (b200m_r128* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, int nsl, cudaEvent_t* ready)
@@ -67,7 +67,7 @@ static int r128_run (b200m_r128* h, const float* d_in, size_t stride, uint32_t n
     if (int rc = ebu_process_sliced (h->ebu, d_in, stride, nfram, st, nsl, bi, ready, pdl ? r128_tp_behind_k1 : nullptr, &step)) return rc;
     if (h->dbtp) {
         if (!pdl) {
-            if (int rc = tpk_process_sliced (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, conc ? h->side : st, nsl, bc, conc ? ready : nullptr, h->d_tpmax, false)) return rc;
+            if (int rc = tpk_process_sliced (h->tpk, d_in, stride, nfram, B200M_TP_MODE_MAX, conc ? h->side : st, nsl, bc, conc ? ready : nullptr, h->d_tpmax, false, nullptr)) return rc;
             if (conc) { B200M_CUDA (cudaEventRecord (h->ev_tp, h->side)); B200M_CUDA (cudaStreamWaitEvent (st, h->ev_tp, 0)); }
         }
     } else {

@@ -17,6 +17,7 @@
 #include <math.h>
 #include <stdlib.h>
 #include "common.cuh"
+#include "tpk_internal.cuh"
 
 namespace b200m {
 
@@ -280,10 +281,10 @@ B200M_DEV void fir16 (const float (&w)[52], const float* xw, float (&o)[16], con
 // 16 channels x {z1 filter, z2 filter} = 32 busy lanes (the two one-pole attack filters are independent until
 // the per-sample m = max (m, z1 + z2), which costs one shuffle), so the serial part issues ~1/4 of the
 // instructions it would with one channel per lane.
-template <int CH, int TC, bool TP, bool TPMAX, bool KM, bool IMM>
+template <int CH, int TC, bool TP, bool TPMAX, bool KM, bool IMM, bool DR>
 __global__ void __launch_bounds__ (TPK_THREADS)
 tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, int elide0, TpkParams prm,
-            TpkState st, float* __restrict__ dbg, float* __restrict__ r128_tpmax)
+            TpkState st, float* __restrict__ dbg, float* __restrict__ r128_tpmax, TpkDr dr)
 {
     // processes channels [c_first, n_chan): `n_chan` is the END of the slice (absolute channel index)
     constexpr int XP = 48 + TC + 4;               // x row pitch (floats): 16-byte multiple
@@ -354,6 +355,12 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
         kz1 = a > 50 ? 50 : (a < 0 ? 0 : a);
         kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
     }
+    // role 2 (idle otherwise while the serial lanes run): DR-14 sums, lane = channel
+    const bool dr_warp = DR && BAL && KM && dr.rms_sum != nullptr && wrole == 2;
+    const int dch = min (c0 + (lane & (CH - 1)), n_chan - 1);
+    const bool dr_live = dr_warp && lane < CH && (c0 + lane) < n_chan;
+    float drs = 0, drp = 0;
+    if (dr_warp) { drs = dr.rms_sum[dch]; drp = dr.peak_cur[dch]; }
     float vmax = 0.0f;                                                    // process_max: plain running max (:109-122), per FIR lane
     const int km_n = (nfram / 4) * 4;                                     // "n /= 4" drops n mod 4 samples (:79)
 
@@ -453,9 +460,28 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
                 kz2 = __fadd_rn (kz2, __fmul_rn (om4, __fsub_rn (kz1, kz2)));
             }
         }
+        if (dr_warp) {
+            const float* xr = &xs[buf][lane & (CH - 1)][48];
+            for (int j = 0; j < len; ++j) {
+                const float v = xr[j];
+                drs = __fadd_rn (drs, __fmul_rn (v, v));
+                drp = drp > v ? drp : v;                    // MAX (peak_cur, v) on the RAW sample (:408), NaN-transparent like the macro
+                if (s0 + j == dr.cut) {                      // ++scnt > slmt (:410): the 3 s window closes after this sample
+                    const float other = dr.nch == 2 ? __shfl_xor_sync (0xffffffffu, drs, 1) : drs;
+                    const bool silent = !((double)drs > dr.silent_thr) && !((double)other > dr.silent_thr);
+                    if (dr_live) {
+                        dr.emit_valid[dch] = silent ? 0 : 1;
+                        if (!silent) { dr.emit_rms[dch] = drs; dr.emit_peak[dch] = drp; }
+                    }
+                    drs = 0.0f;                              // silent windows keep peak_cur (:293-296)
+                    if (!silent) drp = 0.0f;
+                }
+            }
+        }
         __syncthreads ();                                   // ob / xs[buf] free for reuse
     }
     cp_async_wait<0> ();
+    if (dr_live) { dr.rms_sum[dch] = drs; dr.peak_cur[dch] = drp; }
 
     // ---- end of block --------------------------------------------------------------------
     if (TP) {
@@ -560,6 +586,7 @@ struct b200m_tpk {
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
     int imm = 0;                            // host table == literal table: use the immediate-coefficient kernels
     int elide0 = 0;                         // phase 0 of the table is the unit-tap delay fir16's guard assumes
+    TpkDr dr{}; bool dr_on = false;         // DR-14 accumulation of the next process() call (set by dr14.cu)
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 
@@ -594,13 +621,19 @@ static void tpk_design (float fsamp, TpkParams& prm, float* ctab)
     zita_table (ctab, 24, 4, 1.0);                  // setup (fsamp, fsamp * 4.0, 1, 24, 1.0): np = 4, ratio-only
 }
 
+namespace b200m {
+void tpk_set_dr (b200m_tpk* h, const TpkDr* dr) { h->dr_on = dr != nullptr; if (dr) h->dr = *dr; }
+const b200m_tpk_result* tpk_device_results (b200m_tpk* h) { return h->d_res; }
+}
+
 static cudaStream_t tpk_stream (b200m_tpk* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
 
 // process()/process_max() of every meter; channel slices [bounds[s], bounds[s+1]) are launched separately, slice s
 // after event ready[s] when `ready` is given (see ebu_process_sliced).
 int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st,
-                        int nsl, const uint32_t* bounds, cudaEvent_t* ready, float* r128_tpmax, bool pdl)
+                        int nsl, const uint32_t* bounds, cudaEvent_t* ready, float* r128_tpmax, bool pdl, const void* dr_v)
 {
+    const TpkDr* dr = (const TpkDr*)dr_v;
     const bool tp = h->flags & B200M_TPK_TRUEPEAK, km = h->flags & B200M_TPK_KMETER;
     TpkParams prm = h->prm;
     // Kmeterdsp::process (:65-70): per-period fallback multiplier, a pure function of n
@@ -613,16 +646,18 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
         if (ready) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
         // cudaLaunchKernelEx so that the EBUr128 cycle can attach the programmatic-serialization attribute (pdl): the kernel
         // may then start while the K-weighting kernel launched just before it on `st` is still running (r128.cu)
+        TpkDr drp = {};
+        if (dr && tp && km && tp_mode == B200M_TP_MODE_PROCESS) drp = *dr;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = blk; cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-#define TPK_GO(CH, TC, TP, MX, KM) do { cfg.gridDim = dim3 ((ce - cf + CH - 1) / CH); \
-            if (h->imm) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax)); \
-            else B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, false>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax)); } while (0)
-        if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true); else TPK_GO (8, 256, true, true, false); }
-        else if (tp) { if (km) TPK_GO (16, 64, true, false, true); else TPK_GO (16, 64, true, false, false); }
-        else tpk_kernel<16, 64, false, false, true, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax);
+#define TPK_GO(CH, TC, TP, MX, KM, DRM) do { cfg.gridDim = dim3 ((ce - cf + CH - 1) / CH); \
+            if (h->imm) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); \
+            else B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, false, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); } while (0)
+        if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true, false); else TPK_GO (8, 256, true, true, false, false); }
+        else if (tp) { if (km) { if (drp.rms_sum) TPK_GO (16, 64, true, false, true, true); else TPK_GO (16, 64, true, false, true, false); } else TPK_GO (16, 64, true, false, false, false); }
+        else tpk_kernel<16, 64, false, false, true, false, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp);
 #undef TPK_GO
         B200M_LAUNCHED (1);
     }
@@ -633,7 +668,7 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
 static int tpk_process (b200m_tpk* h, const float* d_in, size_t stride, uint32_t nfram, uint32_t tp_mode, cudaStream_t st)
 {
     const uint32_t bounds[2] = {0, h->n_chan};
-    return tpk_process_sliced (h, d_in, stride, nfram, tp_mode, st, 1, bounds, nullptr, nullptr, false);
+    return tpk_process_sliced (h, d_in, stride, nfram, tp_mode, st, 1, bounds, nullptr, nullptr, false, h->dr_on ? &h->dr : nullptr);
 }
 
 extern "C" {
