@@ -1,14 +1,14 @@
 // lv2_shim.cu — per-instance LV2 façade over the batched engine: `lv2_descriptor()` with the reference's URIs,
 // port indices and run() semantics, so that an LV2 host can load this library where it loaded meters.so.
 //
-// Covers the 22 pure control-port plugins (src/meters.cc:745-792 lists all 38 descriptors):
+// Covers the 28 pure control-port plugins (src/meters.cc:745-792 lists all 38 descriptors):
 //   VU / BBC / EBU / DIN / NOR mono+stereo (run :298-331), BBCM6 (bbcm_run :552-589),
 //   COR (cor_run :511-536), dBTPmono/stereo (dbtp_run :438-508), K12/K14/K20 mono/stereo (kmeter_run :333-418),
-//   spectr30mono/stereo (spectrum_run, src/spectrumlv2.c:159-257);
+//   spectr30mono/stereo (spectrum_run, src/spectrumlv2.c:159-257), surround3..8 (sur_run, src/surmeter.c:115-147);
 // the plugins with atom ports live in lv2_ebur128.cu (EBUr128), lv2_stats.cu (SigDistHist, bitmeter) and lv2_dr14.cu
 // (dr14mono/stereo, TPnRMSmono/stereo).
-// Not wrapped yet: goniometer, phasewheel, stereoscope (their notify ports stream raw audio to the GUI, src/xfer.c) and
-// the surround meters.
+// Not wrapped: goniometer, phasewheel, stereoscope -- their notify ports stream the raw audio to the GUI, which does the
+// analysis there (src/xfer.c, gui/*.c); the GPU analysis of that path is the batch API b200m_pw_* / b200m_cor_* (DESIGN.md §7).
 // Each LV2 instance owns a bank of one instance; run() is synchronous (host buffers in, ports out), exactly the
 // reference's calling convention (robtk/jackwrap.c:531-544).  LV2 core types are restated from the LV2
 // specification (the SDK is not installed); the struct layout is the stable public C ABI.
@@ -27,7 +27,7 @@ const LV2_Descriptor* lv2_dr14_descriptor (uint32_t i);   // lv2_dr14.cu: dr14mo
 
 namespace {
 
-enum Kind { K_COR, K_DBTP, K_KMETER, K_SPEC, K_NEEDLE, K_BBCM6 };
+enum Kind { K_COR, K_DBTP, K_KMETER, K_SPEC, K_NEEDLE, K_BBCM6, K_SUR };
 
 struct Shim {
     Kind kind; uint32_t chn;
@@ -35,6 +35,7 @@ struct Shim {
     float rlgain = 1.0f;                  // needle meters: reference-level gain (src/meters.cc:243,303-306)
     float* port[68] = {nullptr};          // raw port pointers, indexed as in the reference's enums
     float* stage = nullptr; size_t stage_cap = 0;   // pinned [chn][cap] planar staging
+    float* stage2 = nullptr; size_t stage2_cap = 0; // surround meters: [8][cap] = the 4 correlation pairs
     float p_refl = -9999, peak_max[2] = {0, 0}, peak_hold = 0;   // src/meters.cc:245-251
 };
 
@@ -76,6 +77,12 @@ LV2_Handle shim_instantiate (const LV2_Descriptor* d, double rate, const char*, 
         const int kind = !strncmp (u, "VU", 2) ? B200M_PPM_VU : (!strncmp (u, "DIN", 3) || !strncmp (u, "NOR", 3)) ? B200M_PPM_IEC1 : B200M_PPM_IEC2;
         rc = b200m_ppm_create (&s->ppm, 0, s->chn, (float)rate, kind);
     }
+    else if (!strncmp (u, "surround", 8) && u[8] >= '3' && u[8] <= '8' && !u[9]) {          // src/surmeter.c:24-70
+        s->kind = K_SUR; s->chn = (uint32_t)(u[8] - '0');
+        rc = b200m_tpk_create (&s->tpk, 0, s->chn, (float)rate, B200M_TPK_KMETER);
+        if (!rc) rc = b200m_cor_create (&s->cor, 0, 4, (int)rate, 2e3f, 0.3f);
+        if (rc) { b200m_tpk_destroy (s->tpk); b200m_cor_destroy (s->cor); }
+    }
     else if (!strncmp (u, "spectr30", 8)) { s->kind = K_SPEC; s->chn = strstr (u, "stereo") ? 2 : 1; rc = b200m_spec_create (&s->spec, 0, 1, s->chn, rate); }
     if (rc) { delete s; return nullptr; }                  // instantiate() -> NULL, as the reference does on failure
     return s;
@@ -92,6 +99,7 @@ void shim_cleanup (LV2_Handle h)
     Shim* s = (Shim*)h;
     b200m_cor_destroy (s->cor); b200m_tpk_destroy (s->tpk); b200m_spec_destroy (s->spec); b200m_ppm_destroy (s->ppm);
     if (s->stage) b200m_host_free (s->stage);
+    if (s->stage2) b200m_host_free (s->stage2);
     delete s;
 }
 
@@ -199,6 +207,42 @@ void run_spec (Shim* s, uint32_t n)
     pass_through (in, out, s->chn, n);
 }
 
+// sur_run (src/surmeter.c:115-147): 3 or 4 selectable-pair correlation meters + one K-meter per channel
+void run_sur (Shim* s, uint32_t n)
+{
+    float* in[8]; float* out[8];
+    for (uint32_t c = 0; c < s->chn; ++c) { in[c] = s->port[13 + 4 * c]; out[c] = s->port[14 + 4 * c]; if (!in[c]) return; }
+    if (n > s->stage2_cap) {
+        if (s->stage2) b200m_host_free (s->stage2);
+        s->stage2 = nullptr; s->stage2_cap = 0;
+        const size_t cap = n < 1024 ? 1024 : B200M_MAX_BLOCK;
+        if (b200m_host_alloc ((void**)&s->stage2, 8 * cap * sizeof (float))) return;
+        s->stage2_cap = cap;
+    }
+    const uint32_t cors = s->chn > 3 ? 4 : 3;
+    for (uint32_t c = 0; c < 4; ++c) {
+        float* a = s->stage2 + (size_t)(2 * c) * s->stage2_cap; float* b = a + s->stage2_cap;
+        if (c < cors && s->port[1 + 3 * c] && s->port[2 + 3 * c]) {
+            uint32_t in_a = (uint32_t)rintf (*s->port[1 + 3 * c]), in_b = (uint32_t)rintf (*s->port[2 + 3 * c]);
+            if (in_a >= s->chn) in_a = s->chn - 1;
+            if (in_b >= s->chn) in_b = s->chn - 1;
+            memcpy (a, in[in_a], n * sizeof (float)); memcpy (b, in[in_b], n * sizeof (float));
+        } else { memset (a, 0, n * sizeof (float)); memset (b, 0, n * sizeof (float)); }     // cor4[3] idles on a 3-channel meter
+    }
+    float cv[4] = {0, 0, 0, 0};
+    if (b200m_cor_process_host (s->cor, s->stage2, s->stage2_cap, n) || b200m_cor_results (s->cor, cv, nullptr)) return;
+    for (uint32_t c = 0; c < cors; ++c) if (s->port[3 + 3 * c]) *s->port[3 + 3 * c] = cv[c];
+    if (!stage_in (s, in, n)) return;
+    b200m_tpk_result r[8];
+    if (b200m_tpk_process_host (s->tpk, s->stage, s->stage_cap, n, B200M_TP_MODE_PROCESS) || b200m_tpk_read_device (s->tpk, nullptr) ||
+        b200m_tpk_results (s->tpk, r, nullptr)) return;
+    for (uint32_t c = 0; c < s->chn; ++c) {
+        if (s->port[15 + 4 * c]) *s->port[15 + 4 * c] = r[c].km_rms;         // Kmeterdsp::read (m, p): *level = m, *peak = p
+        if (s->port[16 + 4 * c]) *s->port[16 + 4 * c] = r[c].km_peak;
+    }
+    pass_through (in, out, s->chn, n);
+}
+
 void shim_run (LV2_Handle h, uint32_t n)
 {
     Shim* s = (Shim*)h;
@@ -208,6 +252,7 @@ void shim_run (LV2_Handle h, uint32_t n)
     case K_DBTP: case K_KMETER: run_tpk (s, n); break;
     case K_SPEC: run_spec (s, n); break;
     case K_NEEDLE: case K_BBCM6: run_needle (s, n); break;
+    case K_SUR: run_sur (s, n); break;
     }
 }
 
@@ -218,6 +263,7 @@ const LV2_Descriptor g_desc[] = {
     DESC ("COR"), DESC ("spectr30mono"), DESC ("dBTPmono"), DESC ("dBTPstereo"),
     DESC ("K12mono"), DESC ("K14mono"), DESC ("K20mono"), DESC ("K12stereo"), DESC ("K14stereo"), DESC ("K20stereo"),
     DESC ("spectr30stereo"),
+    DESC ("surround8"), DESC ("surround7"), DESC ("surround6"), DESC ("surround5"), DESC ("surround4"), DESC ("surround3"),
 };
 
 }  // namespace

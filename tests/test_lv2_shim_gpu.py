@@ -101,7 +101,7 @@ def test_descriptor_table():
     d, _ = descriptors(B.LIB_PATH)
     assert set(d) == {"COR", "spectr30mono", "spectr30stereo", "dBTPmono", "dBTPstereo", "K12mono", "K14mono", "K20mono",
                       "K12stereo", "K14stereo", "K20stereo", "TPnRMSmono", "TPnRMSstereo", "BBCM6", "EBUr128", "SigDistHist", "bitmeter", "dr14mono", "dr14stereo"} | {
-                          k + c for k in ("VU", "BBC", "EBU", "DIN", "NOR") for c in ("mono", "stereo")}
+                          k + c for k in ("VU", "BBC", "EBU", "DIN", "NOR") for c in ("mono", "stereo")} | {"surround%d" % k for k in range(3, 9)}
     r, _ = descriptors(O.PATHS["reference"])
     assert set(d) <= set(r) and len(r) == 38          # src/meters.cc:745-792
 
@@ -229,4 +229,32 @@ def test_tpnrms_plugin_vs_reference_plugin():
             p.run(1024)
         for i in (3, 6, 7, 8, 9, 13, 14, 15, 16):
             assert u32(ports[0][i])[0] == u32(ports[1][i])[0], (b, i, ports[0][i][0], ports[1][i][0])
+    g.close(); r.close()
+
+
+@pytest.mark.parametrize("chn,pairs", [(5, [(0, 1), (2, 3), (0, 4), (9, 1)]), (3, [(0, 1), (1, 2), (2, 0)]), (8, [(7, 6), (5, 4), (3, 2), (1, 0)])])
+def test_surround_meters_vs_reference_plugins(chn, pairs):
+    """sur_run (src/surmeter.c:115-147): selectable-pair correlation meters (out-of-range selections clamp) + K-meters"""
+    g, r, keep = _pair("surround%d" % chn)
+    x = S.white(8, 1024 * 20, seed=97)
+    x[1] = 0.6 * x[0] + 0.4 * x[1]; x[3] = -x[2]                           # correlated / anti-correlated pairs
+    outs = []
+    for p in (g, r):
+        o = {}
+        for c, (a, b) in enumerate(pairs):
+            pa = np.full(1, a, np.float32); pb = np.full(1, b, np.float32); pc = np.zeros(1, np.float32)
+            p.port(1 + 3 * c, pa); p.port(2 + 3 * c, pb); p.port(3 + 3 * c, pc); o[3 + 3 * c] = pc
+        for c in range(chn):
+            lv = np.zeros(1, np.float32); pk = np.zeros(1, np.float32)
+            p.port(15 + 4 * c, lv); p.port(16 + 4 * c, pk); o[15 + 4 * c] = lv; o[16 + 4 * c] = pk
+        p.port(0, np.zeros(1, np.float32))
+        outs.append(o)
+    for b in range(20):
+        for p in (g, r):
+            for c in range(chn):
+                a = np.ascontiguousarray(x[c, b * 1024:(b + 1) * 1024])
+                p.port(13 + 4 * c, a); p.port(14 + 4 * c, a)
+            p.run(1024)
+        for i in outs[0]:
+            assert u32(outs[0][i])[0] == u32(outs[1][i])[0], (chn, b, i, outs[0][i][0], outs[1][i][0])
     g.close(); r.close()
