@@ -75,14 +75,16 @@ public:
     void prop_bool (LV2_URID key, bool v) { const int32_t b = v ? 1 : 0; prop (key, t_bool, &b); }
     void prop_long (LV2_URID key, int64_t v) { prop8 (key, t_long, &v); }
     void prop_double (LV2_URID key, double v) { prop8 (key, t_double, &v); }
-    // atom:Vector of n int32 (child_size 4, child_type Int); the data is padded to 8 bytes like every atom body
-    void prop_vector_i32 (LV2_URID key, const int32_t* v, uint32_t n)
+    // atom:Vector of n 4-byte elements (child_size 4, child_type Int or Float); the data is padded to 8 bytes like every atom body
+    void prop_vector32 (LV2_URID key, LV2_URID child_type, const void* v, uint32_t n)
     {
-        const uint32_t head[6] = {key, 0u, 8u + 4u * n, t_vector, 4u, t_int};
+        const uint32_t head[6] = {key, 0u, 8u + 4u * n, t_vector, 4u, child_type};
         if (!put (head, sizeof (head))) return;
         if (!put (v, 4u * (n & ~1u))) return;
-        if (n & 1u) { const uint32_t tail[2] = {(uint32_t)v[n - 1], 0u}; put (tail, sizeof (tail)); }
+        if (n & 1u) { uint32_t tail[2] = {0u, 0u}; memcpy (tail, (const uint8_t*)v + 4u * (n - 1), 4); put (tail, sizeof (tail)); }
     }
+    void prop_vector_i32 (LV2_URID key, const int32_t* v, uint32_t n) { prop_vector32 (key, t_int, v, n); }
+    void prop_vector_f32 (LV2_URID key, const float* v, uint32_t n) { prop_vector32 (key, t_float, v, n); }
     uint32_t sequence_size () const { return base_ ? ((const AtomHead*)base_)->size : 0; }
     bool ok () const { return ok_; }
 

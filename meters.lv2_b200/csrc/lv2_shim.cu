@@ -7,8 +7,9 @@
 //   spectr30mono/stereo (spectrum_run, src/spectrumlv2.c:159-257), surround3..8 (sur_run, src/surmeter.c:115-147);
 // the plugins with atom ports live in lv2_ebur128.cu (EBUr128), lv2_stats.cu (SigDistHist, bitmeter) and lv2_dr14.cu
 // (dr14mono/stereo, TPnRMSmono/stereo).
-// Not wrapped: goniometer, phasewheel, stereoscope -- their notify ports stream the raw audio to the GUI, which does the
-// analysis there (src/xfer.c, gui/*.c); the GPU analysis of that path is the batch API b200m_pw_* / b200m_cor_* (DESIGN.md §7).
+// lv2_xfer.cu adds phasewheel and stereoscope (raw-audio forwarding to the GUI + correlation).  Not wrapped: goniometer,
+// whose GUI reaches into the plugin's C struct through LV2 instance-access (ring buffer, mutex: src/goniometer.h) -- that
+// struct layout is a private ABI between the reference's plugin and its own GUI.
 // Each LV2 instance owns a bank of one instance; run() is synchronous (host buffers in, ports out), exactly the
 // reference's calling convention (robtk/jackwrap.c:531-544).  LV2 core types are restated from the LV2
 // specification (the SDK is not installed); the struct layout is the stable public C ABI.
@@ -23,6 +24,7 @@ const LV2_Descriptor* lv2_ebur128_descriptor ();        // lv2_ebur128.cu
 const LV2_Descriptor* lv2_sigdisthist_descriptor ();    // lv2_stats.cu
 const LV2_Descriptor* lv2_bitmeter_descriptor ();
 const LV2_Descriptor* lv2_dr14_descriptor (uint32_t i);   // lv2_dr14.cu: dr14mono, dr14stereo, TPnRMSmono, TPnRMSstereo
+const LV2_Descriptor* lv2_xfer_descriptor (uint32_t i);   // lv2_xfer.cu: phasewheel, stereoscope
 }
 
 namespace {
@@ -278,5 +280,6 @@ extern "C" __attribute__ ((visibility ("default"))) const LV2_Descriptor* lv2_de
     if (index == n + 1) return b200m::lv2_sigdisthist_descriptor ();
     if (index == n + 2) return b200m::lv2_bitmeter_descriptor ();
     if (index < n + 7) return b200m::lv2_dr14_descriptor (index - (n + 3));
+    if (index < n + 9) return b200m::lv2_xfer_descriptor (index - (n + 7));
     return nullptr;
 }
