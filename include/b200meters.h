@@ -290,6 +290,11 @@ int b200m_spec_coeffs (const b200m_spec* h, double* W1080);              /* [30]
 typedef struct b200m_pw b200m_pw;
 int b200m_pw_create (b200m_pw** out, int device, uint32_t n_inst, uint32_t fft_bins, double rate);
 int b200m_pw_destroy (b200m_pw* h);
+/* which GUI's process_audio follows the FFTs: PHASEWHEEL (default; phase difference, level, peak: gui/phasewheel.c:1307-1342)
+ * or STEREOSCOPE (gui/stereoscope.c:705-741: smoothed lr[] returned in `phase`, smoothed level[]; db_thresh fixed at 1e-20,
+ * no peak; the reference GUI defaults to fft_bins 512).  Re-initialises the outputs like the GUI's reinitialize_fft. */
+enum { B200M_PW_PHASEWHEEL = 0, B200M_PW_STEREOSCOPE = 1 };
+int b200m_pw_set_mode (b200m_pw* h, int mode);
 /* returns (via *fired) whether this call completed an analysis (fftx_run()==0) */
 int b200m_pw_process_device (b200m_pw* h, const float* d_in, size_t stride, uint32_t nfram, float db_thresh, int* fired, void* stream);
 int b200m_pw_process_host (b200m_pw* h, const float* in, size_t stride, uint32_t nfram, float db_thresh, int* fired);

@@ -136,6 +136,7 @@ _PROTOS = {
     "b200m_spec_coeffs": (C.c_int, [_v, _v]),
     # phasewheel
     "b200m_pw_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_uint32, C.c_double]),
+    "b200m_pw_set_mode": (C.c_int, [_v, C.c_int]),
     "b200m_pw_destroy": (C.c_int, [_v]),
     "b200m_pw_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_int), _v]),
     "b200m_pw_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_float, C.POINTER(C.c_int)]),
@@ -646,6 +647,10 @@ class Phasewheel(_Bank):
         fired = C.c_int(0)
         _ck(lib().b200m_pw_process_device(self.h, C.c_void_p(ptr), stride, nfram, db_thresh, C.byref(fired), _stream_ptr(stream)))
         return fired.value
+
+    def set_mode(self, mode):
+        """0: phasewheel process_audio; 1: stereoscope process_audio (read() then returns lr[] as `phase`)"""
+        _ck(lib().b200m_pw_set_mode(self.h, int(mode)))
 
     def read(self, stream=None):
         ph = np.empty((self.n_inst, self.bins), np.float32); lv = np.empty((self.n_inst, self.bins), np.float32)

@@ -36,7 +36,7 @@ B200M_DEV float2 cmul (float2 a, float2 b) { return make_float2 (fmaf (a.x, b.x,
 __global__ void __launch_bounds__ (PW_THREADS)
 pw_analyze_kernel (const float* __restrict__ ring, int N, int log2n, int start, const float* __restrict__ window,
                    const float2* __restrict__ tw, float db_thresh, float* __restrict__ rawp /* [inst][4][bins] */,
-                   float* __restrict__ phase, float* __restrict__ level, float* __restrict__ peak)
+                   float* __restrict__ phase, float* __restrict__ level, float* __restrict__ peak, int mode)
 {
     extern __shared__ __align__ (16) float2 sm[];          // two ping-pong buffers of N complex values
     __shared__ float red[PW_THREADS / 32];
@@ -99,7 +99,19 @@ pw_analyze_kernel (const float* __restrict__ ring, int N, int log2n, int start, 
             fl = atan2f (lim, lre); fr = atan2f (rim, rre);
         }
         pwl[k] = pl; pwr[k] = pr; phl[k] = fl; phr[k] = fr;
-        if (k >= 1 && k < bins - 1) {
+        if (mode == 1 && k >= 1 && k < bins - 1) {
+            // stereoscope process_audio (gui/stereoscope.c:713-739): phase[] holds ui->lr[], both outputs are smoothed state
+            float* lrp = phase + (size_t)inst * bins + k; float* lvp = level + (size_t)inst * bins + k;
+            if (pl < 1e-20f && pr < 1e-20f) { *lrp = 0.5f; *lvp = 0.0f; }
+            else {
+                const float lv = pl > pr ? pl : pr;
+                const float dq = __fsub_rn (__fsqrt_rn (pr), __fsqrt_rn (pl));
+                const float lr = __double2float_rn (.5 + __ddiv_rn (__dmul_rn (.5, (double)dq), (double)__fsqrt_rn (lv)));
+                const float l0 = *lvp, r0 = *lrp;
+                *lvp = __double2float_rn ((double)l0 + (__dmul_rn (.1, (double)__fsub_rn (lv, l0)) + 1e-20));
+                *lrp = __double2float_rn ((double)r0 + (__dmul_rn (.1, (double)__fsub_rn (lr, r0)) + 1e-10));
+            }
+        } else if (k >= 1 && k < bins - 1) {
             float ph, lv;
             if (pl < db_thresh || pr < db_thresh) { ph = 0.0f; lv = -100.0f; }
             else { ph = __fsub_rn (fr, fl); lv = pl > pr ? pl : pr; if (lv > pk) pk = lv; }   // MAX(a,b) = a > b ? a : b
@@ -111,7 +123,7 @@ pw_analyze_kernel (const float* __restrict__ ring, int N, int log2n, int start, 
     for (int o = 16; o; o >>= 1) pk = fmaxf (pk, __shfl_xor_sync (0xffffffffu, pk, o));
     if ((tid & 31) == 0) red[tid >> 5] = pk;
     __syncthreads ();
-    if (tid == 0) {
+    if (tid == 0 && mode == 0) {
         for (int i = 1; i < PW_THREADS / 32; ++i) pk = fmaxf (pk, red[i]);
         // ui->peak += .04 * (peak - ui->peak) + 1e-15;  (double arithmetic on a float lvalue, :1333-1335)
         float up = peak[inst];
@@ -122,7 +134,7 @@ pw_analyze_kernel (const float* __restrict__ ring, int N, int log2n, int start, 
     }
 }
 
-__global__ void pw_init_kernel (size_t n, float* level) { const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) level[i] = -100.0f; }
+__global__ void pw_init_kernel (size_t n, float* level, float* phase, float ph0) { const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; if (i < n) { level[i] = -100.0f; phase[i] = ph0; } }
 
 }  // namespace b200m
 
@@ -131,6 +143,7 @@ using namespace b200m;
 struct b200m_pw {
     int device; uint32_t n_inst, bins, N; int log2n; double rate;
     uint32_t rboff, smps, sps, step;                       // shared ring offset + 25 Hz analysis clock (gui/fft.c:43-64)
+    int mode = 0;                                          // 0: phasewheel process_audio, 1: stereoscope process_audio
     float *d_ring = nullptr, *d_win = nullptr, *d_raw = nullptr, *d_phase = nullptr, *d_level = nullptr, *d_peak = nullptr;
     float2* d_tw = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
@@ -161,7 +174,7 @@ static int pw_process (b200m_pw* h, const float* d_in, size_t stride, uint32_t n
             h->step = h->smps; h->smps = 0;
             if (step == last_fire) {
                 pw_analyze_kernel<<<h->n_inst, PW_THREADS, (size_t)2 * h->N * sizeof (float2), st>>> (
-                    h->d_ring, (int)h->N, h->log2n, (int)h->rboff, h->d_win, h->d_tw, db_thresh, h->d_raw, h->d_phase, h->d_level, h->d_peak);
+                    h->d_ring, (int)h->N, h->log2n, (int)h->rboff, h->d_win, h->d_tw, db_thresh, h->d_raw, h->d_phase, h->d_level, h->d_peak, h->mode);
                 B200M_LAUNCHED (1);
             }
             any = 1;
@@ -218,7 +231,7 @@ int b200m_pw_create (b200m_pw** out, int device, uint32_t n_inst, uint32_t fft_b
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         const size_t n = (size_t)n_inst * fft_bins;       // ui->level[i] = -100, ui->phase[i] = 0 (phasewheel.c:199-202)
-        pw_init_kernel<<<(unsigned)((n + 255) / 256), 256>>> (n, h->d_level);
+        pw_init_kernel<<<(unsigned)((n + 255) / 256), 256>>> (n, h->d_level, h->d_phase, 0.0f);
         B200M_LAUNCHED (1);
         e = cudaDeviceSynchronize ();
     }
@@ -236,6 +249,22 @@ int b200m_pw_destroy (b200m_pw* h)
     h->stage.release ();
     if (h->own) cudaStreamDestroy (h->own);
     delete h;
+    return 0;
+}
+
+int b200m_pw_set_mode (b200m_pw* h, int mode)
+{
+    // selects which GUI's process_audio follows the two FFTs and re-initialises the outputs as that GUI's reinitialize_fft
+    // does: phasewheel phase = 0 / level = -100 (gui/phasewheel.c:199-202), stereoscope lr = 0.5 / level = -100 (gui/stereoscope.c:143-146)
+    if (!h || (mode != B200M_PW_PHASEWHEEL && mode != B200M_PW_STEREOSCOPE)) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    B200M_CUDA (cudaDeviceSynchronize ());
+    h->mode = mode;
+    const size_t n = (size_t)h->n_inst * h->bins;
+    pw_init_kernel<<<(unsigned)((n + 255) / 256), 256>>> (n, h->d_level, h->d_phase, mode == B200M_PW_STEREOSCOPE ? 0.5f : 0.0f);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaMemset (h->d_peak, 0, h->n_inst * sizeof (float)));
+    B200M_CUDA (cudaDeviceSynchronize ());
     return 0;
 }
 

@@ -121,6 +121,7 @@ void  orc_sdh_read    (void* h, int inst, int32_t* hist361, int32_t* maxpeak2, d
  * kind "reference" returns NULL from orc_pw_create: FFTW3 is not vendored and absent here. */
 void* orc_pw_create   (int n_inst, int fft_bins, double rate);
 void  orc_pw_destroy  (void* h);
+void  orc_pw_set_mode (void* h, int mode);   /* 0: phasewheel process_audio, 1: stereoscope process_audio (gui/stereoscope.c:705-741; phase[] = lr[]) */
 int   orc_pw_process  (void* h, const float* in, size_t stride, int nfram, float db_thresh, int nthreads);
                        /* returns 1 if an analysis fired (all instances are in lock step) */
 void  orc_pw_read     (void* h, float* phase, float* level, float* peak); /* [n_inst][fft_bins] x2, [n_inst] */

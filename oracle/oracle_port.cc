@@ -582,14 +582,28 @@ struct FftA {                                    // struct FFTAnalysis, gui/fft.
     }
 };
 struct Pw {
-    FftA a, b; int bins; std::vector<float> phase, level; float peak;
+    FftA a, b; int bins; std::vector<float> phase, level; float peak; int mode = 0;   // mode 1: stereoscope (phase[] holds lr[])
     void init (int fft_bins, double rate) {      // reinitialize_fft, gui/phasewheel.c:178-202
         bins = fft_bins; a.init (2 * bins, rate, 25); b.init (2 * bins, rate, 25);
         phase.assign (bins, 0.f); level.assign (bins, -100.f); peak = 0;
     }
+    void set_mode (int m) {                      // stereoscope: reinitialize_fft, gui/stereoscope.c:143-146
+        mode = m; phase.assign (bins, m ? 0.5f : 0.f); level.assign (bins, -100.f); peak = 0;
+    }
     int process (const float* l, const float* r, int n, float thr) {   // process_audio :1307-1342
         a.run (l, n);
         const bool display = !b.run (r, n);
+        if (display && mode == 1) {              // stereoscope process_audio, gui/stereoscope.c:705-741
+            const float db_thresh = 1e-20;
+            for (int i = 1; i < bins - 1; ++i) {
+                if (a.power[i] < db_thresh && b.power[i] < db_thresh) { phase[i] = 0.5; level[i] = 0; continue; }
+                const float lv = a.power[i] > b.power[i] ? a.power[i] : b.power[i];
+                const float lr = .5 + .5 * (sqrtf (b.power[i]) - sqrtf (a.power[i])) / sqrtf (lv);
+                level[i] += .1 * (lv - level[i]) + 1e-20;
+                phase[i] += .1 * (lr - phase[i]) + 1e-10;
+            }
+            return 1;
+        }
         if (display) {
             float pk = 0;
             for (int i = 1; i < bins - 1; ++i) {
@@ -772,6 +786,7 @@ void  orc_sdh_read (void* h, int inst, int32_t* hist, int32_t* mp, double* av, i
 
 void* orc_pw_create (int n, int fft_bins, double rate) { auto* b = new Bank<Pw>; b->n = n; b->v.resize (n); for (auto& p : b->v) p.init (fft_bins, rate); return b; }
 void orc_pw_destroy (void* h) { delete (Bank<Pw>*)h; }
+void orc_pw_set_mode (void* h, int mode) { for (auto& p : ((Bank<Pw>*)h)->v) p.set_mode (mode); }
 int orc_pw_process (void* h, const float* in, size_t stride, int nfram, float thr, int nthreads) {
     auto* b = (Bank<Pw>*)h; std::vector<int> fired (b->n, 0);
     par_for (b->n, nthreads, [&] (int a, int e) { for (int i = a; i < e; ++i) fired[i] = b->v[i].process (in + (size_t)(2 * i) * stride, in + (size_t)(2 * i + 1) * stride, nfram, thr); });

@@ -390,6 +390,7 @@ void  orc_sdh_read (void* h, int inst, int32_t* hist, int32_t* mp, double* av, i
 /* ------------------------------------------------------------------ phasewheel: FFTW3 absent */
 void* orc_pw_create (int, int, double) { return 0; }
 void  orc_pw_destroy (void*) {}
+void  orc_pw_set_mode (void*, int) {}
 int   orc_pw_process (void*, const float*, size_t, int, float, int) { return 0; }
 void  orc_pw_read (void*, float*, float*, float*) {}
 void  orc_pw_raw (void*, int, float*, float*, float*, float*) {}

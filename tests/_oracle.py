@@ -87,6 +87,7 @@ def _proto(lib):
         "orc_spec_coeffs": (None, [_v, _v]),
         "orc_pw_create": (_v, [C.c_int, C.c_int, C.c_double]),
         "orc_pw_destroy": (None, [_v]),
+        "orc_pw_set_mode": (None, [_v, C.c_int]),
         "orc_pw_process": (C.c_int, [_v, _v, C.c_size_t, C.c_int, C.c_float, C.c_int]),
         "orc_pw_read": (None, [_v, _v, _v, _v]),
         "orc_pw_raw": (None, [_v, C.c_int, _v, _v, _v, _v]),
@@ -422,6 +423,10 @@ class Phasewheel:
     def __del__(self):
         if getattr(self, "h", None):
             self.L.orc_pw_destroy(self.h); self.h = None
+
+    def set_mode(self, mode):
+        """0: phasewheel, 1: stereoscope process_audio (read() then returns lr[] in place of phase[])"""
+        self.L.orc_pw_set_mode(self.h, mode)
 
     def process(self, x, db_thresh=1e-6, nthreads=1):
         p, s = planar(x)

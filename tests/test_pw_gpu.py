@@ -67,3 +67,31 @@ def test_phasewheel_tones_and_phase_difference():
 def test_other_sizes_and_ragged_blocks(bins, blocks):
     x = S.white(2 * 3, sum(blocks), seed=42)
     _compare(3, bins, blocks, x)
+
+
+@pytest.mark.parametrize("bins", [512, 1024])
+def test_stereoscope_process_audio(bins):
+    """stereoscope mode (gui/stereoscope.c:705-741): smoothed lr[] / level[] after the same two FFTs; tolerance as for the
+    phasewheel path (FFT "parity unpinned"), the smoothing itself is restated operation for operation"""
+    import torch
+    import meters_lv2_b200 as B
+    n_inst, nb = 5, 24
+    x = S.white(2 * n_inst, 1024 * nb, seed=43)
+    x[1] *= 0.25; x[2] = x[3]                                   # hard-left-ish pair, identical pair (lr -> 0.5)
+    x[4:6, 1024 * 10:] = 0.0                                    # goes silent: lr = 0.5, level = 0 branch
+    g = B.Phasewheel(n_inst, bins); g.set_mode(1)
+    o = O.Phasewheel(n_inst, bins, kind="port"); o.set_mode(1)
+    xd = torch.from_numpy(x).cuda()
+    fired = 0
+    for b in range(nb):
+        fg = g.process(xd[:, b * 1024:(b + 1) * 1024]); fo = o.process(np.ascontiguousarray(x[:, b * 1024:(b + 1) * 1024]), nthreads=4)
+        assert fg == fo
+        fired += fg
+        lr, lv, _ = g.read(); olr, olv, _ = o.read()
+        assert np.allclose(lv[:, 1:bins - 1], olv[:, 1:bins - 1], rtol=3e-4, atol=1e-9 * max(1e-30, float(olv.max())))
+        strong = olv[:, 1:bins - 1] > 1e-5 * olv.max()
+        assert np.abs(lr[:, 1:bins - 1] - olr[:, 1:bins - 1])[strong].max() < 2e-3 if strong.any() else True
+    assert fired >= 10
+    lr, lv, _ = g.read()
+    assert abs(float(np.median(lr[1, 1:bins - 1])) - 0.5) < 0.02          # identical channels sit in the middle
+    assert float(np.median(lr[0, 1:bins - 1])) < 0.35                     # right channel 12 dB down: pulled left
