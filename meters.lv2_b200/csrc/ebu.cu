@@ -17,9 +17,16 @@
 
 namespace b200m {
 
-constexpr int EBU_TILE   = 64;            // samples per smem tile
-constexpr int EBU_ROWP   = EBU_TILE + 4;  // padded row pitch (floats): 68 = 4 mod 32 -> LDS.128 conflict free
-constexpr int EBU_STAGES = 3;             // cp.async pipeline depth (2 tiles = 128 samples in flight per channel)
+#ifndef B200M_EBU_TILE
+#define B200M_EBU_TILE 64
+#endif
+#ifndef B200M_EBU_STAGES
+#define B200M_EBU_STAGES 3
+#endif
+constexpr int EBU_TILE   = B200M_EBU_TILE;   // samples per smem tile (64 or 128)
+constexpr int EBU_ROWP   = EBU_TILE + 4;  // padded row pitch (floats): = 4 mod 32 -> LDS.128 conflict free
+constexpr int EBU_STAGES = B200M_EBU_STAGES; // cp.async pipeline depth (2 tiles = 128 samples in flight per channel)
+static_assert (EBU_TILE == 64 || EBU_TILE == 128, "tile geometry");
 constexpr int EBU_WARPS  = 4;             // warps per CTA: one per SM sub-partition, each an independent 32-channel pipeline
 constexpr int EBU_WARP_FLOATS = EBU_STAGES * 32 * EBU_ROWP;
 constexpr int EBU_SMEM_BYTES = EBU_WARPS * EBU_WARP_FLOATS * 4;
@@ -75,27 +82,29 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k
     const bool live = (k0 + lane) < k_end;
     const int ntiles = (nfram + EBU_TILE - 1) / EBU_TILE;
     const bool full_warp = k0 + 32 <= k_end;
-    const float* src_base = in + (size_t)min (k0 + (lane >> 4), k_end - 1) * stride + (lane & 15) * 4;
+    const float* src_base = in + (size_t)min (k0 + lane / (EBU_TILE / 4), k_end - 1) * stride + (lane & (EBU_TILE / 4 - 1)) * 4;
 
     auto issue = [&] (int t) {
         if (t < ntiles) {
             float* dst = tile + (t % EBU_STAGES) * (32 * EBU_ROWP);
             const int s0 = t * EBU_TILE;
+            constexpr int LPR = EBU_TILE / 4;                    // lanes per row (16-byte pieces), rows per pass = 32 / LPR
+            constexpr int RPP = 32 / LPR;
             if (ALIGNED) {
-                const int c4 = (lane & 15) * 4;                  // column of this lane's 16-byte piece
+                const int c4 = (lane & (LPR - 1)) * 4;           // column of this lane's 16-byte piece
                 const int left = (nfram - (s0 + c4)) * 4;        // bytes still inside the block
                 const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
                 if (full_warp) {
-                    // rows 2i + (lane >> 4): one base pointer per lane, a constant 2-row step (all 32 channels exist)
+                    // rows RPP * i + lane / LPR: one base pointer per lane, a constant row step (all 32 channels exist)
                     const float* sp = nb ? src_base + s0 : in;
-                    const size_t step = nb ? 2 * stride : 0;
-                    float* d = dst + (lane >> 4) * EBU_ROWP + c4;
+                    const size_t step = nb ? RPP * stride : 0;
+                    float* d = dst + (lane / LPR) * EBU_ROWP + c4;
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) cp_async16 (d + i * 2 * EBU_ROWP, sp + i * step, nb);
+                    for (int i = 0; i < 32 / RPP; ++i) cp_async16 (d + i * RPP * EBU_ROWP, sp + i * step, nb);
                 } else {
 #pragma unroll 4
-                    for (int i = 0; i < 16; ++i) {
-                        const int r = 2 * i + (lane >> 4);
+                    for (int i = 0; i < 32 / RPP; ++i) {
+                        const int r = RPP * i + lane / LPR;
                         const int kr = min (k0 + r, k_end - 1);
                         const float* src = in + (size_t)kr * stride + s0 + c4;
                         cp_async16 (dst + r * EBU_ROWP + c4, nb ? src : in, nb);
@@ -106,7 +115,7 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k
                 for (int r = 0; r < 32; ++r) {
                     const int kr = min (k0 + r, k_end - 1);
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {
+                    for (int h = 0; h < EBU_TILE / 32; ++h) {
                         const int c = lane + 32 * h;
                         const bool ok = (s0 + c) < nfram;
                         cp_async4 (dst + r * EBU_ROWP + c, ok ? in + (size_t)kr * stride + s0 + c : in, ok ? 4 : 0);
@@ -186,6 +195,8 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k
                 if (a == cend) chunk_end ();
             }
         }
+        // requested after tile t is consumed, not before: measured 178 vs 183 us per EBUr128 cycle (the earlier request competes
+        // with the recurrence for issue slots), 64-sample tiles x 3 stages vs 128 x 2: +5 us per cycle for -1.5 us standalone
         __syncwarp ();
         issue (t + EBU_STAGES - 1);
     }
