@@ -143,7 +143,9 @@ void run_tpk (Shim* s, uint32_t n)
     if (!stage_in (s, in, n)) return;
     if (b200m_tpk_process_host (s->tpk, s->stage, s->stage_cap, n, B200M_TP_MODE_PROCESS)) return;
     pass_through (in, out, s->chn, n);
-    if (reinit) {                                          // force parameter change (:381-389, :476-489)
+    if (reinit) {                                          // force parameter change (:381-389, :476-489); no read() in such a cycle
+        b200m_tpk_result sync[2];
+        b200m_tpk_results (s->tpk, sync, nullptr);          // stream sync only: run() must not return while the upload of `stage` is in flight
         if (km) { if (s->chn == 1) *s->port[MTR_OUTPUT1] = -1 - (rand () & 0xffff); else *s->port[MTR_HOLD] = -1 - (rand () & 0xffff); }
         else if (s->chn == 1) { *s->port[MTR_LEVEL0] = -500 - (rand () & 0xffff); *s->port[MTR_INPUT1] = -500 - (rand () & 0xffff); }
         else { for (int p : {MTR_LEVEL0, MTR_LEVEL1, MTR_PEAK0, MTR_PEAK1}) *s->port[p] = -500 - (rand () & 0xffff); }

@@ -170,6 +170,9 @@ void bim_run (StatsPlugin* p, uint32_t n)
         }
     }
     if (!stage_block (p, n) || b200m_bim_run_host (p->bim, p->stage, p->stage_cap, n)) return;
+    // run() is synchronous for the host: the staging block is rewritten next cycle, so the asynchronous upload and the scan
+    // must have finished before we return even when nothing is published (a results call with no outputs = stream sync)
+    if (b200m_bim_results (p->bim, 0, nullptr, nullptr, nullptr, nullptr, nullptr)) return;
     const bool closed = b200m_bim_window_closed (p->bim) != 0;
     if (closed || p->send_state_to_ui) {                       // :267-327
         if (p->ui_active && (p->integrating || p->send_state_to_ui)) {
@@ -235,6 +238,7 @@ void sdh_run (StatsPlugin* p, uint32_t n)
         }
     }
     if (!stage_block (p, n) || b200m_sdh_run_host (p->sdh, p->stage, p->stage_cap, n)) return;
+    if (b200m_sdh_results (p->sdh, 0, nullptr, nullptr, nullptr, nullptr, nullptr)) return;      // synchronous run(), see bim_run
     const double lim = p->rate / 25.f;                         // const int fps_limit = MAX (rate / 25.f, n_samples)  (:329)
     const int fps_limit = (int)(lim > n ? lim : (double)n);
     p->radar_resync += (int)n;
