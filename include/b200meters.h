@@ -107,6 +107,9 @@ int b200m_ebu_results (b200m_ebu* h, b200m_ebu_result* out, void* stream);
 /* histogram_M()/histogram_S() (:91-92) of one instance: 751 + 751 int32 */
 int b200m_ebu_histogram (b200m_ebu* h, uint32_t inst, int32_t* hist_M, int32_t* hist_S, void* stream);
 /* K-weighting coefficients as designed on the host (detect_init, :263-293): a0 a1 a2 b1 b2 c3 c4 */
+size_t b200m_ebu_snapshot_size (b200m_ebu* h);                          /* see b200m_r128_snapshot */
+int b200m_ebu_snapshot (b200m_ebu* h, void* buf, size_t bytes, void* stream);
+int b200m_ebu_restore (b200m_ebu* h, const void* buf, size_t bytes, void* stream);
 int b200m_ebu_coeffs (const b200m_ebu* h, float out7[7]);
 /* internal state of one instance for differential tests: z[nchan][4], power ring[64], frpwr,
  * counters {frcnt, wrind, div1, div2} */
@@ -152,6 +155,9 @@ int b200m_tpk_reset (b200m_tpk* h, int32_t chan, void* stream);
 int b200m_tpk_reset_kmeter (b200m_tpk* h, void* stream);
 /* host-designed constants: w[4] = w1 w2 w3 g (truepeakdsp.cc:153-157); ctab[120] = zita table
  * (zita-resampler/resampler-table.cc:52-75, hl=24 np=4 fr=1); km[2] = omega, (float)hold */
+size_t b200m_tpk_snapshot_size (b200m_tpk* h);                          /* see b200m_r128_snapshot */
+int b200m_tpk_snapshot (b200m_tpk* h, void* buf, size_t bytes, void* stream);
+int b200m_tpk_restore (b200m_tpk* h, const void* buf, size_t bytes, void* stream);
 int b200m_tpk_coeffs (const b200m_tpk* h, float w[4], float ctab[120], float km[2]);
 /* internal state for differential tests, arrays of n_chan: tp {m,p,z1,z2,res}, km [n][8] as
  * z1 z2 rms peak fall cnt fpp flag */
@@ -182,6 +188,13 @@ int b200m_r128_results (b200m_r128* h, b200m_ebu_result* ebu_out, float* tp_max_
 int b200m_r128_set_dbtp (b200m_r128* h, int enable);
 /* histogram_M() / histogram_S() of one instance (src/ebulv2.cc:425-429), ordered after the bank's last run */
 int b200m_r128_histogram (b200m_r128* h, uint32_t inst, int32_t* hist_M, int32_t* hist_S, void* stream);
+/* Checkpoint / resume (new: the reference saves only UI settings, never DSP state -- src/ebulv2.cc:513-548): the complete
+ * state of the bank (filters, 64-fragment rings, both histograms of every instance, gating clocks, true-peak histories and
+ * holds) as one host blob.  restore() needs a bank created with the same n_inst / fsamp; processing then continues
+ * bit-identically to the bank the snapshot was taken from.  Also available per bank: b200m_ebu_* / b200m_tpk_*. */
+size_t b200m_r128_snapshot_size (b200m_r128* h);
+int b200m_r128_snapshot (b200m_r128* h, void* buf, size_t bytes, void* stream);
+int b200m_r128_restore (b200m_r128* h, const void* buf, size_t bytes, void* stream);
 b200m_ebu* b200m_r128_ebu (b200m_r128* h);     /* the underlying banks (histograms, state, coefficients) */
 b200m_tpk* b200m_r128_tpk (b200m_r128* h);
 

@@ -84,6 +84,15 @@ _PROTOS = {
     "b200m_r128_results": (C.c_int, [_v, _v, _v, _v]),
     "b200m_r128_set_dbtp": (C.c_int, [_v, C.c_int]),
     "b200m_r128_histogram": (C.c_int, [_v, C.c_uint32, _v, _v, _v]),
+    "b200m_r128_snapshot_size": (C.c_size_t, [_v]),
+    "b200m_r128_snapshot": (C.c_int, [_v, _v, C.c_size_t, _v]),
+    "b200m_r128_restore": (C.c_int, [_v, _v, C.c_size_t, _v]),
+    "b200m_ebu_snapshot_size": (C.c_size_t, [_v]),
+    "b200m_ebu_snapshot": (C.c_int, [_v, _v, C.c_size_t, _v]),
+    "b200m_ebu_restore": (C.c_int, [_v, _v, C.c_size_t, _v]),
+    "b200m_tpk_snapshot_size": (C.c_size_t, [_v]),
+    "b200m_tpk_snapshot": (C.c_int, [_v, _v, C.c_size_t, _v]),
+    "b200m_tpk_restore": (C.c_int, [_v, _v, C.c_size_t, _v]),
     "b200m_r128_ebu": (_v, [_v]),
     "b200m_r128_tpk": (_v, [_v]),
     # Stcorr
@@ -706,6 +715,17 @@ class EBUr128(_Bank):
         tp = np.empty(self.n_inst, np.float32) if tp is None else tp
         _ck(lib().b200m_r128_results(self.h, _np_ptr(out), _np_ptr(tp), _stream_ptr(stream)))
         return out, tp
+
+    def snapshot(self, stream=None):
+        """the whole bank state as bytes (checkpoint)"""
+        n = lib().b200m_r128_snapshot_size(self.h)
+        buf = np.empty(n, np.uint8)
+        _ck(lib().b200m_r128_snapshot(self.h, _np_ptr(buf), n, _stream_ptr(stream)))
+        return buf
+
+    def restore(self, blob, stream=None):
+        blob = np.ascontiguousarray(blob, np.uint8)
+        _ck(lib().b200m_r128_restore(self.h, _np_ptr(blob), blob.size, _stream_ptr(stream)))
 
     def set_dbtp(self, enable):
         """self->dbtp_enable (src/ebulv2.cc:316-317): takes effect with the next run"""

@@ -694,6 +694,69 @@ int b200m_ebu_histogram (b200m_ebu* h, uint32_t inst, int32_t* hist_M, int32_t* 
     return 0;
 }
 
+// ---- snapshot / restore (the reference never saves DSP state; a batch engine integrating for hours should) ----
+// blob = header, the host-side clocks and phase book-keeping, then every device state array in a fixed order
+namespace {
+struct EbuSnapHead { uint32_t magic, n_inst, nchan; float fsamp; int32_t frcnt, wrind, G, cnt10[10]; };
+constexpr uint32_t EBU_SNAP_MAGIC = 0x42453031u;              // "BE01"
+struct EbuSeg { void* p; size_t bytes; };
+int ebu_segments (b200m_ebu* h, EbuSeg* seg)
+{
+    const size_t n = h->n_inst, nch = (size_t)h->n_inst * h->nchan;
+    int k = 0;
+    seg[k++] = {h->d_z, 4 * nch * sizeof (float)}; seg[k++] = {h->d_frpwr, n * sizeof (float)}; seg[k++] = {h->d_ring, 64 * n * sizeof (float)};
+    seg[k++] = {h->d_ctl, n * sizeof (EbuCtl)}; seg[k++] = {h->d_res, n * sizeof (b200m_ebu_result)};
+    seg[k++] = {h->d_histM, (size_t)HIST_PITCH * n * sizeof (int)}; seg[k++] = {h->d_histS, (size_t)HIST_PITCH * n * sizeof (int)};
+    seg[k++] = {h->d_cnt, 4 * n * sizeof (int)};
+    return k;
+}
+}
+
+size_t b200m_ebu_snapshot_size (b200m_ebu* h)
+{
+    if (!h) return 0;
+    EbuSeg seg[8]; const int k = ebu_segments (h, seg);
+    size_t b = sizeof (EbuSnapHead) + 3 * (size_t)h->n_inst;
+    b = (b + 15) & ~size_t (15);
+    for (int i = 0; i < k; ++i) b += (seg[i].bytes + 15) & ~size_t (15);
+    return b;
+}
+
+int b200m_ebu_snapshot (b200m_ebu* h, void* buf, size_t bytes, void* stream)
+{
+    if (!h || !buf || bytes < b200m_ebu_snapshot_size (h)) return set_err (B200M_E_INVAL, "bad argument / buffer too small");
+    DeviceGuard g (h->device);
+    cudaStream_t st = ebu_stream (h, stream);
+    uint8_t* o = (uint8_t*)buf;
+    EbuSnapHead hd = {EBU_SNAP_MAGIC, h->n_inst, h->nchan, h->fsamp, h->frcnt, h->wrind, h->G, {0}};
+    memcpy (hd.cnt10, h->cnt10, sizeof (hd.cnt10));
+    memcpy (o, &hd, sizeof (hd)); o += sizeof (hd);
+    memcpy (o, h->integ.data (), h->n_inst); o += h->n_inst; memcpy (o, h->base.data (), h->n_inst); o += h->n_inst; memcpy (o, h->frozen.data (), h->n_inst); o += h->n_inst;
+    o = (uint8_t*)buf + ((sizeof (hd) + 3 * (size_t)h->n_inst + 15) & ~size_t (15));
+    EbuSeg seg[8]; const int k = ebu_segments (h, seg);
+    for (int i = 0; i < k; ++i) { B200M_CUDA (cudaMemcpyAsync (o, seg[i].p, seg[i].bytes, cudaMemcpyDeviceToHost, st)); o += (seg[i].bytes + 15) & ~size_t (15); }
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_ebu_restore (b200m_ebu* h, const void* buf, size_t bytes, void* stream)
+{
+    if (!h || !buf || bytes < b200m_ebu_snapshot_size (h)) return set_err (B200M_E_INVAL, "bad argument / buffer too small");
+    EbuSnapHead hd; memcpy (&hd, buf, sizeof (hd));
+    if (hd.magic != EBU_SNAP_MAGIC || hd.n_inst != h->n_inst || hd.nchan != h->nchan || hd.fsamp != h->fsamp)
+        return set_err (B200M_E_INVAL, "snapshot does not match this bank (instances / channels / sample rate)");
+    DeviceGuard g (h->device);
+    cudaStream_t st = ebu_stream (h, stream);
+    const uint8_t* o = (const uint8_t*)buf + sizeof (hd);
+    h->frcnt = hd.frcnt; h->wrind = hd.wrind; h->G = hd.G; memcpy (h->cnt10, hd.cnt10, sizeof (hd.cnt10));
+    memcpy (h->integ.data (), o, h->n_inst); o += h->n_inst; memcpy (h->base.data (), o, h->n_inst); o += h->n_inst; memcpy (h->frozen.data (), o, h->n_inst);
+    o = (const uint8_t*)buf + ((sizeof (hd) + 3 * (size_t)h->n_inst + 15) & ~size_t (15));
+    EbuSeg seg[8]; const int k = ebu_segments (h, seg);
+    for (int i = 0; i < k; ++i) { B200M_CUDA (cudaMemcpyAsync (seg[i].p, o, seg[i].bytes, cudaMemcpyHostToDevice, st)); o += (seg[i].bytes + 15) & ~size_t (15); }
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
 int b200m_ebu_coeffs (const b200m_ebu* h, float o[7])
 {
     if (!h || !o) return set_err (B200M_E_INVAL, "NULL argument");

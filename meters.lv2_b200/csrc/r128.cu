@@ -201,6 +201,54 @@ int b200m_r128_histogram (b200m_r128* h, uint32_t inst, int32_t* hist_M, int32_t
     return b200m_ebu_histogram (h->ebu, inst, hist_M, hist_S, h->last_host ? (void*)h->own : stream);
 }
 
+// snapshot = [u64 ebu bytes][u64 tpk bytes][ebu blob][tpk blob][tp_max floats][dbtp flag]
+size_t b200m_r128_snapshot_size (b200m_r128* h)
+{
+    if (!h) return 0;
+    return 16 + b200m_ebu_snapshot_size (h->ebu) + b200m_tpk_snapshot_size (h->tpk) + (((size_t)h->n_inst * 4 + 15) & ~size_t (15)) + 16;
+}
+
+int b200m_r128_snapshot (b200m_r128* h, void* buf, size_t bytes, void* stream)
+{
+    if (!h || !buf || bytes < b200m_r128_snapshot_size (h)) return set_err (B200M_E_INVAL, "bad argument / buffer too small");
+    DeviceGuard g (h->device);
+    void* st = h->last_host ? (void*)h->own : stream;
+    const uint64_t eb = b200m_ebu_snapshot_size (h->ebu), tb = b200m_tpk_snapshot_size (h->tpk);
+    uint8_t* o = (uint8_t*)buf;
+    memcpy (o, &eb, 8); memcpy (o + 8, &tb, 8); o += 16;
+    if (int rc = b200m_ebu_snapshot (h->ebu, o, eb, st)) return rc;
+    o += eb;
+    if (int rc = b200m_tpk_snapshot (h->tpk, o, tb, st)) return rc;
+    o += tb;
+    B200M_CUDA (cudaMemcpyAsync (o, h->d_tpmax, (size_t)h->n_inst * 4, cudaMemcpyDeviceToHost, (cudaStream_t)st));
+    B200M_CUDA (cudaStreamSynchronize ((cudaStream_t)st));
+    o += ((size_t)h->n_inst * 4 + 15) & ~size_t (15);
+    const int32_t fl[4] = {h->dbtp, 0, 0, 0};
+    memcpy (o, fl, 16);
+    return 0;
+}
+
+int b200m_r128_restore (b200m_r128* h, const void* buf, size_t bytes, void* stream)
+{
+    if (!h || !buf || bytes < b200m_r128_snapshot_size (h)) return set_err (B200M_E_INVAL, "bad argument / buffer too small");
+    DeviceGuard g (h->device);
+    void* st = h->last_host ? (void*)h->own : stream;
+    uint64_t eb, tb;
+    const uint8_t* o = (const uint8_t*)buf;
+    memcpy (&eb, o, 8); memcpy (&tb, o + 8, 8); o += 16;
+    if (eb != b200m_ebu_snapshot_size (h->ebu) || tb != b200m_tpk_snapshot_size (h->tpk)) return set_err (B200M_E_INVAL, "snapshot does not match this bank");
+    if (int rc = b200m_ebu_restore (h->ebu, o, eb, st)) return rc;
+    o += eb;
+    if (int rc = b200m_tpk_restore (h->tpk, o, tb, st)) return rc;
+    o += tb;
+    B200M_CUDA (cudaMemcpyAsync (h->d_tpmax, o, (size_t)h->n_inst * 4, cudaMemcpyHostToDevice, (cudaStream_t)st));
+    B200M_CUDA (cudaStreamSynchronize ((cudaStream_t)st));
+    o += ((size_t)h->n_inst * 4 + 15) & ~size_t (15);
+    int32_t fl[4]; memcpy (fl, o, 16);
+    h->dbtp = fl[0] ? 1 : 0;
+    return 0;
+}
+
 b200m_ebu* b200m_r128_ebu (b200m_r128* h) { return h ? h->ebu : nullptr; }
 b200m_tpk* b200m_r128_tpk (b200m_r128* h) { return h ? h->tpk : nullptr; }
 

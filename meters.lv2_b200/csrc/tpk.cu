@@ -802,6 +802,59 @@ int b200m_tpk_reset_kmeter (b200m_tpk* h, void* stream)
     return 0;
 }
 
+// ---- snapshot / restore: header + every per-channel state array in TpkState order
+namespace {
+struct TpkSnapHead { uint32_t magic, n_chan, flags; float fsamp; };
+constexpr uint32_t TPK_SNAP_MAGIC = 0x50543031u;              // "TP01"
+int tpk_segments (b200m_tpk* h, void** p, size_t* b)
+{
+    const size_t n = h->n_chan;
+    void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms, h->st.km_peak,
+                  h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res};
+    const size_t bs[] = {n * 48 * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * 4, n * sizeof (b200m_tpk_result)};
+    for (int i = 0; i < 15; ++i) { p[i] = ps[i]; b[i] = bs[i]; }
+    return 15;
+}
+}
+
+size_t b200m_tpk_snapshot_size (b200m_tpk* h)
+{
+    if (!h) return 0;
+    void* p[15]; size_t b[15]; const int k = tpk_segments (h, p, b);
+    size_t t = 16;
+    for (int i = 0; i < k; ++i) t += (b[i] + 15) & ~size_t (15);
+    return t;
+}
+
+int b200m_tpk_snapshot (b200m_tpk* h, void* buf, size_t bytes, void* stream)
+{
+    if (!h || !buf || bytes < b200m_tpk_snapshot_size (h)) return set_err (B200M_E_INVAL, "bad argument / buffer too small");
+    DeviceGuard g (h->device);
+    cudaStream_t st = tpk_stream (h, stream);
+    const TpkSnapHead hd = {TPK_SNAP_MAGIC, h->n_chan, h->flags, h->fsamp};
+    memcpy (buf, &hd, sizeof (hd));
+    uint8_t* o = (uint8_t*)buf + 16;
+    void* p[15]; size_t b[15]; const int k = tpk_segments (h, p, b);
+    for (int i = 0; i < k; ++i) { B200M_CUDA (cudaMemcpyAsync (o, p[i], b[i], cudaMemcpyDeviceToHost, st)); o += (b[i] + 15) & ~size_t (15); }
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
+int b200m_tpk_restore (b200m_tpk* h, const void* buf, size_t bytes, void* stream)
+{
+    if (!h || !buf || bytes < b200m_tpk_snapshot_size (h)) return set_err (B200M_E_INVAL, "bad argument / buffer too small");
+    TpkSnapHead hd; memcpy (&hd, buf, sizeof (hd));
+    if (hd.magic != TPK_SNAP_MAGIC || hd.n_chan != h->n_chan || hd.flags != h->flags || hd.fsamp != h->fsamp)
+        return set_err (B200M_E_INVAL, "snapshot does not match this bank (channels / meters / sample rate)");
+    DeviceGuard g (h->device);
+    cudaStream_t st = tpk_stream (h, stream);
+    const uint8_t* o = (const uint8_t*)buf + 16;
+    void* p[15]; size_t b[15]; const int k = tpk_segments (h, p, b);
+    for (int i = 0; i < k; ++i) { B200M_CUDA (cudaMemcpyAsync (p[i], o, b[i], cudaMemcpyHostToDevice, st)); o += (b[i] + 15) & ~size_t (15); }
+    B200M_CUDA (cudaStreamSynchronize (st));
+    return 0;
+}
+
 int b200m_tpk_coeffs (const b200m_tpk* h, float w[4], float ctab[120], float km[2])
 {
     if (!h) return set_err (B200M_E_INVAL, "NULL handle");

@@ -226,3 +226,33 @@ def test_r128_bank_vs_reference_ebur128_plugin():
             for i, name in enumerate(RES):
                 assert np.array_equal(res[name].view(np.uint32), ref[:, i].view(np.uint32)), (b, name)
             assert np.array_equal(tp.view(np.uint32), ref[:, 9].view(np.uint32)), (b, tp, ref[:, 9])
+
+
+def test_r128_snapshot_restore_continues_bit_identically():
+    """checkpoint / resume: a fresh bank restored from a snapshot continues exactly like the original (results, tp_max,
+    histograms), including the host-tracked fragment clock and gating phases (blocks of 1000 frames: the 2400-frame
+    fragment boundary falls at a different offset in every block)."""
+    import torch
+    import meters_lv2_b200 as B
+    n, blk, nb1, nb2 = 9, 1000, 37, 55
+    x = S.white(2 * n, blk * (nb1 + nb2), seed=77)
+    xd = torch.from_numpy(x).cuda()
+    a = B.EBUr128(n, 48000.0, dbtp_enable=True); a.control(B.EBUr128.START)
+    for b in range(nb1):
+        if b == 20:
+            a.control(B.EBUr128.PAUSE, 3)                    # per-instance control state must travel too
+        a.run(xd[:, b * blk:(b + 1) * blk])
+    blob = a.snapshot()
+    c = B.EBUr128(n, 48000.0, dbtp_enable=False)             # dbtp flag comes from the snapshot
+    c.restore(blob)
+    for b in range(nb1, nb1 + nb2):
+        if b == nb1 + 10:
+            a.control(B.EBUr128.START, 3); c.control(B.EBUr128.START, 3)
+        a.run(xd[:, b * blk:(b + 1) * blk]); c.run(xd[:, b * blk:(b + 1) * blk])
+    ra, ta = a.results(); rc, tc = c.results()
+    assert ra.tobytes() == rc.tobytes() and ta.tobytes() == tc.tobytes()
+    for inst in (0, 3, n - 1):
+        ma, sa = a.histogram(inst); mc, sc = c.histogram(inst)
+        assert np.array_equal(ma, mc) and np.array_equal(sa, sc) and ma.sum() > 0
+    with pytest.raises(Exception):
+        B.EBUr128(n + 1, 48000.0).restore(blob)             # shape mismatch is refused
