@@ -32,7 +32,7 @@ struct b200m_r128 {
     // own: EBU kernels + joins (host path);  side: true-peak kernels (run concurrently with the latency-bound EBU
     // kernel);  copy: host->device slices, so that the copy of slice s+1 overlaps the kernels of slice s
     cudaStream_t own = nullptr, side = nullptr, copy = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_tp = nullptr, ev_done = nullptr, ev_ready[R128_SLICES] = {nullptr};
+    cudaEvent_t ev_tp = nullptr, ev_done = nullptr, ev_ready[R128_SLICES] = {nullptr};
     HostStage stage; bool last_host = false; int concurrent = 1, slices = R128_SLICES;
 };
 
@@ -97,7 +97,7 @@ int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsam
         DeviceGuard g (device);
         cudaError_t e = cudaMalloc ((void**)&h->d_tpmax, n_inst * sizeof (float));
         for (cudaStream_t* sp : {&h->own, &h->side, &h->copy}) if (e == cudaSuccess) e = cudaStreamCreateWithFlags (sp, cudaStreamNonBlocking);
-        for (cudaEvent_t* ep : {&h->ev_in, &h->ev_tp, &h->ev_done}) if (e == cudaSuccess) e = cudaEventCreateWithFlags (ep, cudaEventDisableTiming);
+        for (cudaEvent_t* ep : {&h->ev_tp, &h->ev_done}) if (e == cudaSuccess) e = cudaEventCreateWithFlags (ep, cudaEventDisableTiming);
         for (int s = 0; s < R128_SLICES; ++s) if (e == cudaSuccess) e = cudaEventCreateWithFlags (&h->ev_ready[s], cudaEventDisableTiming);
         if (e == cudaSuccess) {
             r128_fill_kernel<<<(n_inst + 255) / 256, 256>>> ((int)n_inst, h->d_tpmax, -INFINITY);
@@ -119,7 +119,7 @@ int b200m_r128_destroy (b200m_r128* h)
     cudaDeviceSynchronize ();
     cudaFree (h->d_tpmax); h->stage.release ();
     for (cudaStream_t sp : {h->own, h->side, h->copy}) if (sp) cudaStreamDestroy (sp);
-    for (cudaEvent_t ep : {h->ev_in, h->ev_tp, h->ev_done}) if (ep) cudaEventDestroy (ep);
+    for (cudaEvent_t ep : {h->ev_tp, h->ev_done}) if (ep) cudaEventDestroy (ep);
     for (int s = 0; s < R128_SLICES; ++s) if (h->ev_ready[s]) cudaEventDestroy (h->ev_ready[s]);
     delete h;
     return 0;

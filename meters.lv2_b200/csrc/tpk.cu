@@ -383,6 +383,24 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
             const int r = tid / LPR, ql = tid % LPR;
             float M = 0.0f;
             if (elide0) M = row_absmax<LPR, 12 + GPC> (reinterpret_cast<const float4*> (&xs[buf][r][0]), lane);
+            // digital silence on every row this warp works on (chunk + its 48-sample prefix all +-0): each of the 4 phases is
+            // (1e-20f + 0) - 1e-20f = +0, so the FIR is skipped altogether (idle channels of a large bank cost no arithmetic)
+            const bool silent_rows = elide0 && __all_sync (0xffffffffu, M == 0.0f);
+            if (silent_rows) {
+                // outputs are all +0: nothing to add to a running max; process() still needs its |out| tile, the debug tap its zeros
+                for (int q = ql; q < GPC && 4 * q < len; q += LPR) {
+                    if (BAL) {
+                        float4* d = reinterpret_cast<float4*> (&ob[BAL ? r : 0][0]);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d[BAL ? i * GPC + q : 0] = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                    if (dbg && (c0 + r) < n_chan) {
+                        float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d[i] = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+                    }
+                }
+            } else
 #pragma unroll 1
             for (int q = ql; q < GPC; q += LPR) {
                 const bool act = 4 * q < len;
