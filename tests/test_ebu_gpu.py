@@ -73,6 +73,19 @@ def test_white_noise_bit_exact(n_inst, blocks):
     _assert_equal(g, o, gr, orr, n_inst)
 
 
+def test_tma_staging_is_bit_identical(monkeypatch):
+    """the opt-in TMA staging of the K-weighting kernel (B200M_EBU_TMA=1: 128B-swizzled boxes, mbarrier) produces the same
+    bits as the default cp.async staging, incl. ragged blocks (partial tiles, fragment cuts inside a tile) and a mono bank"""
+    monkeypatch.setenv("B200M_EBU_TMA", "1")
+    blocks = [1024] * 40 + [64] * 30 + [480] * 20 + [8192] * 3 + [4, 8, 1020, 2404, 4800]
+    x = S.white(2 * 37, sum(blocks), seed=31)
+    g, o, gr, orr = _run_both(x, blocks)
+    _assert_equal(g, o, gr, orr, 37)
+    x1 = S.white(40, 1024 * 30, seed=32)
+    g, o, gr, orr = _run_both(x1, [1024] * 30, nchan=1)
+    _assert_equal(g, o, gr, orr, 40, nchan=1)
+
+
 def test_mono_bank():
     x = S.white(33, 1024 * 120)
     g, o, gr, orr = _run_both(x, [1024] * 120, nchan=1)
