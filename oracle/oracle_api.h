@@ -117,6 +117,15 @@ void  orc_sdh_integrate (void* h, int on);
 void  orc_sdh_process (void* h, const float* in, size_t stride, int nfram, int nthreads);
 void  orc_sdh_read    (void* h, int inst, int32_t* hist361, int32_t* maxpeak2, double* avg_tmp_var3, int64_t* itime);
 
+/* DR-14 / TPnRMS: dr14_run (src/dr14.c:354-482) for n instances of nch channels; rows inst*nch + c.
+ * read: 12 floats per instance = the output ports v_rms[2] v_peak[2] m_peak[2] m_rms[2] dr[2] dr_total block_count.
+ * kind "reference" drives the reference's own dr14 / TPnRMS plugins through LV2 run() (follow-transport off, no atoms). */
+void* orc_dr14_create  (int n, int nch, double rate, int dr_mode);
+void  orc_dr14_destroy (void* h);
+void  orc_dr14_process (void* h, const float* in, size_t stride, int nfram, int nthreads);
+void  orc_dr14_reset   (void* h);
+void  orc_dr14_read    (void* h, float* out12);
+
 /* ---- phasewheel / stereoscope FFT analysis (gui/fft.c:208-340, gui/phasewheel.c:1307-1342) ----
  * kind "reference" returns NULL from orc_pw_create: FFTW3 is not vendored and absent here. */
 void* orc_pw_create   (int n_inst, int fft_bins, double rate);

@@ -620,6 +620,97 @@ struct Pw {
     }
 };
 
+// =====================================================================================
+// DR-14 / TPnRMS — src/dr14.c
+// =====================================================================================
+struct Dr14 {
+    static constexpr int BINS = 8000;            // DR_HISTBINS :45
+    int nch; bool dr_mode; double rate; uint64_t n_sample_cnt, sample_count = 0, num_fragments = 0;
+    TruePeak tp[2]; Kmeter km[2];
+    float m_dbtp[2], m_peak[2], m_rms[2], rms_sum[2], peak_cur[2], peak_hist[2][2];
+    std::vector<uint32_t> hist[2];
+    float port[12];                              // v_rms[2] v_peak[2] m_peak[2] m_rms[2] dr[2] dr_total block_count
+
+    static float coeff_to_db (float c) { if (c < .0001) return -80; return 20 * log10f (c); }       // :236-239
+    static float db_to_coeff (float db) { if (db <= -80) return 0; return powf (10, 0.05 * db); }   // :241-244
+
+    void init (int n_channels, double r, bool dr) {                                                  // dr14_instantiate :104-166
+        nch = n_channels; dr_mode = dr; rate = r; n_sample_cnt = rintf (rate * 3.0);
+        Kmeter::init (r);
+        for (int c = 0; c < nch; ++c) { tp[c].init (r); km[c] = Kmeter (); m_rms[c] = m_peak[c] = -81; m_dbtp[c] = 0; rms_sum[c] = peak_cur[c] = 0;
+                                        peak_hist[c][0] = peak_hist[c][1] = 0; if (dr) hist[c].assign (BINS, 0); }
+        memset (port, 0, sizeof (port));
+    }
+    void reset_peaks () {                                                                            // :241-258
+        for (int c = 0; c < nch; ++c) {
+            m_peak[c] = -81; m_rms[c] = -81; m_dbtp[c] = 0; rms_sum[c] = 0; peak_cur[c] = 0; peak_hist[c][0] = peak_hist[c][1] = 0;
+            km[c].reset ();
+            if (dr_mode) std::fill (hist[c].begin (), hist[c].end (), 0u);
+        }
+        sample_count = 0; num_fragments = 0;
+    }
+    void calc_rms_score () {                                                                         // dr14_calc_rms_score :285-352
+        bool silent = true;
+        for (int c = 0; c < nch; ++c) if (rms_sum[c] > 1e-9 * (float)n_sample_cnt) silent = false;
+        if (silent) { for (int c = 0; c < nch; ++c) rms_sum[c] = 0; return; }
+        num_fragments++;
+        const float mc = floorf (num_fragments / 5.0);
+        const uint32_t m_cut = 1 > mc ? 1 : mc;
+        for (int c = 0; c < nch; ++c) {
+            const float rms = sqrt (2.f * rms_sum[c] / (float)n_sample_cnt);
+            rms_sum[c] = 0;
+            int bin = rintf (100.f * (80.f + coeff_to_db (rms))) - 1;
+            if (bin >= BINS) bin = BINS - 1;
+            if (bin > 0) hist[c][bin]++;
+            uint32_t n_cut = 0; float rms_score = 0;
+            if (num_fragments > 2)
+                for (int32_t b = BINS - 1; b > 0 && n_cut < m_cut; --b) {
+                    const uint32_t bc = hist[c][b];
+                    if (bc == 0) continue;
+                    const float cd = db_to_coeff ((b - BINS + 1) / 100.0);
+                    rms_score += cd * cd * (float)bc;
+                    n_cut += bc;
+                }
+            m_rms[c] = n_cut > 0 ? coeff_to_db (sqrtf (rms_score / n_cut)) : -81;
+            if (peak_cur[c] >= peak_hist[c][0]) { peak_hist[c][1] = peak_hist[c][0]; peak_hist[c][0] = peak_cur[c]; }
+            else if (peak_cur[c] > peak_hist[c][1]) peak_hist[c][1] = peak_cur[c];
+            peak_cur[c] = 0;
+            m_peak[c] = num_fragments > 2 ? coeff_to_db (peak_hist[c][1]) : -81;
+        }
+    }
+    void run (const float* const* in, int n) {                                                        // dr14_run :391-462 (no atoms, button up)
+        for (int c = 0; c < nch; ++c) { km[c].process (in[c], n); tp[c].process (in[c], n); }
+        if (dr_mode) {
+            uint64_t scnt = sample_count;
+            for (int s = 0; s < n; ++s) {
+                for (int c = 0; c < nch; ++c) { const float v = in[c][s]; rms_sum[c] += v * v; peak_cur[c] = peak_cur[c] > v ? peak_cur[c] : v; }
+                if (++scnt > n_sample_cnt) { calc_rms_score (); scnt = 0; }
+            }
+            sample_count = scnt;
+        }
+        float dr_total = 0; int dr_valid = 0;
+        for (int c = 0; c < nch; ++c) {
+            const float pv = tp[c].m, pp = tp[c].p; tp[c].res = true;                               // read (pv, pp)
+            const float rv = km[c].rms, rp = km[c].peak; km[c].flag = true;                         // read (rv, rp)
+            m_dbtp[c] = m_dbtp[c] > pp ? m_dbtp[c] : pp;
+            port[0 + c] = coeff_to_db (rv); port[2 + c] = coeff_to_db (pv); port[4 + c] = coeff_to_db (m_dbtp[c]);
+            if (dr_mode) {
+                const float rdb = m_rms[c], pdb = m_peak[c];
+                const float dr = (0 < pdb ? 0 : pdb) - rdb;
+                if (rdb > -80 && pdb > -80) { dr_total += dr; dr_valid++; }
+                const float lo = 20 < dr ? 20 : dr;
+                port[8 + c] = (rdb > -80 && pdb > -80) ? (1 > lo ? 1 : lo) : 21;
+                port[6 + c] = rdb;
+            } else port[6 + c] = coeff_to_db (rp);
+        }
+        if (nch > 1 && dr_mode) {
+            if (dr_valid > 0) { const float a = dr_total / (float)dr_valid; const float lo = 20 < a ? 20 : a; port[10] = 1 > lo ? 1 : lo; }
+            else port[10] = 21;
+        }
+        port[11] = 3.0 * num_fragments;
+    }
+};
+
 template <class T> struct Bank { int n, nchan; std::vector<T> v; };
 
 }  // namespace
@@ -783,6 +874,15 @@ void  orc_sdh_read (void* h, int inst, int32_t* hist, int32_t* mp, double* av, i
     const Sdh& m = ((Bank<Sdh>*)h)->v[inst];
     memcpy (hist, m.hist, sizeof (m.hist)); mp[0] = m.mx; mp[1] = m.peak; av[0] = m.avg; av[1] = m.tmp; av[2] = m.var; *it = (int64_t)m.itime;
 }
+
+void* orc_dr14_create (int n, int nch, double rate, int dr_mode) { auto* b = new Bank<Dr14>; b->n = n; b->nchan = nch; b->v.resize (n); for (auto& d : b->v) d.init (nch, rate, dr_mode != 0); return b; }
+void orc_dr14_destroy (void* h) { delete (Bank<Dr14>*)h; }
+void orc_dr14_process (void* h, const float* in, size_t stride, int nfram, int nthreads) {
+    auto* b = (Bank<Dr14>*)h;
+    par_for (b->n, nthreads, [=] (int a, int e) { for (int i = a; i < e; ++i) { const float* ip[2] = {in + (size_t)(i * b->nchan) * stride, in + (size_t)(i * b->nchan + b->nchan - 1) * stride}; b->v[i].run (ip, nfram); } });
+}
+void orc_dr14_reset (void* h) { for (auto& d : ((Bank<Dr14>*)h)->v) d.reset_peaks (); }
+void orc_dr14_read (void* h, float* out) { auto* b = (Bank<Dr14>*)h; for (int i = 0; i < b->n; ++i) memcpy (out + 12 * i, b->v[i].port, sizeof (b->v[i].port)); }
 
 void* orc_pw_create (int n, int fft_bins, double rate) { auto* b = new Bank<Pw>; b->n = n; b->v.resize (n); for (auto& p : b->v) p.init (fft_bins, rate); return b; }
 void orc_pw_destroy (void* h) { delete (Bank<Pw>*)h; }

@@ -387,6 +387,45 @@ void  orc_sdh_integrate (void* h, int on) { PlugB* b = (PlugB*)h; for (auto p : 
 void  orc_sdh_process (void* h, const float* in, size_t stride, int nfram, int nthreads) { plug_process (h, in, stride, nfram, nthreads); }
 void  orc_sdh_read (void* h, int inst, int32_t* hist, int32_t* mp, double* av, int64_t* it) { refsdh_snapshot (((PlugB*)h)->p[inst], hist, mp, av, it); }
 
+/* ------------------------------------------------------------------ DR-14 / TPnRMS through the reference plugins' run() */
+struct Dr14B { int n, nch, dr; std::vector<void*> p; std::vector<float> ports; float follow, button; };   /* 19 port floats per instance */
+void* orc_dr14_create (int n, int nch, double rate, int dr_mode)
+{
+    Dr14B* b = new Dr14B; b->n = n; b->nch = nch; b->dr = dr_mode; b->follow = 0; b->button = 0; b->ports.assign ((size_t)n * 19, 0.f);
+    const char* uri = dr_mode ? (nch == 2 ? "dr14stereo" : "dr14mono") : (nch == 2 ? "TPnRMSstereo" : "TPnRMSmono");
+    for (int i = 0; i < n; ++i) {
+        void* p = refplug_new (uri, rate);             /* port 0 = the harness's empty atom sequence; port 1 is re-connected below */
+        if (!p) { delete b; return 0; }
+        b->p.push_back (p);
+        refplug_connect (p, 1, &b->follow); refplug_connect (p, 2, &b->button);                 /* DR_HOST_TRANSPORT, DR_RESET */
+        for (int k : {3, 6, 7, 8, 9, 10, 13, 14, 15, 16, 17, 18}) refplug_connect (p, k, &b->ports[(size_t)i * 19 + k]);
+    }
+    return b;
+}
+void  orc_dr14_destroy (void* h) { Dr14B* b = (Dr14B*)h; for (auto p : b->p) refplug_free (p); delete b; }
+void  orc_dr14_process (void* h, const float* in, size_t stride, int nfram, int nthreads)
+{
+    Dr14B* b = (Dr14B*)h;                              /* DRPortIndex (src/dr14.c:27-43): 4 in0 5 out0 11 in1 12 out1 */
+    par_for (b->n, nthreads, [=] (int a, int e) {
+        for (int i = a; i < e; ++i) {
+            float* l = const_cast<float*> (in + (size_t)(i * b->nch) * stride); float* r = const_cast<float*> (in + (size_t)(i * b->nch + b->nch - 1) * stride);
+            refplug_connect (b->p[i], 4, l); refplug_connect (b->p[i], 5, l); refplug_connect (b->p[i], 11, r); refplug_connect (b->p[i], 12, r);
+            refplug_run (b->p[i], (uint32_t)nfram);
+        }
+    });
+    b->button = 0;
+}
+/* the plugin samples its reset button at the top of run(): latch it for the next process call (state in between is unobservable) */
+void  orc_dr14_reset (void* h) { ((Dr14B*)h)->button = 1; }
+void  orc_dr14_read (void* h, float* out)
+{
+    Dr14B* b = (Dr14B*)h;
+    for (int i = 0; i < b->n; ++i) {
+        const float* p = &b->ports[(size_t)i * 19]; float* o = out + 12 * i;
+        o[0] = p[8]; o[1] = p[15]; o[2] = p[6]; o[3] = p[13]; o[4] = p[7]; o[5] = p[14]; o[6] = p[9]; o[7] = p[16]; o[8] = p[10]; o[9] = p[17]; o[10] = p[18]; o[11] = p[3];
+    }
+}
+
 /* ------------------------------------------------------------------ phasewheel: FFTW3 absent */
 void* orc_pw_create (int, int, double) { return 0; }
 void  orc_pw_destroy (void*) {}

@@ -85,6 +85,11 @@ def _proto(lib):
         "orc_spec_read": (None, [_v, _v]),
         "orc_spec_state": (None, [_v, C.c_int, _v, _v, _v]),
         "orc_spec_coeffs": (None, [_v, _v]),
+        "orc_dr14_create": (_v, [C.c_int, C.c_int, C.c_double, C.c_int]),
+        "orc_dr14_destroy": (None, [_v]),
+        "orc_dr14_process": (None, [_v, _v, C.c_size_t, C.c_int, C.c_int]),
+        "orc_dr14_reset": (None, [_v]),
+        "orc_dr14_read": (None, [_v, _v]),
         "orc_pw_create": (_v, [C.c_int, C.c_int, C.c_double]),
         "orc_pw_destroy": (None, [_v]),
         "orc_pw_set_mode": (None, [_v, C.c_int]),
@@ -411,6 +416,32 @@ class Spectr30:
         W = np.empty((30, 6, 6), np.float64)
         self.L.orc_spec_coeffs(self.h, ptr(W))
         return W
+
+
+class Dr14:
+    """dr14_run for n instances; read() -> [n, 12] = v_rms[2] v_peak[2] m_peak[2] m_rms[2] dr[2] dr_total block_count"""
+
+    def __init__(self, n_inst, nch=2, rate=48000.0, dr_mode=True, kind="best"):
+        self.L = load(kind); self.n, self.nch = n_inst, nch
+        self.h = self.L.orc_dr14_create(n_inst, nch, rate, int(dr_mode))
+        assert self.h
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.orc_dr14_destroy(self.h); self.h = None
+
+    def process(self, x, nthreads=1):
+        p, s = planar(x)
+        assert x.shape[0] == self.n * self.nch
+        self.L.orc_dr14_process(self.h, p, s, x.shape[1], nthreads)
+
+    def reset(self):
+        self.L.orc_dr14_reset(self.h)
+
+    def read(self):
+        out = np.empty((self.n, 12), np.float32)
+        self.L.orc_dr14_read(self.h, ptr(out))
+        return out
 
 
 class Phasewheel:

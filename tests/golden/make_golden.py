@@ -77,6 +77,26 @@ def compute(kind):
     for b in range(300):
         e2.process(np.ascontiguousarray(y[:, b * 1024:(b + 1) * 1024]))
     out["ebu_tone_results"] = e2.read()
+    # DR-14 (stereo, 36 s in 8192-frame blocks: 12 scored windows) and TPnRMS (mono)
+    t = np.arange(8192 * 212) / 48000.0
+    env = (0.2 + 0.8 * np.abs(np.sin(2 * np.pi * t / 6.1))).astype(np.float32)
+    xd = (S.white(4, 8192 * 212, seed=0xD214) * env * np.float32(2.5)).astype(np.float32)
+    xd[2:4, 8192 * 60:8192 * 110] = 0.0                                    # instance 1: 3 s windows of silence are not scored
+    dr = O.Dr14(2, 2, 48000.0, True, kind=kind)
+    reads = []
+    for b in range(212):
+        dr.process(np.ascontiguousarray(xd[:, b * 8192:(b + 1) * 8192]))
+        if b % 4 == 3:
+            reads.append(dr.read())
+        if b == 150:
+            dr.reset()
+    out["dr14_ports"] = np.stack(reads)
+    tn = O.Dr14(3, 1, 44100.0, False, kind=kind)
+    reads = []
+    for b in range(40):
+        tn.process(np.ascontiguousarray(x[:3, b * 1000:(b + 1) * 1000]))
+        reads.append(tn.read())
+    out["tpnrms_ports"] = np.stack(reads)
     # phasewheel (port only)
     pw = O.Phasewheel(2, 1024, kind="port")
     for b in range(4):

@@ -135,6 +135,30 @@ def test_bitmeter_and_sigdist_port_equals_reference_plugins():
         assert np.array_equal(ra[2].view(np.uint64), rb[2].view(np.uint64))
 
 
+@needs_both
+@pytest.mark.parametrize("nch,dr_mode,rate,block", [(2, True, 48000.0, 8192), (1, True, 44100.0, 1000), (2, False, 48000.0, 1024)])
+def test_dr14_port_equals_reference_plugins(nch, dr_mode, rate, block):
+    """restatement of dr14_run / dr14_calc_rms_score vs the reference's dr14 / TPnRMS plugins run through their own LV2 run()"""
+    n_inst = 3
+    nb = int(rate * 22 / block) if dr_mode else 30
+    t = np.arange(nb * block) / rate
+    env = (0.15 + 0.85 * np.abs(np.sin(2 * np.pi * t / 5.3))).astype(np.float32)
+    x = (S.white(n_inst * nch, nb * block, seed=123) * env * np.float32(2.0)).astype(np.float32)
+    x[0, 5 * block + 7] = np.nan                                # one poisoned window
+    x[nch:2 * nch] *= np.float32(1e-6)                           # instance 1 stays below the silence gate
+    a, b = O.Dr14(n_inst, nch, rate, dr_mode, kind="reference"), O.Dr14(n_inst, nch, rate, dr_mode, kind="port")
+    for k in range(nb):
+        blk = np.ascontiguousarray(x[:, k * block:(k + 1) * block])
+        a.process(blk); b.process(blk)
+        if k == nb // 2 + 3:
+            a.reset(); b.reset()
+        ra, rb = a.read(), b.read()
+        same = (u32(ra) == u32(rb)) | (np.isnan(ra) & np.isnan(rb))
+        assert same.all(), (k, ra[~same], rb[~same])
+    if dr_mode:
+        assert ra[0, 11] > 0 and ra[1, 11] == 0                  # scored windows on the loud instance only
+
+
 @needs_port
 def test_port_phasewheel_against_numpy_fft():
     """the FFT restatement (FFTW absent => parity unpinned) is at least a correct DFT of the windowed ring."""
