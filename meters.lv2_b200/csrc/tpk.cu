@@ -6,12 +6,15 @@
 //
 // B200 design (not the reference's ring-buffer walk): the resampler's steady state is a fixed
 // 48-tap x 4-phase FIR over the last 48 inputs, which is time-parallel, so a CTA
-// stages a [8 channels x 128 samples (+48 history)] tile in shared memory with cp.async and every
-// thread produces 4 consecutive input positions x 4 phases = 16 outputs from a 52-float register
-// window, coefficients read as constant-bank operands.  The non-linear ballistics
-// (truepeakdsp.cc:57-84) and the K-meter recurrences are serial in time, so one lane per channel
-// walks the |oversampled| tile in shared memory while the other CTAs resident on the SM run
-// their FIR phase.  The input is read from HBM exactly once for both meters.
+// stages [channels x chunk (+48 history)] tiles in shared memory with cp.async (8 x 256 for
+// process_max, 16 x 64 for process) and every thread, staying on one channel row, produces 4 consecutive
+// input positions x 4 phases = 16 outputs from a 52-float register window with the coefficients as
+// instruction immediates.  Phase 0 of the table is a unit tap: under a proven magnitude guard it is the
+// delayed input itself and is not evaluated (phase0_is_delay); rows of digital silence skip the FIR.
+// The non-linear ballistics (truepeakdsp.cc:57-84), the K-meter recurrences and the DR-14 window sums
+// are serial in time: lane roles on otherwise idle warps walk the |oversampled| / input tiles in shared
+// memory while the other CTAs resident on the SM run their FIR phase.  The input is read from HBM
+// exactly once for all meters.
 // All arithmetic keeps the reference's operation order without FMA contraction: outputs are
 // bit-identical to the reference build, not merely within tolerance.
 #include <math.h>
@@ -277,7 +280,7 @@ B200M_DEV void fir16 (const float (&w)[52], const float* xw, float (&o)[16], con
 // breaks the reference's rounding sequence.
 
 // Tile geometry: CH channels x TC input samples per chunk.  process_max (no serial true-peak lane) uses
-// <8,128>: smallest tiles, best balance over 148 SMs.  process() uses <16,64>: the ballistics warp then runs
+// <8,256>: 2048 CTAs for 16384 channels, 8 resident per SM.  process() uses <16,64>: the ballistics warp then runs
 // 16 channels x {z1 filter, z2 filter} = 32 busy lanes (the two one-pole attack filters are independent until
 // the per-sample m = max (m, z1 + z2), which costs one shuffle), so the serial part issues ~1/4 of the
 // instructions it would with one channel per lane.
