@@ -55,6 +55,28 @@ def test_argument_errors_are_codes_not_crashes():
     assert L.b200m_ebu_destroy(None) == 0
 
 
+def test_lv2_descriptor_table_and_instantiate_failures():
+    """the LV2 facade enumerates 37 of the reference's 38 URIs (src/meters.cc:745-792; goniometer excluded) and, like the
+    reference, answers instantiate() with NULL when it cannot run: no urid:map feature for the atom plugins, no GPU for any"""
+    import torch
+    import meters_lv2_b200 as B
+    from test_lv2_shim_gpu import Feature, _feats, descriptors
+    d, lib = descriptors(B.LIB_PATH)
+    uris = set(d)
+    assert len(uris) == 37 and "goniometer" not in uris
+    for u in ("EBUr128", "dr14stereo", "TPnRMSmono", "SigDistHist", "bitmeter", "phasewheel", "stereoscope", "surround8", "K20stereo", "BBCM6"):
+        assert u in uris, u
+    if O.available("reference"):
+        r, _ = descriptors(O.PATHS["reference"])
+        assert uris | {"goniometer"} == set(r)
+    none = (C.POINTER(Feature) * 1)(None)
+    for u in ("EBUr128", "dr14mono", "SigDistHist", "bitmeter", "phasewheel"):
+        assert not d[u].contents.instantiate(d[u], 48000.0, b"", none), u           # urid:map missing -> NULL
+    if not torch.cuda.is_available():
+        for u in ("EBUr128", "K20stereo", "COR", "spectr30stereo", "surround5"):
+            assert not d[u].contents.instantiate(d[u], 48000.0, b"", _feats), u     # no device, no CPU fallback -> NULL
+
+
 @pytest.mark.parametrize("fs", [48000.0, 44100.0, 96000.0, 88200.0, 192000.0])
 def test_host_design_bitwise_equals_oracle(fs):
     import meters_lv2_b200 as B
