@@ -165,6 +165,25 @@ def run_b200(args):
                       "prime_blocks": PRIME, "parallelism": "channel-shard x%d, no data-path collective" % ws},
            "value_per_gpu": value / ws, "gpu_launches": int(launches), "clocks": sampler.summary()}
 
+    # ---- whole-mix gated loudness (the path's one exchange): per-GPU histogram sum -> ONE int32[1508] all-reduce
+    # (NCCL when N > 1) -> calc_integ / calc_range on the sum.  Not part of the timed cycle: it is due once per 0.5 s of audio.
+    try:
+        from meters_lv2_b200 import shard
+        mixv = torch.zeros(B.MIX_WORDS, dtype=torch.int32, device=dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(3):                                   # first calls set up the communicator
+            bank.ebu.mix_reduce(mixv); shard.allreduce_mix(mixv)
+        torch.cuda.synchronize(); e0.record()
+        bank.ebu.mix_reduce(mixv); shard.allreduce_mix(mixv)
+        e1.record(); torch.cuda.synchronize()
+        mo = bank.ebu.mix_finish(mixv)
+        cm = int(mixv[2 * 752].item()); res0, _tp0 = bank.results()
+        out["whole_mix"] = {"integrated": float(mo[0]), "range_min": float(mo[2]), "range_max": float(mo[3]),
+                            "hist_M_points": cm, "hist_M_points_rank0_times_n": int(res0["hist_M_count"].astype(np.int64).sum()) * ws,
+                            "reduce_plus_allreduce_us": e0.elapsed_time(e1) * 1e3, "collective": "nccl all_reduce int32[%d]" % B.MIX_WORDS if ws > 1 else "none (N = 1)"}
+    except Exception as e:
+        out["whole_mix"] = {"error": repr(e)}
+
     # ---- parity spot check against the CPU oracle on the first instances (same block sequence) ----------------
     if rank == 0:
         try:

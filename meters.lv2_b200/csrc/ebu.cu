@@ -542,14 +542,19 @@ __global__ void ebu_ctl_kernel (int n_inst, int inst_sel, int cmd, int nchan, fl
 __global__ void ebu_mix_reduce_kernel (int n_inst, const int* __restrict__ histM, const int* __restrict__ histS,
                                        const int* __restrict__ cnt, int* __restrict__ out)
 {
-    // block b handles bin column(s); thread t strides over instances: coalescing is across bins
+    // blockIdx.x: bin column group (coalescing is across bins); blockIdx.y: slice of the instances.  Integer partial sums are
+    // merged with atomicAdd into the zeroed output: order-independent, hence exact.
     const int col = blockIdx.x * blockDim.x + threadIdx.x;    // 0..1507
     if (col >= B200M_MIX_WORDS) return;
+    const int per = (n_inst + gridDim.y - 1) / gridDim.y, i0 = blockIdx.y * per, i1 = min (n_inst, i0 + per);
+    const int* src; size_t pitch; int c;
+    if (col < 752) { src = histM; pitch = HIST_PITCH; c = col; }
+    else if (col < 1504) { src = histS; pitch = HIST_PITCH; c = col - 752; }
+    else { src = cnt; pitch = 4; c = col - 1504; }
     int acc = 0;
-    if (col < 752)       for (int i = 0; i < n_inst; ++i) acc += histM[(size_t)i * HIST_PITCH + col];
-    else if (col < 1504) for (int i = 0; i < n_inst; ++i) acc += histS[(size_t)i * HIST_PITCH + (col - 752)];
-    else                 for (int i = 0; i < n_inst; ++i) acc += cnt[(size_t)i * 4 + (col - 1504)];
-    out[col] = acc;
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) acc += src[(size_t)i * pitch + c];
+    if (acc) atomicAdd (out + col, acc);
 }
 
 __global__ void ebu_mix_finish_kernel (const int* __restrict__ mix, const float* __restrict__ bin_power, float* out5)
@@ -940,7 +945,10 @@ int b200m_ebu_mix_reduce (b200m_ebu* h, int32_t* d_out, void* stream)
 {
     if (!h || !d_out) return set_err (B200M_E_INVAL, "NULL argument");
     DeviceGuard g (h->device);
-    ebu_mix_reduce_kernel<<<(B200M_MIX_WORDS + 63) / 64, 64, 0, ebu_stream (h, stream)>>> ((int)h->n_inst, h->d_histM, h->d_histS, h->d_cnt, d_out);
+    cudaStream_t st = ebu_stream (h, stream);
+    B200M_CUDA (cudaMemsetAsync (d_out, 0, B200M_MIX_WORDS * sizeof (int32_t), st));
+    const unsigned slices = (unsigned)std::min<uint32_t> (h->n_inst, 128u);      // ~24 x 128 CTAs: enough loads in flight to stream the histograms
+    ebu_mix_reduce_kernel<<<dim3 ((B200M_MIX_WORDS + 63) / 64, slices), 64, 0, st>>> ((int)h->n_inst, h->d_histM, h->d_histS, h->d_cnt, d_out);
     B200M_LAUNCHED (1);
     B200M_CUDA (cudaGetLastError ());
     return 0;
