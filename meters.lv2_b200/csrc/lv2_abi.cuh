@@ -116,7 +116,7 @@ private:
 // Read-only view of one object atom of a control sequence.
 struct AtomObject {
     const AtomHead* a = nullptr;                               // a->type is Object or Blank
-    uint32_t otype () const { return ((const uint32_t*)(a + 1))[1]; }
+    uint32_t otype () const { return a->size >= 8 ? ((const uint32_t*)(a + 1))[1] : 0u; }      // 0 = no type: a truncated object matches nothing
     // value atom of the first property with this key, or NULL
     const AtomHead* get (LV2_URID key) const
     {
