@@ -342,8 +342,16 @@ def other_configs(torch, dist, B, x, K, W, hbm_peak):
     # C5: 2048 stereo phasewheel 2048-pt FFT + Stcorr (unit: stereo frames)
     pw = B.Phasewheel(2048, 1024, FS); co = B.Stcorrdsp(2048, int(FS))
 
+    # two independent banks over the same input: the latency-bound correlation kernel (64 warps) runs on a second stream
+    # beside the FFT kernels, joined at the end of every block
+    side = torch.cuda.Stream()
+
     def c5(s):
-        co.process_ptr(blk(s), stride, NFRAM); pw.process_ptr(blk(s), stride, NFRAM)
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        co.process_ptr(blk(s), stride, NFRAM, stream=side)
+        pw.process_ptr(blk(s), stride, NFRAM)
+        cur.wait_stream(side)
     for s in range(W + 1):
         c5(s)
     k5 = K - (K % 2)
