@@ -342,19 +342,21 @@ def other_configs(torch, dist, B, x, K, W, hbm_peak):
     # C5: 2048 stereo phasewheel 2048-pt FFT + Stcorr (unit: stereo frames)
     pw = B.Phasewheel(2048, 1024, FS); co = B.Stcorrdsp(2048, int(FS))
 
-    # two independent banks over the same input: the latency-bound correlation kernel (64 warps) runs on a second stream
-    # beside the FFT kernels, joined at the end of every block
+    # two independent banks over the same input ring, each on its own stream (the latency-bound correlation kernel, 64 warps,
+    # runs beside the FFT kernels); the streams fork at the first block of a loop and join at its last
     side = torch.cuda.Stream()
+    k5 = K - (K % 2)
 
-    def c5(s):
+    def c5(s, last=None):
         cur = torch.cuda.current_stream()
-        side.wait_stream(cur)
+        if s == 0:
+            side.wait_stream(cur)
         co.process_ptr(blk(s), stride, NFRAM, stream=side)
         pw.process_ptr(blk(s), stride, NFRAM)
-        cur.wait_stream(side)
+        if s == (k5 - 1 if last is None else last):
+            cur.wait_stream(side)
     for s in range(W + 1):
-        c5(s)
-    k5 = K - (K % 2)
+        c5(s, last=W)
     ms = timed_loop(torch, dist, 1, c5, k5)
     fr = 2048 * NFRAM
     cfg["C5_phasewheel_stcorr_2048st"] = {"frames_per_s": fr * k5 / (ms * 1e-3), "ms_per_block": ms / k5, "hbm_frac": fr * 12 * k5 / (ms * 1e-3) / 1e9 / hbm_peak}
