@@ -318,6 +318,22 @@ def other_configs(torch, dist, B, x, K, W, hbm_peak):
     n = N_INST * 2 * NFRAM
     cfg["C2_ebu_r128_8192st"] = {"samples_per_s": n * K / (ms * 1e-3), "ms_per_block": ms / K, "hbm_frac": n * 4 * K / (ms * 1e-3) / 1e9 / hbm_peak}
     del e
+    # the same bank at 4x the BASELINE batch: 8192 stereo instances are 512 warps for 592 SM sub-partitions (latency bound, the
+    # block time is flat from 2048 to 8192 instances); with 32768 the kernel streams (profiles/r1_scale_channels.txt)
+    try:
+        n4 = 4 * N_INST
+        x4 = (torch.rand((2 * n4, 4 * NFRAM), device=x.device, dtype=torch.float32) * 2 - 1) * 0.25
+        e4 = B.Ebu_r128_proc(n4, 2, FS); e4.integr_start()
+        b4, s4 = x4.data_ptr(), x4.stride(0)
+        for s in range(W + 4):
+            e4.process_ptr(b4 + 4 * NFRAM * (s % 4), s4, NFRAM)
+        k4x = max(10, K // 4)
+        ms = timed_loop(torch, dist, 1, lambda s: e4.process_ptr(b4 + 4 * NFRAM * (s % 4), s4, NFRAM), k4x)
+        cfg["C2x4_ebu_r128_32768st"] = {"samples_per_s": 4 * n * k4x / (ms * 1e-3), "ms_per_block": ms / k4x,
+                                        "hbm_frac": 4 * n * 4 * k4x / (ms * 1e-3) / 1e9 / hbm_peak, "note": "not a BASELINE config: shows the kernel's bandwidth when the chip is filled"}
+        del e4, x4
+    except Exception as ex:  # an extra, never fatal
+        cfg["C2x4_ebu_r128_32768st"] = {"error": repr(ex)}
     # C3: true peak (process) + K-meter, read every block (TPnRMS, src/dr14.c:391-450)
     t = B.TruePeakKmeter(2 * N_INST, FS)
 
