@@ -174,8 +174,9 @@ int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t
  * One host->device copy per block feeds both meters.  Atom/radar/GUI messaging is out of scope.
  * ====================================================================================== */
 typedef struct b200m_r128 b200m_r128;
-enum { B200M_R128_START = 1, B200M_R128_PAUSE = 2, B200M_R128_RESET = 3 };   /* CTL_START/PAUSE/RESET, src/uris.h:187-203; RESET = ebu_reset
-                                                                                * (src/ebulv2.cc:45-61): integr_reset + tp_max hold cleared */
+enum { B200M_R128_START = 1, B200M_R128_PAUSE = 2, B200M_R128_RESET = 3, B200M_R128_CLEAR_TPMAX = 4 };   /* CTL_START/PAUSE/RESET, src/uris.h:187-203; RESET = ebu_reset
+                                                                                * (src/ebulv2.cc:45-61): integr_reset + tp_max hold cleared;
+                                                                                * CLEAR_TPMAX: the hold alone (a dBTP-disabled cycle, :365-366) */
 int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsamp, int dbtp_enable);
 int b200m_r128_destroy (b200m_r128* h);
 int b200m_r128_control (b200m_r128* h, int32_t inst, int cmd, void* stream);      /* inst = -1: all */

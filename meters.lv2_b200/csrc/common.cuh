@@ -51,6 +51,10 @@ struct HostStage {
 
 int check_block_args (const void* h, const void* in, size_t stride, uint32_t nfram);
 
+// A bank switches to its own stream with the first *_host call; whatever the caller queued before that (controls on the
+// streams it passed) must not race with it: one device-wide synchronisation at the transition, nothing afterwards.
+#define B200M_ENTER_HOST_PATH(h) do { if (!(h)->last_host) B200M_CUDA (cudaDeviceSynchronize ()); } while (0)
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------- device helpers
 #define B200M_DEV __device__ __forceinline__

@@ -256,6 +256,7 @@ int b200m_dr14_run_host (b200m_dr14* h, const float* in, size_t stride, uint32_t
 {
     if (int rc = check_block_args (h, in, stride, nfram)) return rc;
     DeviceGuard g (h->device);
+    B200M_ENTER_HOST_PATH (h);
     // one stream for the copy and every kernel: stage here, then drive the true-peak bank's device path on it
     const size_t n_ch = (size_t)h->n_inst * h->nch;
     if (h->stage.ensure (n_ch, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");

@@ -822,6 +822,7 @@ int b200m_ebu_process_host (b200m_ebu* h, const float* in, size_t stride, uint32
 {
     if (int rc = check_block_args (h, in, stride, nfram)) return rc;
     DeviceGuard g (h->device);
+    B200M_ENTER_HOST_PATH (h);
     const size_t nch = (size_t)h->n_inst * h->nchan;
     if (h->stage.ensure (nch, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
     B200M_CUDA (cudaMemcpy2DAsync (h->stage.d, h->stage.cap * sizeof (float), in, stride * sizeof (float),

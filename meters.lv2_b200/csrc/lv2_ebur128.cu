@@ -15,6 +15,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
+#include <vector>
 #include "common.cuh"
 #include "lv2_abi.cuh"
 
@@ -36,8 +38,9 @@ struct Urids {
     LV2_URID ebu_state, rdr_histogram, rdr_histpoint, rdr_radarpoint, rdr_pointpos, rdr_pos_cur, rdr_pos_max;
 };
 
+struct EbuHub;
 struct EbuPlugin {
-    b200m_r128* bank = nullptr;
+    b200m_r128* bank = nullptr; EbuHub* hub = nullptr; int slot = -1;       // private bank of one, or slot `slot` of a shared bank
     float* stage = nullptr; size_t stage_cap = 0;             // pinned [2][cap] planar staging
     Urids u; AtomWriter out;
     const void* control = nullptr; void* notify = nullptr;
@@ -53,6 +56,101 @@ struct EbuPlugin {
     int sentM[HIST_LEN], sentS[HIST_LEN], hist_maxM = 0, hist_maxS = 0;   // what the UI has been told so far
     int32_t histM[HIST_LEN], histS[HIST_LEN];
 };
+
+// ---- batched mode (opt-in: B200M_LV2_BATCH=<slots>) ---------------------------------------------------------------------
+// Every EBUr128 instance a host loads is by default a synchronous bank of one: exact, but one upload / launch / download
+// round trip per instance and cycle.  With B200M_LV2_BATCH=N the instances of one sample rate share ONE bank of N slots:
+// run() copies its two input buffers into its rows of a pinned staging block and publishes the results of the PREVIOUS
+// cycle (one declared cycle of latency on every notify message; audio pass-through is not delayed); the instance whose
+// run() completes the cycle (all members have submitted) launches the bank asynchronously.  Host contract: every instance
+// runs once per cycle with the same n_samples; if one is skipped, the next double submission launches the cycle anyway.
+// dBTP is processed for every slot as soon as one member enables it; after a disable/enable the oversampler history is
+// current rather than frozen (the reference does not run the meter while disabled).
+struct EbuHub {
+    std::mutex mu;
+    double rate = 0; uint32_t slots = 0, members = 0;
+    b200m_r128* bank = nullptr; float* stage = nullptr;       // pinned [2 * slots][B200M_MAX_BLOCK]
+    std::vector<EbuPlugin*> member; std::vector<uint8_t> submitted; uint32_t n_submitted = 0, cycle_n = 0;
+    bool inflight = false;
+    std::vector<b200m_ebu_result> res; std::vector<float> tp;  // results of the last completed cycle
+};
+std::mutex g_hub_mu;
+std::vector<EbuHub*> g_hubs;
+
+void hub_fetch (EbuHub* hub)                                  // results of the cycle in flight (waits for it)
+{
+    if (!hub->inflight) return;
+    b200m_r128_results (hub->bank, hub->res.data (), hub->tp.data (), nullptr);
+    hub->inflight = false;
+}
+
+void hub_launch (EbuHub* hub)
+{
+    bool any_dbtp = false;
+    for (EbuPlugin* m : hub->member) if (m && m->dbtp_enable) any_dbtp = true;
+    b200m_r128_set_dbtp (hub->bank, any_dbtp);
+    if (hub->cycle_n && b200m_r128_run_host (hub->bank, hub->stage, B200M_MAX_BLOCK, hub->cycle_n) == 0) hub->inflight = true;
+    std::fill (hub->submitted.begin (), hub->submitted.end (), 0);
+    hub->n_submitted = 0; hub->cycle_n = 0;
+}
+
+EbuHub* hub_join (EbuPlugin* p, double rate)
+{
+    const char* v = getenv ("B200M_LV2_BATCH");
+    const int want = v ? atoi (v) : 0;
+    if (want < 2) return nullptr;
+    std::lock_guard<std::mutex> lk (g_hub_mu);
+    EbuHub* hub = nullptr;
+    for (EbuHub* h : g_hubs) if (h->rate == rate && h->members < h->slots) hub = h;
+    if (!hub) {
+        hub = new (std::nothrow) EbuHub;
+        if (!hub) return nullptr;
+        hub->rate = rate; hub->slots = (uint32_t)want;
+        if (b200m_r128_create (&hub->bank, 0, hub->slots, (float)rate, 0) ||
+            b200m_host_alloc ((void**)&hub->stage, (size_t)2 * hub->slots * B200M_MAX_BLOCK * sizeof (float))) {
+            b200m_r128_destroy (hub->bank); delete hub; return nullptr;
+        }
+        memset (hub->stage, 0, (size_t)2 * hub->slots * B200M_MAX_BLOCK * sizeof (float));
+        hub->member.assign (hub->slots, nullptr); hub->submitted.assign (hub->slots, 0);
+        hub->res.resize (hub->slots); hub->tp.assign (hub->slots, -INFINITY);
+        b200m_r128_results (hub->bank, hub->res.data (), hub->tp.data (), nullptr);     // the getters' initial values
+        g_hubs.push_back (hub);
+    }
+    std::lock_guard<std::mutex> lh (hub->mu);
+    for (uint32_t i = 0; i < hub->slots; ++i)
+        if (!hub->member[i]) { hub->member[i] = p; p->slot = (int)i; ++hub->members; return hub; }
+    return nullptr;
+}
+
+void hub_leave (EbuPlugin* p)
+{
+    EbuHub* hub = p->hub;
+    std::lock_guard<std::mutex> lk (g_hub_mu);
+    bool empty;
+    {
+        std::lock_guard<std::mutex> lh (hub->mu);
+        hub_fetch (hub);
+        if (hub->submitted[p->slot]) { hub->submitted[p->slot] = 0; --hub->n_submitted; }
+        hub->member[p->slot] = nullptr; --hub->members;
+        // the slot's next tenant starts from a reset instance and silence
+        b200m_r128_control (hub->bank, p->slot, B200M_R128_PAUSE, nullptr);
+        b200m_r128_control (hub->bank, p->slot, B200M_R128_RESET, nullptr);
+        memset (hub->stage + (size_t)2 * p->slot * B200M_MAX_BLOCK, 0, (size_t)2 * B200M_MAX_BLOCK * sizeof (float));
+        empty = hub->members == 0;
+    }
+    if (empty) {
+        for (size_t i = 0; i < g_hubs.size (); ++i) if (g_hubs[i] == hub) { g_hubs.erase (g_hubs.begin () + i); break; }
+        b200m_r128_destroy (hub->bank); b200m_host_free (hub->stage); delete hub;
+    }
+}
+
+// bank control for this instance (all of a private bank, one slot of a shared one)
+void bank_control (EbuPlugin* p, int cmd)
+{
+    if (!p->hub) { b200m_r128_control (p->bank, -1, cmd, nullptr); return; }
+    std::lock_guard<std::mutex> lh (p->hub->mu);
+    b200m_r128_control (p->hub->bank, p->slot, cmd, nullptr);
+}
 
 void send_control (EbuPlugin* p, int key, float value)       // forge_kvcontrolmessage, src/uris.h:279-294
 {
@@ -89,7 +187,7 @@ void forget_sent_histogram (EbuPlugin* p)
 
 void reset_all (EbuPlugin* p)                                // ebu_reset (:45-61)
 {
-    b200m_r128_control (p->bank, -1, B200M_R128_RESET, nullptr);
+    bank_control (p, B200M_R128_RESET);
     send_control (p, CTL_LV2_RESETRADAR, 0);
     for (int i = 0; i < p->radar_pos_max; ++i) { p->radarS[i] = -INFINITY; p->radarM[i] = -INFINITY; }
     forget_sent_histogram (p);
@@ -102,8 +200,8 @@ void integrate (EbuPlugin* p, bool on)                       // ebu_integrate (:
     if (p->integrating == on) return;
     if (on) {
         if (p->follow_transport_mode & 2) reset_all (p);
-        b200m_r128_control (p->bank, -1, B200M_R128_START, nullptr);
-    } else b200m_r128_control (p->bank, -1, B200M_R128_PAUSE, nullptr);
+        bank_control (p, B200M_R128_START);
+    } else bank_control (p, B200M_R128_PAUSE);
     p->integrating = on;
 }
 
@@ -141,6 +239,7 @@ void on_config (EbuPlugin* p, const AtomObject& obj, uint32_t n_samples)      //
         break;
     case CTL_UISETTINGS:
         p->ui_settings = (uint32_t)v;
+        if (p->hub && !p->dbtp_enable && (p->ui_settings & 64)) bank_control (p, B200M_R128_CLEAR_TPMAX);   // the hold restarts, as after disabled cycles
         p->dbtp_enable = (p->ui_settings & 64) != 0;
         break;
     default: break;
@@ -174,7 +273,8 @@ LV2_Handle ebur_instantiate (const LV2_Descriptor* d, double rate, const char*, 
     for (int i = 0; i < RADAR_POINTS; ++i) { p->radarS[i] = -INFINITY; p->radarM[i] = -INFINITY; }
     set_radarspeed (p, 2.0 * 60.0);
     forget_sent_histogram (p);
-    if (b200m_r128_create (&p->bank, 0, 1, (float)rate, 0)) { delete p; return nullptr; }     // ebu->init (2, rate); 2 x TruePeakdsp (:189-196)
+    p->hub = hub_join (p, rate);
+    if (!p->hub && b200m_r128_create (&p->bank, 0, 1, (float)rate, 0)) { delete p; return nullptr; }     // ebu->init (2, rate); 2 x TruePeakdsp (:189-196)
     return p;
 }
 
@@ -190,6 +290,13 @@ void ebur_connect (LV2_Handle h, uint32_t port, void* data)
     case EBU_OUTPUT1: p->output[1] = (float*)data; break;
     default: break;
     }
+}
+
+bool fetch_histogram (EbuPlugin* p)
+{
+    if (!p->hub) return b200m_r128_histogram (p->bank, 0, p->histM, p->histS, nullptr) == 0;
+    std::lock_guard<std::mutex> lh (p->hub->mu);               // waits for a cycle in flight: only instances with an open UI pay this
+    return b200m_r128_histogram (p->hub->bank, (uint32_t)p->slot, p->histM, p->histS, nullptr) == 0;
 }
 
 void ebur_run (LV2_Handle h, uint32_t n_samples)
@@ -223,7 +330,19 @@ void ebur_run (LV2_Handle h, uint32_t n_samples)
     b200m_ebu_result r; float tp_max = -INFINITY;
     memset (&r, 0, sizeof (r));
     bool ran = false;
-    if (n_samples >= 1 && n_samples <= B200M_MAX_BLOCK) {
+    if (p->hub && n_samples >= 1 && n_samples <= B200M_MAX_BLOCK) {
+        EbuHub* hub = p->hub;
+        std::lock_guard<std::mutex> lh (hub->mu);
+        hub_fetch (hub);                                       // first caller of a cycle: collect the previous cycle (the staging block is free again)
+        if (hub->submitted[p->slot] || (hub->cycle_n && hub->cycle_n != n_samples)) hub_launch (hub), hub_fetch (hub);   // contract broken: close the cycle as it is
+        r = hub->res[p->slot]; tp_max = p->dbtp_enable ? hub->tp[p->slot] : -INFINITY;
+        float* rows = hub->stage + (size_t)2 * p->slot * B200M_MAX_BLOCK;
+        memcpy (rows, p->input[0], n_samples * sizeof (float));
+        memcpy (rows + B200M_MAX_BLOCK, p->input[1], n_samples * sizeof (float));
+        hub->submitted[p->slot] = 1; ++hub->n_submitted; hub->cycle_n = n_samples;
+        if (hub->n_submitted == hub->members) hub_launch (hub);
+        ran = true;
+    } else if (n_samples >= 1 && n_samples <= B200M_MAX_BLOCK) {
         if (n_samples > p->stage_cap) {
             if (p->stage) b200m_host_free (p->stage);
             p->stage = nullptr; p->stage_cap = 0;
@@ -263,7 +382,7 @@ void ebur_run (LV2_Handle h, uint32_t n_samples)
     }
 
     if (p->ui_active && r.hist_M_count > 10 && r.hist_S_count > 10 &&
-        b200m_r128_histogram (p->bank, 0, p->histM, p->histS, nullptr) == 0) {             // histogram deltas (:420-461)
+        fetch_histogram (p)) {                                                                // histogram deltas (:420-461)
         int msgtx = 0; bool max_changed = false;
         for (int i = 110; i < 650; ++i) {
             const int vm = p->histM[i], vs = p->histS[i];
@@ -310,7 +429,7 @@ void ebur_run (LV2_Handle h, uint32_t n_samples)
 void ebur_cleanup (LV2_Handle h)
 {
     EbuPlugin* p = (EbuPlugin*)h;
-    b200m_r128_destroy (p->bank);
+    if (p->hub) hub_leave (p); else b200m_r128_destroy (p->bank);
     if (p->stage) b200m_host_free (p->stage);
     delete p;
 }

@@ -263,6 +263,7 @@ int b200m_ppm_process_host (b200m_ppm* h, const float* in, size_t stride, uint32
 {
     if (int rc = check_block_args (h, in, stride, nfram)) return rc;
     DeviceGuard g (h->device);
+    B200M_ENTER_HOST_PATH (h);
     const size_t rows = h->kind == B200M_PPM_MS ? (size_t)2 * h->n_units : h->n_units;
     if (h->stage.ensure (rows, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
     B200M_CUDA (cudaMemcpy2DAsync (h->stage.d, h->stage.cap * sizeof (float), in, stride * sizeof (float),

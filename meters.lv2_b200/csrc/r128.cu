@@ -132,14 +132,15 @@ int b200m_r128_control (b200m_r128* h, int32_t inst, int cmd, void* stream)
     switch (cmd) {
     case B200M_R128_START: return b200m_ebu_integr_start (h->ebu, inst, st);
     case B200M_R128_PAUSE: return b200m_ebu_integr_pause (h->ebu, inst, st);
-    case B200M_R128_RESET: {                                // ebu_reset (src/ebulv2.cc:45-61): integr_reset + tp_max = -inf
+    case B200M_R128_RESET:                                  // ebu_reset (src/ebulv2.cc:45-61): integr_reset + tp_max = -inf
+    case B200M_R128_CLEAR_TPMAX: {                          // tp_max = -inf alone: what a cycle with dBTP disabled leaves behind (:365-366)
         if (inst >= (int32_t)h->n_inst) return set_err (B200M_E_INVAL, "bad instance %d", inst);
         DeviceGuard g (h->device);
         const int first = inst < 0 ? 0 : inst, cnt = inst < 0 ? (int)h->n_inst : 1;
         r128_fill_kernel<<<(cnt + 255) / 256, 256, 0, (cudaStream_t)st>>> (cnt, h->d_tpmax + first, -INFINITY);
         B200M_LAUNCHED (1);
         B200M_CUDA (cudaGetLastError ());
-        return b200m_ebu_integr_reset (h->ebu, inst, st);
+        return cmd == B200M_R128_RESET ? b200m_ebu_integr_reset (h->ebu, inst, st) : 0;
     }
     default: return set_err (B200M_E_INVAL, "unknown control %d", cmd);
     }
@@ -157,6 +158,7 @@ int b200m_r128_run_host (b200m_r128* h, const float* in, size_t stride, uint32_t
 {
     if (int rc = check_block_args (h, in, stride, nfram)) return rc;
     DeviceGuard g (h->device);
+    B200M_ENTER_HOST_PATH (h);
     const size_t nch = (size_t)2 * h->n_inst;
     if (h->stage.ensure (nch, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
     // the staging buffer is single: the next copy may only start when the previous cycle's kernels have read it

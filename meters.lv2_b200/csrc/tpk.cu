@@ -775,6 +775,7 @@ int b200m_tpk_process_host (b200m_tpk* h, const float* in, size_t stride, uint32
     if (int rc = check_block_args (h, in, stride, nfram)) return rc;
     if (tp_mode > 1) return set_err (B200M_E_INVAL, "bad tp_mode %u", tp_mode);
     DeviceGuard g (h->device);
+    B200M_ENTER_HOST_PATH (h);
     if (h->stage.ensure (h->n_chan, nfram)) return set_err (B200M_E_NOMEM, "staging buffer allocation failed");
     B200M_CUDA (cudaMemcpy2DAsync (h->stage.d, h->stage.cap * sizeof (float), in, stride * sizeof (float),
                                    (size_t)nfram * sizeof (float), h->n_chan, cudaMemcpyHostToDevice, h->own));

@@ -130,3 +130,69 @@ def test_small_notify_buffer_and_odd_blocks():
     script = {0: [obj(MTR + b"meteron"), cfg("START", 0)]}
     drive(script, 120, block=1000, cap=1100)
     drive(script, 40, block=333, cap=4096, rate=44100.0)
+
+
+def _levels(buf):
+    """the 10 property values of the ebulevels object in a notify buffer -> {key urid: 4 value bytes}, or None"""
+    size = struct.unpack("<I", buf[:4])[0]
+    off, end, want = 16, 8 + size, urid(MTR + b"ebulevels")
+    while off + 16 <= end:
+        sz = struct.unpack("<I", buf[off + 8:off + 12])[0]
+        oid, ot = struct.unpack("<II", buf[off + 16:off + 24])
+        if ot == want:
+            props, q = {}, off + 24
+            while q + 16 <= off + 16 + sz:
+                key, _ctx, vs, _vt = struct.unpack("<IIII", buf[q:q + 16])
+                props[key] = bytes(buf[q + 16:q + 16 + vs])
+                q += 16 + (vs + 7) // 8 * 8
+            return props
+        off += 16 + (sz + 7) // 8 * 8
+    return None
+
+
+def test_batched_mode_one_cycle_latency(monkeypatch):
+    """B200M_LV2_BATCH: six EBUr128 instances share one bank; what each instance reports in cycle k + 1 is bit for bit what the
+    reference plugin reports in cycle k (loudness values, ranges, true peak), with per-instance controls"""
+    import meters_lv2_b200 as B
+    monkeypatch.setenv("B200M_LV2_BATCH", "6")
+    n, nb, blk = 6, 140, 1024
+    mine, l1 = descriptors(B.LIB_PATH)
+    ref, l2 = descriptors(O.PATHS["reference"])
+    gs = [Plugin(mine["EBUr128"]) for _ in range(n)]
+    rs = [Plugin(ref["EBUr128"]) for _ in range(n)]
+    x = S.white(2 * n, blk * nb, seed=61) * np.float32(3.0)
+    x[2:4] *= np.float32(0.05)
+    keys = [urid(MTR + k) for k in (b"ebu_loudnessM", b"ebu_maxloudnM", b"ebu_loudnessS", b"ebu_maxloudnS", b"ebu_integrated",
+                                   b"ebu_range_min", b"ebu_range_max", b"truepeak", b"ebu_integrating")]
+    script = {i: {} for i in range(n)}
+    for i in range(n):
+        script[i][1] = [obj(MTR + b"meteron")]
+        script[i][2] = [cfg("UISETTINGS", 8 + 64 if i != 5 else 8), cfg("START", 0)]        # instance 5 never enables dBTP
+    script[3][40] = [cfg("PAUSE", 0)]; script[3][55] = [cfg("START", 0)]
+    script[4][70] = [cfg("RESET", 0)]
+    empty = sequence([])
+    notes_g = [np.zeros(CAP, np.uint8) for _ in range(n)]; notes_r = [np.zeros(CAP, np.uint8) for _ in range(n)]
+    prev_ref = [None] * n
+    checked = 0
+    for b in range(nb):
+        for plugs, notes in ((gs, notes_g), (rs, notes_r)):
+            for i, p in enumerate(plugs):
+                note = notes[i]
+                note[:] = 0
+                note[:8] = np.frombuffer(struct.pack("<II", CAP - 8, 0), np.uint8)
+                ctl = sequence(script[i][b]) if b in script[i] else empty
+                bufs = [np.ascontiguousarray(x[2 * i + c, b * blk:(b + 1) * blk]) for c in range(2)]
+                p.port(0, ctl); p.port(1, note)
+                for c in range(2):
+                    p.port(2 + 2 * c, bufs[c]); p.port(3 + 2 * c, bufs[c])
+                p.run(blk)
+        for i in range(n):
+            lg, lr = _levels(notes_g[i].tobytes()), _levels(notes_r[i].tobytes())
+            if lg is not None and prev_ref[i] is not None and b >= 4:
+                for k in keys[:8]:
+                    assert lg[k] == prev_ref[i][k], (b, i, k, struct.unpack("<f", lg[k]), struct.unpack("<f", prev_ref[i][k]))
+                checked += 1
+            prev_ref[i] = lr
+    assert checked > n * 100
+    for p in gs + rs:
+        p.close()
