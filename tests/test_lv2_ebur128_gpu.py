@@ -196,3 +196,43 @@ def test_batched_mode_one_cycle_latency(monkeypatch):
     assert checked > n * 100
     for p in gs + rs:
         p.close()
+
+
+@pytest.mark.timeout(180)
+def test_batched_mode_survives_a_host_that_breaks_the_contract(monkeypatch):
+    """a skipped instance, a changing block size and instances leaving in the middle must neither hang nor corrupt the others:
+    a double submission (or a different n_samples) closes the open cycle as it is"""
+    import meters_lv2_b200 as B
+    monkeypatch.setenv("B200M_LV2_BATCH", "4")
+    mine, l1 = descriptors(B.LIB_PATH)
+    ps = [Plugin(mine["EBUr128"]) for _ in range(3)]                      # 3 members of a 4-slot hub
+    x = S.white(6, 1024 * 60, seed=5)
+    notes = [np.zeros(CAP, np.uint8) for _ in range(3)]
+    on = sequence([obj(MTR + b"meteron"), cfg("START", 0)]); empty = sequence([])
+    last = None
+    for b in range(60):
+        n = 512 if 30 <= b < 34 else 1024                                # the host changes its block size for a few cycles
+        for i, p in enumerate(ps):
+            if i == 1 and 10 <= b < 20:
+                continue                                                 # instance 1 is bypassed for ten cycles
+            if p is None:
+                continue
+            notes[i][:] = 0
+            notes[i][:8] = np.frombuffer(struct.pack("<II", CAP - 8, 0), np.uint8)
+            bufs = [np.ascontiguousarray(x[2 * i + c, b * 1024:b * 1024 + n]) for c in range(2)]
+            p.port(0, on if b == 0 else empty); p.port(1, notes[i])
+            for c in range(2):
+                p.port(2 + 2 * c, bufs[c]); p.port(3 + 2 * c, bufs[c])
+            p.run(n)
+        if b == 45:
+            ps[0].close(); ps[0] = None                                  # leaves while the others keep running
+        lv = _levels(notes[2].tobytes())
+        if lv is not None and b > 8:
+            last = struct.unpack("<f", lv[urid(MTR + b"ebu_loudnessM")])[0]
+            assert np.isfinite(last) and -40.0 < last < 10.0, (b, last)
+    assert last is not None
+    for p in ps:
+        if p is not None:
+            p.close()
+    late = Plugin(mine["EBUr128"])                                       # a fresh hub can be created after the old one emptied
+    late.close()
