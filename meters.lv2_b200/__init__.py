@@ -68,6 +68,8 @@ _PROTOS = {
     "b200m_tpk_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_uint32, _v]),
     "b200m_tpk_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_uint32]),
     "b200m_tpk_read_device": (C.c_int, [_v, _v]),
+    "b200m_tpk_set_precision": (C.c_int, [_v, C.c_int]),
+    "b200m_tpk_precision": (C.c_int, [_v]),
     "b200m_tpk_results": (C.c_int, [_v, _v, _v]),
     "b200m_tpk_reset": (C.c_int, [_v, C.c_int32, _v]),
     "b200m_tpk_reset_kmeter": (C.c_int, [_v, _v]),
@@ -83,6 +85,7 @@ _PROTOS = {
     "b200m_r128_run_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32]),
     "b200m_r128_results": (C.c_int, [_v, _v, _v, _v]),
     "b200m_r128_set_dbtp": (C.c_int, [_v, C.c_int]),
+    "b200m_r128_set_precision": (C.c_int, [_v, C.c_int]),
     "b200m_r128_histogram": (C.c_int, [_v, C.c_uint32, _v, _v, _v]),
     "b200m_r128_snapshot_size": (C.c_size_t, [_v]),
     "b200m_r128_snapshot": (C.c_int, [_v, _v, C.c_size_t, _v]),
@@ -357,6 +360,7 @@ class Ebu_r128_proc(_Bank):
 
 TPK_TRUEPEAK, TPK_KMETER = 1, 2
 TP_MODE_PROCESS, TP_MODE_MAX = 0, 1
+PREC_EXACT, PREC_FMA = 0, 1
 
 
 class TruePeakKmeter(_Bank):
@@ -384,6 +388,10 @@ class TruePeakKmeter(_Bank):
 
     def process_max(self, x, stream=None):
         self.process(x, TP_MODE_MAX, stream)
+
+    def set_precision(self, mode):
+        """PREC_EXACT (bit-identical floats, default) or PREC_FMA (fused FIR, readings within +-1e-4 dB)"""
+        _ck(lib().b200m_tpk_set_precision(self.h, int(mode)))
 
     def read_device(self, stream=None):
         _ck(lib().b200m_tpk_read_device(self.h, _stream_ptr(stream)))
@@ -730,6 +738,10 @@ class EBUr128(_Bank):
     def set_dbtp(self, enable):
         """self->dbtp_enable (src/ebulv2.cc:316-317): takes effect with the next run"""
         _ck(lib().b200m_r128_set_dbtp(self.h, int(bool(enable))))
+
+    def set_precision(self, mode):
+        """precision of the dBTP FIR (PREC_EXACT / PREC_FMA); the EBU R128 part is always exact"""
+        _ck(lib().b200m_r128_set_precision(self.h, int(mode)))
 
     def histogram(self, inst, stream=None):
         m = np.empty(751, np.int32); s = np.empty(751, np.int32)

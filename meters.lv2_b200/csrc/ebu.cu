@@ -651,7 +651,8 @@ static int ebu_ctl (b200m_ebu* h, int32_t inst, int cmd, void* stream)
     if (inst >= (int32_t)h->n_inst) return set_err (B200M_E_INVAL, "instance %d out of range", inst);
     DeviceGuard g (h->device);
     if (cmd == 3) h->phase_reset (); else h->phase_ctl (inst, cmd);
-    ebu_ctl_kernel<<<(h->n_inst + 127) / 128, 128, 0, (cudaStream_t)stream>>> (
+    // after process_host the bank runs on its own stream: a control on any other stream would race with the kernels in flight
+    ebu_ctl_kernel<<<(h->n_inst + 127) / 128, 128, 0, h->last_host ? h->own : (cudaStream_t)stream>>> (
         (int)h->n_inst, inst, cmd, (int)h->nchan, h->d_z, h->d_frpwr, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt);
     B200M_LAUNCHED (1);
     B200M_CUDA (cudaGetLastError ());

@@ -197,6 +197,12 @@ int b200m_r128_set_dbtp (b200m_r128* h, int enable)
     return 0;
 }
 
+int b200m_r128_set_precision (b200m_r128* h, int mode)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    return b200m_tpk_set_precision (h->tpk, mode);         // the EBU R128 part is always exact: it feeds the integer histograms
+}
+
 int b200m_r128_histogram (b200m_r128* h, uint32_t inst, int32_t* hist_M, int32_t* hist_S, void* stream)
 {
     if (!h) return set_err (B200M_E_INVAL, "NULL handle");

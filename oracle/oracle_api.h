@@ -136,6 +136,14 @@ int   orc_pw_process  (void* h, const float* in, size_t stride, int nfram, float
 void  orc_pw_read     (void* h, float* phase, float* level, float* peak); /* [n_inst][fft_bins] x2, [n_inst] */
 void  orc_pw_raw      (void* h, int inst, float* powL, float* powR, float* phL, float* phR);
 
+/* ---- the timed CPU baseline (oracle/cpu_bench.inc) ----
+ * orc_cpu_info: hardware threads, CPUs in the affinity mask, cgroup CPU quota (0 = none); returns the number of CPUs
+ * worth starting a thread on.  orc_r128_bench: `steps` steps of `nblocks` blocks of the EBUr128 audio cycle over n_inst
+ * stereo instances on `nthreads` persistent (optionally pinned) workers that own their instances and input;
+ * out6 = samples/s, wall s, threads, steps, slowest/mean worker time, samples/s per thread */
+int   orc_cpu_info    (int* hw_threads, int* affinity_cpus, double* cgroup_quota_cpus);
+int   orc_r128_bench  (int n_inst, int nfram, int nblocks, int nthreads, int pin, int steps, int warmup, float fsamp, double* out6);
+
 #ifdef __cplusplus
 }
 #endif

@@ -903,3 +903,5 @@ void orc_pw_raw (void* h, int inst, float* pl, float* pr, float* fl, float* fr) 
 }
 
 }  // extern "C"
+
+#include "cpu_bench.inc"

@@ -435,3 +435,5 @@ void  orc_pw_read (void*, float*, float*, float*) {}
 void  orc_pw_raw (void*, int, float*, float*, float*, float*) {}
 
 } // extern "C"
+
+#include "cpu_bench.inc"

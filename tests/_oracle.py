@@ -96,6 +96,8 @@ def _proto(lib):
         "orc_pw_process": (C.c_int, [_v, _v, C.c_size_t, C.c_int, C.c_float, C.c_int]),
         "orc_pw_read": (None, [_v, _v, _v, _v]),
         "orc_pw_raw": (None, [_v, C.c_int, _v, _v, _v, _v]),
+        "orc_cpu_info": (C.c_int, [_v, _v, _v]),
+        "orc_r128_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _v]),
     }
     for name, (res, args) in P.items():
         fn = getattr(lib, name)
@@ -117,6 +119,21 @@ def load(kind="best"):
 
 def ptr(a):
     return a.ctypes.data_as(C.c_void_p)
+
+
+def cpu_info(kind="best"):
+    """CPUs this process may use: (threads worth starting, hardware threads, affinity mask size, cgroup quota or 0)"""
+    hw = C.c_int(); af = C.c_int(); q = C.c_double()
+    eff = load(kind).orc_cpu_info(C.byref(hw), C.byref(af), C.byref(q))
+    return eff, hw.value, af.value, q.value
+
+
+def r128_bench(n_inst, nfram, nblocks, nthreads, steps, warmup=1, pin=True, fsamp=48000.0, kind="best"):
+    """the timed CPU baseline (oracle/cpu_bench.inc): persistent pinned workers owning their instances"""
+    out = (C.c_double * 6)()
+    rc = load(kind).orc_r128_bench(n_inst, nfram, nblocks, nthreads, int(pin), steps, warmup, fsamp, out)
+    assert rc == 0
+    return {"samples_per_s": out[0], "wall_s": out[1], "threads": int(out[2]), "steps": int(out[3]), "imbalance": out[4], "per_thread": out[5]}
 
 
 def planar(a):
