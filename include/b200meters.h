@@ -61,6 +61,12 @@ uint64_t    b200m_launch_count (void);
  * result in 1e9 lane-operations/s. */
 int         b200m_peak_probe (int device, int kind, double* gops);
 
+/* Self-test hook: log10f of the `count` floats whose bit patterns are first_bits, first_bits + 1, ... written to the DEVICE
+ * array d_out, evaluated by the device function every loudness / dB value of the engine goes through (a restatement of
+ * glibc's log10f: the reference bins log10f results into integer histograms, ebumeter/ebu_r128_proc.cc:66-79,116-141,259).
+ * tests/test_log10f_sweep_gpu.py sweeps all 2^31 non-negative floats against the host libm with it. */
+int         b200m_selftest_log10f (int device, uint32_t first_bits, uint32_t count, float* d_out, void* stream);
+
 /* Host-side coefficient design, callable without a GPU (pure functions of the sample rate, computed with
  * the host libm in the reference's expression types so that every value is bitwise the reference's):
  *   ebu : detect_init (ebumeter/ebu_r128_proc.cc:263-293)           -> a0 a1 a2 b1 b2 c3 c4

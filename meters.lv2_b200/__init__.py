@@ -68,6 +68,7 @@ _PROTOS = {
     "b200m_tpk_process_device": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_uint32, _v]),
     "b200m_tpk_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_uint32]),
     "b200m_tpk_read_device": (C.c_int, [_v, _v]),
+    "b200m_selftest_log10f": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _v, _v]),
     "b200m_tpk_set_precision": (C.c_int, [_v, C.c_int]),
     "b200m_tpk_precision": (C.c_int, [_v]),
     "b200m_tpk_results": (C.c_int, [_v, _v, _v]),

@@ -71,7 +71,8 @@ static bool gpu_local_cpus (cpu_set_t* set)
     if (!got) return false;
     CPU_ZERO (set);
     int n = 0;
-    for (char* tok = strtok (line, ",\n"); tok; tok = strtok (nullptr, ",\n")) {      // "0-31,64-95"
+    char* save = nullptr;
+    for (char* tok = strtok_r (line, ",\n", &save); tok; tok = strtok_r (nullptr, ",\n", &save)) {      // "0-31,64-95"
         int a = 0, b = 0;
         const int k = sscanf (tok, "%d-%d", &a, &b);
         if (k < 1) continue;

@@ -37,6 +37,7 @@ struct TpkState {                           // SoA, one entry per channel
     float *hist;                            // [n_chan][48]: the 48 inputs preceding the next block
     float *tp_z1, *tp_z2, *tp_m, *tp_p; int *tp_res;
     float *km_z1, *km_z2, *km_rms, *km_peak, *km_fall; int *km_cnt, *km_fpp, *km_flag;
+    unsigned* done_cnt;                     // CTAs of the running grid that reached their end (EBUr128 cycle, see the kernel's epilogue)
 };
 
 // The zita table depends only on (hl = 24, np = 4, fr = 1.0), not on the sample rate, so its 120 floats are universal
@@ -597,8 +598,14 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
                 st.tp_res[ch] = 1; st.tp_res[ch + 1] = 1;
             }
             // launched with programmatic serialization behind the K-weighting kernel (r128.cu): this grid must not complete
-            // before that one has, so that the kernels queued behind it see its results (no-op in a plain launch)
-            asm volatile ("griddepcontrol.wait;" ::: "memory");
+            // before that one has, so that the kernels queued behind it see its results.  Only the LAST CTA to finish waits
+            // (griddepcontrol.wait is a no-op in a plain launch): if every CTA waited, the first wave would sit on its SM
+            // slots until the slower, latency-bound K-weighting grid ends and the second wave could not start.
+            __syncthreads ();
+            if (tid == 0) {
+                const unsigned prev = atomicAdd (st.done_cnt, 1u);
+                if (prev == gridDim.x - 1) { *st.done_cnt = 0u; asm volatile ("griddepcontrol.wait;" ::: "memory"); }
+            }
         }
     }
     if (is_tp && live) {
@@ -797,6 +804,7 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     A ((void**)&h->st.km_z1, n * 4); A ((void**)&h->st.km_z2, n * 4); A ((void**)&h->st.km_rms, n * 4); A ((void**)&h->st.km_peak, n * 4);
     A ((void**)&h->st.km_fall, n * 4); A ((void**)&h->st.km_cnt, n * 4); A ((void**)&h->st.km_fpp, n * 4); A ((void**)&h->st.km_flag, n * 4);
     A ((void**)&h->d_res, n * sizeof (b200m_tpk_result));
+    A ((void**)&h->st.done_cnt, 16);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         // constructors: TruePeakdsp _res(true) (:29); Kmeterdsp _flag(false), all zero (kmeterdsp.cc:30-40);
@@ -816,7 +824,7 @@ int b200m_tpk_destroy (b200m_tpk* h)
     DeviceGuard g (h->device);
     cudaDeviceSynchronize ();
     void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms,
-                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg};
+                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt};
     for (void* p : ps) cudaFree (p);
     h->stage.release ();
     if (h->own) cudaStreamDestroy (h->own);

@@ -142,6 +142,7 @@ void  orc_pw_raw      (void* h, int inst, float* powL, float* powR, float* phL, 
  * stereo instances on `nthreads` persistent (optionally pinned) workers that own their instances and input;
  * out6 = samples/s, wall s, threads, steps, slowest/mean worker time, samples/s per thread */
 int   orc_cpu_info    (int* hw_threads, int* affinity_cpus, double* cgroup_quota_cpus);
+long long orc_log10f_check (uint32_t first_bits, uint32_t count, const float* dev, int nthreads, uint32_t* bad3); /* host libm log10f vs dev[i] */
 int   orc_r128_bench  (int n_inst, int nfram, int nblocks, int nthreads, int pin, int steps, int warmup, float fsamp, double* out6);
 
 #ifdef __cplusplus

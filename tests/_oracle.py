@@ -96,6 +96,7 @@ def _proto(lib):
         "orc_pw_process": (C.c_int, [_v, _v, C.c_size_t, C.c_int, C.c_float, C.c_int]),
         "orc_pw_read": (None, [_v, _v, _v, _v]),
         "orc_pw_raw": (None, [_v, C.c_int, _v, _v, _v, _v]),
+        "orc_log10f_check": (C.c_longlong, [C.c_uint32, C.c_uint32, _v, C.c_int, _v]),
         "orc_cpu_info": (C.c_int, [_v, _v, _v]),
         "orc_r128_bench": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _v]),
     }
