@@ -704,11 +704,16 @@ int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nch
     if (e == cudaSuccess) e = cudaMemcpy (h->d_binpow, bp, sizeof (bp), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
     // K1 carries 102 KB of dynamic shared memory per CTA
-#define EBU_ATTR(NC, AL) if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_frag<NC, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SMEM_BYTES)
+    // ... and asks for the largest shared-memory carveout: with the default the driver configures the SM for just what this kernel
+    // needs (132 KB), which leaves room for ONE CTA of the true-peak kernel that is meant to share the SM with it (r128.cu)
+#define EBU_ATTR(NC, AL) if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_frag<NC, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SMEM_BYTES); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_frag<NC, AL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
     EBU_ATTR (1, true); EBU_ATTR (1, false); EBU_ATTR (2, true); EBU_ATTR (2, false);
 #undef EBU_ATTR
     if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_TMA_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_TMA_SMEM);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_tma<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_tma<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // TMA staging is bit-identical and removes ~120 address instructions per tile, but measured no faster standalone (26.0 vs
     // 25.8 us per block) and 3 % slower inside the EBUr128 cycle (the mbarrier try_wait spin takes issue slots from the
     // co-running true-peak kernel, a scoreboard wait does not): opt-in with B200M_EBU_TMA=1

@@ -56,6 +56,9 @@ void dr_run (LV2_Handle h, uint32_t n)
 {
     DrPlugin* p = (DrPlugin*)h;
     float* in[2] = {fport (p, DR_INPUT0), fport (p, DR_INPUT1)}; float* out[2] = {fport (p, DR_OUTPUT0), fport (p, DR_OUTPUT1)};
+    // audio first (dr14_run ends with this copy, src/dr14.c:477-481): no metering failure may drop it.  TruePeakdsp::process
+    // itself is limited to 8192 frames (jmeters/truepeakdsp.cc:43-44), so longer cycles are forwarded but not metered.
+    for (uint32_t c = 0; c < p->nch; ++c) if (out[c] && in[c] && in[c] != out[c]) memcpy (out[c], in[c], sizeof (float) * n);
     if (!in[0] || (p->nch == 2 && !in[1]) || n < 1 || n > B200M_MAX_BLOCK) return;
     const bool follow_host_transport = fport (p, DR_HOST_TRANSPORT) && *fport (p, DR_HOST_TRANSPORT) != 0;
     bool reset = false;
@@ -106,7 +109,6 @@ void dr_run (LV2_Handle h, uint32_t n)
         for (uint32_t c = 0; c < p->nch; ++c) { W (pm_peak[c], -100); W (pm_rms[c], -100); if (p->dr_mode) W (p_dr[c], 21); }
         W (DR_BLKCNT, -1 - (rand () & 0xffff));
     }
-    for (uint32_t c = 0; c < p->nch; ++c) if (out[c] && in[c] != out[c]) memcpy (out[c], in[c], sizeof (float) * n);
 }
 
 void dr_cleanup (LV2_Handle h)

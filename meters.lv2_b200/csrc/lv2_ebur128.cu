@@ -302,6 +302,10 @@ bool fetch_histogram (EbuPlugin* p)
 void ebur_run (LV2_Handle h, uint32_t n_samples)
 {
     EbuPlugin* p = (EbuPlugin*)h;
+    // audio first, whatever happens to the metering below (the reference ends ebur128_run with this copy, src/ebulv2.cc:484-491;
+    // doing it first means an engine failure, a missing notify port or an over-long cycle can never drop audio)
+    for (int c = 0; c < 2; ++c)
+        if (p->output[c] && p->input[c] && p->input[c] != p->output[c]) memcpy (p->output[c], p->input[c], sizeof (float) * n_samples);
     if (!p->notify || !p->input[0] || !p->input[1]) return;
     const uint32_t capacity = ((const AtomHead*)p->notify)->size;      // host convention: capacity of the output port
     p->out.begin_sequence (p->notify, capacity);
@@ -421,9 +425,6 @@ void ebur_run (LV2_Handle h, uint32_t n_samples)
         p->out.prop_float (p->u.integr_time, (float)(p->integration_time / p->rate));
         p->out.end_object ();
     }
-
-    for (int c = 0; c < 2; ++c)
-        if (p->output[c] && p->input[c] != p->output[c]) memcpy (p->output[c], p->input[c], sizeof (float) * n_samples);
 }
 
 void ebur_cleanup (LV2_Handle h)

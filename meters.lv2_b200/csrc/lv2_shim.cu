@@ -107,14 +107,13 @@ void shim_cleanup (LV2_Handle h)
 
 const void* shim_extension_data (const char*) { return nullptr; }
 
-void run_cor (Shim* s, uint32_t n)
+void run_cor (Shim* s, uint32_t off, uint32_t n)
 {
-    float* in[2] = {s->port[MTR_INPUT0], s->port[MTR_INPUT1]}; float* out[2] = {s->port[MTR_OUTPUT0], s->port[MTR_OUTPUT1]};
+    float* in[2] = {s->port[MTR_INPUT0] + off, s->port[MTR_INPUT1] + off};
     if (!stage_in (s, in, n)) return;
     float v = 0;
     if (b200m_cor_process_host (s->cor, s->stage, s->stage_cap, n) == 0 && b200m_cor_results (s->cor, &v, nullptr) == 0)
         *s->port[MTR_LEVEL0] = v;                          // *level[0] = cor->read() (:516-517)
-    pass_through (in, out, 2, n);
 }
 
 // the "re-use port 0 to request/notify UI" handshake shared by dbtp_run (:444-463) and kmeter_run (:339-357)
@@ -135,14 +134,14 @@ bool refl_handshake (Shim* s, bool kmeter)
     return reinit;
 }
 
-void run_tpk (Shim* s, uint32_t n)
+void run_tpk (Shim* s, uint32_t off, uint32_t n)
 {
     const bool km = s->kind == K_KMETER;
     const bool reinit = refl_handshake (s, km);
-    float* in[2] = {s->port[MTR_INPUT0], s->port[MTR_INPUT1]}; float* out[2] = {s->port[MTR_OUTPUT0], s->port[MTR_OUTPUT1]};
+    // a mono meter re-uses the second channel's port slots for its peak values: only chn audio pointers exist
+    float* in[2] = {s->port[MTR_INPUT0] + off, s->chn == 2 ? s->port[MTR_INPUT1] + off : nullptr};
     if (!stage_in (s, in, n)) return;
     if (b200m_tpk_process_host (s->tpk, s->stage, s->stage_cap, n, B200M_TP_MODE_PROCESS)) return;
-    pass_through (in, out, s->chn, n);
     if (reinit) {                                          // force parameter change (:381-389, :476-489); no read() in such a cycle
         b200m_tpk_result sync[2];
         b200m_tpk_results (s->tpk, sync, nullptr);          // stream sync only: run() must not return while the upload of `stage` is in flight
@@ -180,11 +179,11 @@ void run_tpk (Shim* s, uint32_t n)
 }
 
 // run() and bbcm_run() of the needle meters (src/meters.cc:298-331,552-589)
-void run_needle (Shim* s, uint32_t n)
+void run_needle (Shim* s, uint32_t off, uint32_t n)
 {
     const float r = *s->port[MTR_REFLEVEL];
     if (s->p_refl != r) { s->p_refl = r; s->rlgain = powf (10.0f, 0.05f * (s->p_refl + 18.0)); }
-    float* in[2] = {s->port[MTR_INPUT0], s->port[MTR_INPUT1]}; float* out[2] = {s->port[MTR_OUTPUT0], s->port[MTR_OUTPUT1]};
+    float* in[2] = {s->port[MTR_INPUT0] + off, s->chn == 2 ? s->port[MTR_INPUT1] + off : nullptr};
     if (s->kind == K_BBCM6) {
         const bool s20 = (*s->port[MTR_PEAK0] > 0.5) ? true : false;           // port 7
         b200m_ppm_set_gain (s->ppm, -6, s20 ? +14 : -6);
@@ -194,12 +193,11 @@ void run_needle (Shim* s, uint32_t n)
     if (b200m_ppm_process_host (s->ppm, s->stage, s->stage_cap, n) || b200m_ppm_read_device (s->ppm, nullptr) || b200m_ppm_results (s->ppm, v, nullptr)) return;
     *s->port[MTR_LEVEL0] = s->rlgain * v[0];
     if (s->chn == 2) *s->port[MTR_LEVEL1] = s->rlgain * v[1];
-    pass_through (in, out, s->chn, n);
 }
 
-void run_spec (Shim* s, uint32_t n)
+void run_spec (Shim* s, uint32_t off, uint32_t n)
 {
-    float* in[2] = {s->port[SA_INPUT0], s->port[SA_INPUT1]}; float* out[2] = {s->port[SA_OUTPUT0], s->port[SA_OUTPUT1]};
+    float* in[2] = {s->port[SA_INPUT0] + off, s->chn == 2 ? s->port[SA_INPUT1] + off : nullptr};
     if (!stage_in (s, in, n)) return;
     float ports[60];
     if (b200m_spec_process_host (s->spec, s->stage, s->stage_cap, n, *s->port[SA_SPEED], *s->port[SA_RESET])) return;
@@ -208,14 +206,13 @@ void run_spec (Shim* s, uint32_t n)
         if (s->port[i]) *s->port[i] = ports[i];
         if (s->port[30 + i]) *s->port[30 + i] = ports[30 + i] <= -500.0f ? -500.0f - (rand () & 0xffff) : ports[30 + i];   // :243-246
     }
-    pass_through (in, out, s->chn, n);
 }
 
 // sur_run (src/surmeter.c:115-147): 3 or 4 selectable-pair correlation meters + one K-meter per channel
-void run_sur (Shim* s, uint32_t n)
+void run_sur (Shim* s, uint32_t off, uint32_t n)
 {
-    float* in[8]; float* out[8];
-    for (uint32_t c = 0; c < s->chn; ++c) { in[c] = s->port[13 + 4 * c]; out[c] = s->port[14 + 4 * c]; if (!in[c]) return; }
+    float* in[8];
+    for (uint32_t c = 0; c < s->chn; ++c) { in[c] = s->port[13 + 4 * c]; if (!in[c]) return; in[c] += off; }
     if (n > s->stage2_cap) {
         if (s->stage2) b200m_host_free (s->stage2);
         s->stage2 = nullptr; s->stage2_cap = 0;
@@ -244,19 +241,34 @@ void run_sur (Shim* s, uint32_t n)
         if (s->port[15 + 4 * c]) *s->port[15 + 4 * c] = r[c].km_rms;         // Kmeterdsp::read (m, p): *level = m, *peak = p
         if (s->port[16 + 4 * c]) *s->port[16 + 4 * c] = r[c].km_peak;
     }
-    pass_through (in, out, s->chn, n);
 }
 
 void shim_run (LV2_Handle h, uint32_t n)
 {
     Shim* s = (Shim*)h;
-    if (n == 0 || n > B200M_MAX_BLOCK) return;             // run() never fails
-    switch (s->kind) {
-    case K_COR: run_cor (s, n); break;
-    case K_DBTP: case K_KMETER: run_tpk (s, n); break;
-    case K_SPEC: run_spec (s, n); break;
-    case K_NEEDLE: case K_BBCM6: run_needle (s, n); break;
-    case K_SUR: run_sur (s, n); break;
+    if (n == 0) return;
+    // Audio is forwarded FIRST and unconditionally (every reference run() ends in the in -> out memcpy, src/meters.cc:326-330,
+    // :415-417, :531-535; src/spectrumlv2.c:249-256; src/surmeter.c:143-146): a metering failure -- no memory, a CUDA error --
+    // may cost a meter reading, never the audio.  run() itself never fails.
+    {
+        float* in[8] = {nullptr}; float* out[8] = {nullptr};
+        if (s->kind == K_SUR) for (uint32_t c = 0; c < s->chn; ++c) { in[c] = s->port[13 + 4 * c]; out[c] = s->port[14 + 4 * c]; }
+        else if (s->kind == K_SPEC) { in[0] = s->port[SA_INPUT0]; out[0] = s->port[SA_OUTPUT0]; if (s->chn == 2) { in[1] = s->port[SA_INPUT1]; out[1] = s->port[SA_OUTPUT1]; } }
+        else { in[0] = s->port[MTR_INPUT0]; out[0] = s->port[MTR_OUTPUT0]; if (s->chn == 2) { in[1] = s->port[MTR_INPUT1]; out[1] = s->port[MTR_OUTPUT1]; } }
+        pass_through (in, out, s->chn, n);
+        for (uint32_t c = 0; c < s->chn; ++c) if (!in[c]) return;          // unconnected input: nothing to meter
+    }
+    // the engine's block limit is 8192 frames (B200M_MAX_BLOCK = the hosts' MAXPERIOD); the reference's needle / COR / K-meter /
+    // spectrum plugins take any n, so longer cycles are metered in pieces of at most 8192 frames
+    for (uint32_t off = 0; off < n; off += B200M_MAX_BLOCK) {
+        const uint32_t k = n - off < B200M_MAX_BLOCK ? n - off : B200M_MAX_BLOCK;
+        switch (s->kind) {
+        case K_COR: run_cor (s, off, k); break;
+        case K_DBTP: case K_KMETER: run_tpk (s, off, k); break;
+        case K_SPEC: run_spec (s, off, k); break;
+        case K_NEEDLE: case K_BBCM6: run_needle (s, off, k); break;
+        case K_SUR: run_sur (s, off, k); break;
+        }
     }
 }
 

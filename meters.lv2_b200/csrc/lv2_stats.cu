@@ -266,10 +266,11 @@ void sdh_run (StatsPlugin* p, uint32_t n)
 void stats_run (LV2_Handle h, uint32_t n)
 {
     StatsPlugin* p = (StatsPlugin*)h;
+    // audio first (src/bitmeter.c:330-334, src/sigdistlv2.c:372-376 end with this copy): a metering failure never drops it
+    if (p->output[0] && p->input[0] && p->input[0] != p->output[0]) memcpy (p->output[0], p->input[0], sizeof (float) * n);
     if (!p->notify || !p->input[0]) return;
     p->out.begin_sequence (p->notify, ((const AtomHead*)p->notify)->size);
     if (p->is_bim) bim_run (p, n); else sdh_run (p, n);
-    if (p->output[0] && p->input[0] != p->output[0]) memcpy (p->output[0], p->input[0], sizeof (float) * n);
 }
 
 void stats_cleanup (LV2_Handle h)

@@ -63,6 +63,9 @@ void xfer_connect (LV2_Handle h, uint32_t port, void* data)
 void xfer_run (LV2_Handle h, uint32_t n)
 {
     XferPlugin* p = (XferPlugin*)h;
+    // audio first: the reference forwards it at the end of xfer_run (src/xfer.c:262-275) and therefore DROPS it in a cycle whose
+    // atom buffer is too small (:192-205); here a metering / messaging problem never costs audio
+    for (int c = 0; c < 2; ++c) if (p->output[c] && p->input[c] && p->input[c] != p->output[c]) memcpy (p->output[c], p->input[c], sizeof (float) * n);
     if (!p->notify || !p->input[0] || !p->input[1]) return;
     const size_t size = (sizeof (float) * n + 64) * 2;
     const uint32_t capacity = ((const AtomHead*)p->notify)->size;
@@ -105,7 +108,6 @@ void xfer_run (LV2_Handle h, uint32_t n)
         p->out.prop_vector_f32 (p->audioright, p->input[1], n);
         p->out.end_object ();
     }
-    for (int c = 0; c < 2; ++c) if (p->output[c] && p->input[c] != p->output[c]) memcpy (p->output[c], p->input[c], sizeof (float) * n);
 }
 
 void xfer_cleanup (LV2_Handle h)

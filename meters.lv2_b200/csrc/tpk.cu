@@ -38,6 +38,9 @@ struct TpkState {                           // SoA, one entry per channel
     float *tp_z1, *tp_z2, *tp_m, *tp_p; int *tp_res;
     float *km_z1, *km_z2, *km_rms, *km_peak, *km_fall; int *km_cnt, *km_fpp, *km_flag;
     unsigned* done_cnt;                     // CTAs of the running grid that reached their end (EBUr128 cycle, see the kernel's epilogue)
+    float* hist_alt;                        // tpmax_kernel writes the next block's history here; the host swaps hist / hist_alt
+    unsigned* blk_max;                      // [n_chan] running |v| maximum of the block being processed (float bits), tpmax_kernel
+    unsigned* grp_cnt;                      // [n_chan] finished chunks of the channel group starting at this channel, tpmax_kernel
 };
 
 // The zita table depends only on (hl = 24, np = 4, fr = 1.0), not on the sample rate, so its 120 floats are universal
@@ -288,11 +291,19 @@ B200M_DEV void fir16 (const float (&w)[52], const float* xw, float (&o)[16], con
 #ifndef B200M_TPK_SYM
 #define B200M_TPK_SYM 1
 #endif
-template <bool IMM>
-B200M_DEV void fir16_fma (const float (&w)[52], float (&o)[16])
+B200M_DEV float max3_abs (float a, float b, float c)                 // max (|a|, |b|, |c|), NaN operands ignored like fmaxf
 {
+    float d;
+    asm ("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(fabsf (a)), "f"(fabsf (b)), "f"(fabsf (c)));
+    return d;
+}
+
 #if B200M_TPK_SYM
-    float P[4] = {0.0f, 0.0f, 0.0f, 0.0f}, Q[4] = {0.0f, 0.0f, 0.0f, 0.0f}, R[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+template <bool IMM>
+B200M_DEV void fir_pqr (const float (&w)[52], float (&P)[4], float (&Q)[4], float (&R)[4])
+{
+#pragma unroll
+    for (int r = 0; r < 4; ++r) { P[r] = 0.0f; Q[r] = 0.0f; R[r] = 0.0f; }
 #pragma unroll
     for (int i = 0; i < 24; ++i) {
         const float t1 = IMM ? zita_lit (24 + i) : c_tp_tab[24 + i];
@@ -308,6 +319,27 @@ B200M_DEV void fir16_fma (const float (&w)[52], float (&o)[16])
             R[r] = fmaf (sm, t2, R[r]);
         }
     }
+}
+
+// running maxima of the 4 x `nvalid` outputs without forming phases 1 and 3: max (|ph1|, |ph3|) = (|P| + |Q|) / 2 exactly (one of
+// P + Q, P - Q is the sum of the magnitudes; rounding is sign-symmetric), so `vb` collects |P| + |Q| and the caller halves it once
+template <bool IMM>
+B200M_DEV void fir16_fma_max (const float (&w)[52], int nvalid, float& va, float& vb)
+{
+    float P[4], Q[4], R[4];
+    fir_pqr<IMM> (w, P, Q, R);
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+        if (r < nvalid) { va = max3_abs (va, w[r + 24], R[r]); vb = fmaxf (vb, __fadd_rn (fabsf (P[r]), fabsf (Q[r]))); }
+}
+#endif
+
+template <bool IMM>
+B200M_DEV void fir16_fma (const float (&w)[52], float (&o)[16])
+{
+#if B200M_TPK_SYM
+    float P[4], Q[4], R[4];
+    fir_pqr<IMM> (w, P, Q, R);
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
         o[4 * r] = w[r + 24];
@@ -639,6 +671,163 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     }
 }
 
+// ---- process_max as a grid of independent (channel group x time chunk) CTAs ---------------------------------------------
+// TruePeakdsp::process_max (truepeakdsp.cc:101-124) keeps no serial state besides the running maximum, and the FIR is
+// time-parallel, so one block is cut into [8 channels x 256 samples] items, one CTA each: 4x more CTAs than tpk_kernel<8,256>
+// for a 1024-frame block (8192 for 16384 channels = 5.5 waves of 1480 resident CTAs instead of 1.38: the tail of the last
+// wave costs 8 % instead of 31 %), no chunk loop, no double buffering, one barrier.  A chunk's 48-sample prefix comes from
+// the input itself (chunk 0: from the bank's history); per-chunk maxima meet in blk_max[] with atomicMax on the float bits
+// (all values are >= +0, so unsigned order = float order); the CTA that finishes a channel group last applies
+// `m = _res ? 0 : _m; if (v > m) m = v; _m = m` and, in the EBUr128 cycle, the plugin's read() x 2 + coef_to_db + tp_max hold.
+// The history of the NEXT block goes to the alternate buffer (the group's chunk-0 CTA may still be reading the current one).
+template <bool IMM, bool FMA>
+__global__ void __launch_bounds__ (TPK_THREADS)
+tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int nchunks, int aligned, int elide0,
+              TpkState st, float* __restrict__ dbg, float* __restrict__ r128_tpmax)
+{
+    constexpr int CH = 8, TC = 256;
+    constexpr int XP = 48 + TC + 4;
+    constexpr int GPC = TC / 4, LPR = TPK_THREADS / CH;
+    __shared__ __align__ (16) float xs[CH][XP];
+    __shared__ int s_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int grp = blockIdx.x / nchunks, chunk = blockIdx.x - grp * nchunks;
+    const int c0 = c_first + grp * CH;
+    const int s0 = chunk * TC;
+    const int len = min (TC, nfram - s0);
+
+    // 48-sample prefix: the bank's history for chunk 0, the input itself otherwise (s0 - 48 is a 16-byte multiple)
+    if (chunk == 0) {
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
+            const int r = idx / 48, j = idx % 48;
+            cp_async4 (&xs[r][j], st.hist + (size_t)min (c0 + r, n_chan - 1) * 48 + j, 4);
+        }
+    } else if (aligned) {
+        if (tid < CH * 12) {
+            const int r = tid / 12, c4 = (tid % 12) * 4;
+            cp_async16 (&xs[r][c4], in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 - 48 + c4, 16);
+        }
+    } else {
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
+            const int r = idx / 48, j = idx % 48;
+            cp_async4 (&xs[r][j], in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 - 48 + j, 4);
+        }
+    }
+    if (aligned) {
+#pragma unroll
+        for (int idx = tid; idx < CH * GPC; idx += TPK_THREADS) {
+            const int r = idx / GPC, c4 = (idx % GPC) * 4;
+            const int left = (len - c4) * 4;
+            const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+            cp_async16 (&xs[r][48 + c4], nb ? in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 + c4 : in, nb);
+        }
+    } else {
+        for (int idx = tid; idx < CH * TC; idx += TPK_THREADS) {
+            const int r = idx / TC, cc = idx % TC;
+            const bool ok = cc < len;
+            cp_async4 (&xs[r][48 + cc], ok ? in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 + cc : in, ok ? 4 : 0);
+        }
+    }
+    cp_async_commit ();
+    cp_async_wait<0> ();
+    __syncthreads ();
+
+    const int r = tid / LPR, ql = tid % LPR;
+    float vmax = 0.0f, vmax2 = 0.0f;                        // vmax2: max (|P| + |Q|) = 2 max (|ph1|, |ph3|), tolerance mode
+    {
+        float M = 0.0f;
+        if (elide0) M = row_absmax<LPR, 12 + GPC> (reinterpret_cast<const float4*> (&xs[r][0]), lane);
+        const bool silent_rows = elide0 && __all_sync (0xffffffffu, M == 0.0f);      // every phase of a silent row is +0
+        if (silent_rows) {
+            if (dbg && (c0 + r) < n_chan)
+                for (int q = ql; q < GPC && 4 * q < len; q += LPR) {
+                    float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[i] = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+                }
+        } else
+#pragma unroll 1
+        for (int q = ql; q < GPC; q += LPR) {
+            const bool act = 4 * q < len;
+            bool full0 = !FMA;
+            if (!FMA && elide0) {
+                const float4 xm = *reinterpret_cast<const float4*> (&xs[r][act ? 4 * q + 24 : 0]);
+                full0 = !__all_sync (0xffffffffu, !act || phase0_is_delay (xm, M));
+            }
+            if (act) {
+                float w[52];
+                const float4* xr = reinterpret_cast<const float4*> (&xs[r][4 * q]);
+#pragma unroll
+                for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+#if B200M_TPK_SYM
+                if (FMA && !dbg) { fir16_fma_max<IMM> (w, min (4, len - 4 * q), vmax, vmax2); continue; }      // maxima only (dbg: warp-uniform)
+#endif
+                float o[16];
+                if (FMA) fir16_fma<IMM> (w, o); else fir16<IMM> (w, &xs[r][4 * q], o, full0);
+                if (dbg && (c0 + r) < n_chan) {
+                    float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) d[i] = make_float4 (o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                }
+                // positions beyond len inside the last group come from zero-filled input: exclude them
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (4 * q + i < len)
+                        vmax = fmaxf (fmaxf (vmax, fmaxf (fabsf (o[4 * i]), fabsf (o[4 * i + 1]))), fmaxf (fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3])));
+            }
+        }
+    }
+    vmax = fmaxf (vmax, __fmul_rn (0.5f, vmax2));
+#pragma unroll
+    for (int o = LPR / 2; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));
+    const int ch = c0 + r;
+    if (ql == 0 && ch < n_chan && vmax > 0.0f) atomicMax (st.blk_max + ch, __float_as_uint (vmax));
+
+    // history of the next block = the 48 samples that end this one (the last chunk holds them: prefix + chunk >= 48 samples)
+    if (chunk == nchunks - 1)
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
+            const int rr = idx / 48, j = idx % 48;
+            if (c0 + rr < n_chan) st.hist_alt[(size_t)(c0 + rr) * 48 + j] = xs[rr][len + j];
+        }
+
+    __threadfence ();                                       // this CTA's atomicMax results are visible before its arrival is
+    __syncthreads ();
+    if (tid == 0) s_last = (atomicAdd (st.grp_cnt + c0, 1u) == (unsigned)(nchunks - 1));
+    __syncthreads ();
+    if (s_last && tid < 32) {
+        __threadfence ();
+        const int cc = c0 + lane;
+        const bool own = lane < CH && cc < n_chan;
+        float mm = 0.0f;
+        if (own) {
+            const float bm = __uint_as_float (atomicExch (st.blk_max + cc, 0u));
+            mm = st.tp_res[cc] ? 0.0f : st.tp_m[cc];          // truepeakdsp.cc:108-123
+            if (bm > mm) mm = bm;
+            st.tp_m[cc] = mm;
+        }
+        if (r128_tpmax) {
+            // EBUr128 epilogue (src/ebulv2.cc:227-230,360-367), one lane per stereo instance: read() both meters, coef_to_db, hold
+            const float b = __shfl_xor_sync (0xffffffffu, mm, 1);
+            if (own && (lane & 1) == 0 && cc + 1 < n_chan) {
+                const float v = mm > b ? mm : b;
+                const float tp = (v == 0) ? -INFINITY : __double2float_rn (__dmul_rn (20.0, (double)log10f_glibc (v)));
+                if (tp > r128_tpmax[cc >> 1]) r128_tpmax[cc >> 1] = tp;
+                st.tp_res[cc] = 1; st.tp_res[cc + 1] = 1;
+            }
+        }
+        if (lane == 0) st.grp_cnt[c0] = 0u;
+    }
+    if (r128_tpmax) {
+        // launched with programmatic serialization behind the K-weighting kernel (r128.cu): the grid must not complete before
+        // that one has.  Only the LAST CTA waits (a no-op in a plain launch); see tpk_kernel's epilogue.
+        __syncthreads ();
+        if (tid == 0) {
+            const unsigned prev = atomicAdd (st.done_cnt, 1u);
+            if (prev == gridDim.x - 1) { *st.done_cnt = 0u; asm volatile ("griddepcontrol.wait;" ::: "memory"); }
+        }
+    }
+}
+
 // Tried and dropped (round 1): a warp-specialised pipeline for process() — four FIR warps + a K-meter warp in lock
 // step, the ballistics warp one chunk behind on a double-buffered |out| tile with full/empty named barriers.  It was
 // bit-exact but slower (372 us vs 286 us per 16384 x 1024 block): 48 KB of shared memory and 80 registers x 192 threads
@@ -674,6 +863,7 @@ struct b200m_tpk {
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
     int imm = 0;                            // host table == literal table: use the immediate-coefficient kernels
     int elide0 = 0;                         // phase 0 of the table is the unit-tap delay fir16's guard assumes
+    int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
     int fma = 0;                            // B200M_PREC_FMA: tolerance-mode FIR (fir16_fma); needs the literal table (imm)
     TpkDr dr{}; bool dr_on = false;         // DR-14 accumulation of the next process() call (set by dr14.cu)
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
@@ -729,6 +919,7 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
     prm.fall = powf (10.0f, -0.05f * 15.0f * ((float)(int)nfram / h->fsamp));
     const int aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
     dim3 blk (TPK_THREADS);
+    bool swap_hist = false;
     for (int sl = 0; sl < nsl; ++sl) {
         const int cf = (int)bounds[sl], ce = (int)bounds[sl + 1];
         if (ce <= cf) continue;
@@ -745,12 +936,22 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
             if (h->imm && h->fma) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true, DRM, true>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); \
             else if (h->imm) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); \
             else B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, false, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); } while (0)
-        if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true, false); else TPK_GO (8, 256, true, true, false, false); }
+        if (tp && tp_mode == B200M_TP_MODE_MAX && !km && h->chunked) {
+            // chunk-parallel process_max (tpmax_kernel): stereo pairs of the EBUr128 epilogue need c_first even, which every caller guarantees
+            const int nchunks = ((int)nfram + 255) / 256;
+            cfg.gridDim = dim3 ((unsigned)(((ce - cf + 7) / 8) * nchunks));
+            if (h->imm && h->fma) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpmax_kernel<true, true>, d_in, stride, cf, ce, (int)nfram, nchunks, aligned, h->elide0, h->st, h->d_dbg, r128_tpmax));
+            else if (h->imm) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpmax_kernel<true, false>, d_in, stride, cf, ce, (int)nfram, nchunks, aligned, h->elide0, h->st, h->d_dbg, r128_tpmax));
+            else B200M_CUDA (cudaLaunchKernelEx (&cfg, tpmax_kernel<false, false>, d_in, stride, cf, ce, (int)nfram, nchunks, aligned, h->elide0, h->st, h->d_dbg, r128_tpmax));
+            swap_hist = true;
+        }
+        else if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true, false); else TPK_GO (8, 256, true, true, false, false); }
         else if (tp) { if (km) { if (drp.rms_sum) TPK_GO (16, 64, true, false, true, true); else TPK_GO (16, 64, true, false, true, false); } else TPK_GO (16, 64, true, false, false, false); }
         else tpk_kernel<16, 64, false, false, true, false, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp);
 #undef TPK_GO
         B200M_LAUNCHED (1);
     }
+    if (swap_hist) { float* t = h->st.hist; h->st.hist = h->st.hist_alt; h->st.hist_alt = t; }     // every slice wrote the alternate buffer
     B200M_CUDA (cudaGetLastError ());
     return 0;
 }
@@ -796,6 +997,14 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     if (const char* v = getenv ("B200M_TPK_ELIDE0")) h->elide0 = h->elide0 && atoi (v);      // 0: always evaluate phase 0 (tests, worst-case timing)
     if (const char* v = getenv ("B200M_TPK_PRECISION")) h->fma = (strcmp (v, "fma") == 0) && h->imm && h->ctab[23] == 1.0f;
     cudaError_t e = cudaMemcpyToSymbol (c_tp_tab, h->ctab, sizeof (h->ctab));
+    // the process_max kernels share SMs with the K-weighting kernel in the EBUr128 cycle: same (maximum) carveout, so that the SM
+    // need not be reconfigured between the two
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     auto A = [&] (void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc (p, bytes); if (e == cudaSuccess) e = cudaMemset (*p, 0, bytes); } };
     const size_t n = n_chan;
     A ((void**)&h->st.hist, n * 48 * sizeof (float));
@@ -805,6 +1014,9 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     A ((void**)&h->st.km_fall, n * 4); A ((void**)&h->st.km_cnt, n * 4); A ((void**)&h->st.km_fpp, n * 4); A ((void**)&h->st.km_flag, n * 4);
     A ((void**)&h->d_res, n * sizeof (b200m_tpk_result));
     A ((void**)&h->st.done_cnt, 16);
+    A ((void**)&h->st.hist_alt, n * 48 * sizeof (float));
+    A ((void**)&h->st.blk_max, n * 4); A ((void**)&h->st.grp_cnt, n * 4);
+    if (const char* v = getenv ("B200M_TPK_CHUNKED")) h->chunked = atoi (v) != 0;
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         // constructors: TruePeakdsp _res(true) (:29); Kmeterdsp _flag(false), all zero (kmeterdsp.cc:30-40);
@@ -824,7 +1036,7 @@ int b200m_tpk_destroy (b200m_tpk* h)
     DeviceGuard g (h->device);
     cudaDeviceSynchronize ();
     void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms,
-                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt};
+                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt};
     for (void* p : ps) cudaFree (p);
     h->stage.release ();
     if (h->own) cudaStreamDestroy (h->own);
