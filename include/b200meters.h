@@ -247,6 +247,11 @@ int b200m_cor_destroy (b200m_cor* h);
 int b200m_cor_process_device (b200m_cor* h, const float* d_in, size_t stride, uint32_t nfram, void* stream);
 int b200m_cor_process_host (b200m_cor* h, const float* in, size_t stride, uint32_t nfram);
 int b200m_cor_results (b200m_cor* h, float* out, void* stream);           /* Stcorrdsp::read (:79-82) */
+/* B200M_PREC_EXACT (default): the five recurrences run serially in time, one lane per pair, bit-identical to the reference.
+ * B200M_PREC_FMA: time-parallel evaluation -- the recurrences are linear one-pole filters, so a warp owns ONE pair, its lanes take
+ * consecutive time segments and an affine warp scan stitches them: 32x more parallelism for small banks (2048 pairs are 64 warps
+ * in exact mode); the correlation stays within 1e-5 of the reference (measured ~1e-7). */
+int b200m_cor_set_precision (b200m_cor* h, int mode);
 int b200m_cor_state (b200m_cor* h, float* state5, void* stream);          /* [n][5] zl zr zlr zll zrr */
 int b200m_cor_coeffs (const b200m_cor* h, float w[2]);
 
@@ -318,6 +323,7 @@ int b200m_spec_coeffs (const b200m_spec* h, double* W1080);              /* [30]
  * for both channels plus process_audio (gui/phasewheel.c:1307-1342).
  * ====================================================================================== */
 typedef struct b200m_pw b200m_pw;
+/* fft_bins: the GUI's selector values (gui/phasewheel.c:1108-1116): 64, 128, ... 8192 and 6144 (window = 2 * fft_bins) */
 int b200m_pw_create (b200m_pw** out, int device, uint32_t n_inst, uint32_t fft_bins, double rate);
 int b200m_pw_destroy (b200m_pw* h);
 /* which GUI's process_audio follows the FFTs: PHASEWHEEL (default; phase difference, level, peak: gui/phasewheel.c:1307-1342)
@@ -330,7 +336,14 @@ int b200m_pw_process_device (b200m_pw* h, const float* d_in, size_t stride, uint
 int b200m_pw_process_host (b200m_pw* h, const float* in, size_t stride, uint32_t nfram, float db_thresh, int* fired);
 /* phase[n_inst][fft_bins], level[n_inst][fft_bins], peak[n_inst] (ui->phase/level/peak) */
 int b200m_pw_results (b200m_pw* h, float* phase, float* level, float* peak, void* stream);
+/* ft->power / ft->phase of both channels of the last analysis (gui/fft.c:163-180), kept only while b200m_pw_debug_capture is on */
+int b200m_pw_debug_capture (b200m_pw* h, int enable);
 int b200m_pw_raw (b200m_pw* h, uint32_t inst, float* powL, float* powR, float* phL, float* phR, void* stream);
+/* Fused feed: with a correlation bank of n_inst pairs attached, b200m_pw_process_* also runs Stcorrdsp::process of that bank on the
+ * same block (what xfer_run does per cycle, src/xfer.c:248-251) in ONE kernel that reads the input once: the block is staged in
+ * shared memory for the correlation recurrences and appended to the FFT ring from there.  Read the correlation with
+ * b200m_cor_results; do not call b200m_cor_process_* on an attached bank.  cor = NULL detaches. */
+int b200m_pw_attach_cor (b200m_pw* h, b200m_cor* cor);
 /* device pointers of the result planes, for callers that keep the spectra on the GPU */
 int b200m_pw_device_results (b200m_pw* h, const float** d_phase, const float** d_level, const float** d_peak);
 

@@ -69,6 +69,9 @@ _PROTOS = {
     "b200m_tpk_process_host": (C.c_int, [_v, _v, C.c_size_t, C.c_uint32, C.c_uint32]),
     "b200m_tpk_read_device": (C.c_int, [_v, _v]),
     "b200m_selftest_log10f": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _v, _v]),
+    "b200m_cor_set_precision": (C.c_int, [_v, C.c_int]),
+    "b200m_pw_debug_capture": (C.c_int, [_v, C.c_int]),
+    "b200m_pw_attach_cor": (C.c_int, [_v, _v]),
     "b200m_tpk_set_precision": (C.c_int, [_v, C.c_int]),
     "b200m_tpk_precision": (C.c_int, [_v]),
     "b200m_tpk_results": (C.c_int, [_v, _v, _v]),
@@ -450,6 +453,10 @@ class Stcorrdsp(_Bank):
             assert rows == 2 * self.n_inst
             _ck(lib().b200m_cor_process_device(self.h, p, s, n, _stream_ptr(stream)))
 
+    def set_precision(self, mode):
+        """PREC_EXACT: serial, bit-identical; PREC_FMA: time-parallel warp scan, correlation within 1e-5"""
+        _ck(lib().b200m_cor_set_precision(self.h, int(mode)))
+
     def process_ptr(self, ptr, stride, nfram, stream=None):
         _ck(lib().b200m_cor_process_device(self.h, C.c_void_p(ptr), stride, nfram, _stream_ptr(stream)))
 
@@ -665,6 +672,15 @@ class Phasewheel(_Bank):
         fired = C.c_int(0)
         _ck(lib().b200m_pw_process_device(self.h, C.c_void_p(ptr), stride, nfram, db_thresh, C.byref(fired), _stream_ptr(stream)))
         return fired.value
+
+    def debug_capture(self, enable=True):
+        """keep ft->power / ft->phase of both channels of every analysis (needed by raw())"""
+        _ck(lib().b200m_pw_debug_capture(self.h, int(enable)))
+
+    def attach_cor(self, cor):
+        """fused feed: process*() also runs `cor` (a Stcorrdsp bank of n_inst pairs) on the same block, reading the input once"""
+        _ck(lib().b200m_pw_attach_cor(self.h, cor.h if cor is not None else None))
+        self._cor = cor
 
     def set_mode(self, mode):
         """0: phasewheel process_audio; 1: stereoscope process_audio (read() then returns lr[] as `phase`)"""

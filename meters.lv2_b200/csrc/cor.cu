@@ -6,6 +6,7 @@
 // (separate L and R planes, row pitch 36 floats so that LDS.128 by 32 lanes is conflict free).
 // Operation order is the reference's, without FMA contraction (bit-identical state).
 #include <math.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace b200m {
@@ -14,7 +15,7 @@ constexpr int COR_T = 32, COR_P = COR_T + 4, COR_STAGES = 4;
 
 __global__ void __launch_bounds__ (32)
 cor_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram, int aligned, float w1, float w2,
-            float* __restrict__ st /* [5][n_inst] */, float* __restrict__ res)
+            float* __restrict__ st /* [5][n_inst] */, float* __restrict__ res, float* __restrict__ ring, int N, int rboff)
 {
     __shared__ __align__ (16) float tile[COR_STAGES][2][32 * COR_P];
     const int lane = threadIdx.x;
@@ -70,6 +71,16 @@ cor_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram, 
         const float* pl = tile[t % COR_STAGES][0] + lane * COR_P;
         const float* pr = tile[t % COR_STAGES][1] + lane * COR_P;
         const int len = min (COR_T, nfram - t * COR_T);
+        if (ring && lane < len) {
+            // fused phasewheel feed (b200m_pw_attach_cor): r_buf[(i + n_off) % n_siz] = data[i] (gui/fft.c:302-305) for the 64 rows
+            // of this tile, one 128-byte row segment per store instruction
+            int o = rboff + t * COR_T + lane; if (o >= N) o -= N;
+            const int rows = min (32, n_inst - i0);
+            for (int pr_ = 0; pr_ < rows; ++pr_) {
+                ring[((size_t)(i0 + pr_) * 2 + 0) * N + o] = tile[t % COR_STAGES][0][pr_ * COR_P + lane];
+                ring[((size_t)(i0 + pr_) * 2 + 1) * N + o] = tile[t % COR_STAGES][1][pr_ * COR_P + lane];
+            }
+        }
         int j = 0;
         for (; j + 4 <= len; j += 4) {
             const float4 a = *reinterpret_cast<const float4*> (pl + j);
@@ -92,25 +103,155 @@ cor_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram, 
     }
 }
 
+// ---- time-parallel evaluation (B200M_PREC_FMA) ---------------------------------------------------------------------------
+// Stcorrdsp's recurrences (stcorrdsp.cc:58-62) are one-pole filters, i.e. affine maps of their state:
+//   zl' = (1 - w1) zl + (w1 l + 1e-20),   zlr' = (1 - w2) zlr + w2 (zl' zr')   (zr, zll, zrr alike),
+// and affine maps compose: one warp owns ONE pair, lane j takes frames [32 j, 32 j + 32) of a 1024-frame superchunk,
+//   pass 1: zl, zr over the own segment from a zero state           -> (A, B) with  end = A * start + B,  A = (1 - w1)^count
+//   warp scan (Hillis-Steele on the (A, B) pairs)                    -> the true state at the start of every segment
+//   pass 2: zl, zr again from the true start state, the three product filters from zero, same scan for their block-end state.
+// The per-sample operations are the reference's; only the stitching differs (rounding at the 1e-7 level, contract 1e-5).
+// A bank of 2048 pairs is 2048 warps instead of the 64 of cor_kernel, and 256 pairs per GPU (C5 over eight GPUs) still fill a chip.
+constexpr int CSC_WARPS = 4, CSC_SEG = 32, CSC_SUPER = 32 * CSC_SEG, CSC_PITCH = CSC_SEG + 1;
+
+B200M_DEV void affine_scan (float& A, float& B, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const float Ap = __shfl_up_sync (0xffffffffu, A, d), Bp = __shfl_up_sync (0xffffffffu, B, d);
+        if (lane >= d) { B = fmaf (A, Bp, B); A = A * Ap; }
+    }
+}
+
+__global__ void __launch_bounds__ (CSC_WARPS * 32)
+cor_scan_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram, int aligned, float w1, float w2,
+                 float* __restrict__ st /* [5][n_inst] */, float* __restrict__ res, float* __restrict__ ring, int N, int rboff)
+{
+    __shared__ float sm[CSC_WARPS][2][32 * CSC_PITCH];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int inst = blockIdx.x * CSC_WARPS + warp;
+    if (inst >= n_inst) return;                              // warp-uniform; warps never synchronise with each other
+    float* sl = sm[warp][0]; float* sr = sm[warp][1];
+    const float* gl = in + (size_t)(2 * inst) * stride; const float* gr = gl + stride;
+    float* rl = ring ? ring + (size_t)(2 * inst) * N : nullptr; float* rr = rl ? rl + N : nullptr;
+    const bool ring4 = aligned && (N % 4 == 0) && (rboff % 4 == 0);
+    float zl = st[0 * (size_t)n_inst + inst], zr = st[1 * (size_t)n_inst + inst];
+    float zlr = st[2 * (size_t)n_inst + inst], zll = st[3 * (size_t)n_inst + inst], zrr = st[4 * (size_t)n_inst + inst];
+    const float a1 = 1.0f - w1, a2 = 1.0f - w2;
+
+    for (int s0 = 0; s0 < nfram; s0 += CSC_SUPER) {
+        const int len = min (CSC_SUPER, nfram - s0);
+        __syncwarp ();
+        // stage the superchunk: frame f of the chunk -> slot (f / 32) * 33 + f % 32 (lane j then walks its own 33-float row)
+        if (aligned) {
+#pragma unroll
+            for (int i = 0; i < CSC_SUPER / 128; ++i) {
+                const int f = 4 * (i * 32 + lane);
+                if (f < len) {                                // len - f may be 1..3 on the last group of a ragged block
+                    float4 vl, vr;
+                    if (f + 4 <= len) { vl = *reinterpret_cast<const float4*> (gl + s0 + f); vr = *reinterpret_cast<const float4*> (gr + s0 + f); }
+                    else {
+                        vl = make_float4 (gl[s0 + f], f + 1 < len ? gl[s0 + f + 1] : 0.f, f + 2 < len ? gl[s0 + f + 2] : 0.f, 0.f);
+                        vr = make_float4 (gr[s0 + f], f + 1 < len ? gr[s0 + f + 1] : 0.f, f + 2 < len ? gr[s0 + f + 2] : 0.f, 0.f);
+                    }
+                    const int slot = (f >> 5) * CSC_PITCH + (f & 31);
+                    sl[slot] = vl.x; sl[slot + 1] = vl.y; sl[slot + 2] = vl.z; sl[slot + 3] = vl.w;
+                    sr[slot] = vr.x; sr[slot + 1] = vr.y; sr[slot + 2] = vr.z; sr[slot + 3] = vr.w;
+                    if (rl) {
+                        int o = rboff + s0 + f; o %= N;
+                        if (ring4 && f + 4 <= len) { *reinterpret_cast<float4*> (rl + o) = vl; *reinterpret_cast<float4*> (rr + o) = vr; }
+                        else {
+                            const float al[4] = {vl.x, vl.y, vl.z, vl.w}, ar[4] = {vr.x, vr.y, vr.z, vr.w};
+                            for (int c = 0; c < 4 && f + c < len; ++c) { int oc = o + c; if (oc >= N) oc -= N; rl[oc] = al[c]; rr[oc] = ar[c]; }
+                        }
+                    }
+                }
+            }
+        } else {
+            for (int i = 0; i < CSC_SEG; ++i) {
+                const int f = i * 32 + lane;
+                if (f < len) {
+                    const float vl = gl[s0 + f], vr = gr[s0 + f];
+                    sl[i * CSC_PITCH + lane] = vl; sr[i * CSC_PITCH + lane] = vr;
+                    if (rl) { const int o = (rboff + s0 + f) % N; rl[o] = vl; rr[o] = vr; }
+                }
+            }
+        }
+        __syncwarp ();
+        const int cnt = max (0, min (CSC_SEG, len - lane * CSC_SEG));
+        const float* pl = sl + lane * CSC_PITCH; const float* pr = sr + lane * CSC_PITCH;
+        // pass 1: zl, zr of the own segment from a zero state
+        float A = 1.0f, el = 0.0f, er = 0.0f;
+        for (int i = 0; i < cnt; ++i) {
+            el = __fadd_rn (el, __fadd_rn (__fmul_rn (w1, __fsub_rn (pl[i], el)), 1e-20f));
+            er = __fadd_rn (er, __fadd_rn (__fmul_rn (w1, __fsub_rn (pr[i], er)), 1e-20f));
+            A *= a1;
+        }
+        float Al = A, Ar = A;
+        affine_scan (Al, el, lane); affine_scan (Ar, er, lane);             // (Al, el): composite of segments 0 .. lane
+        const float endl = fmaf (Al, zl, el), endr = fmaf (Ar, zr, er);       // state at the END of this lane's segment
+        float sl0 = __shfl_up_sync (0xffffffffu, endl, 1), sr0 = __shfl_up_sync (0xffffffffu, endr, 1);
+        if (lane == 0) { sl0 = zl; sr0 = zr; }
+        // pass 2: from the true start state; the product filters from zero
+        float xl = sl0, xr = sr0, plr = 0.0f, pll = 0.0f, prr = 0.0f, Bq = 1.0f;
+        for (int i = 0; i < cnt; ++i) {
+            xl = __fadd_rn (xl, __fadd_rn (__fmul_rn (w1, __fsub_rn (pl[i], xl)), 1e-20f));
+            xr = __fadd_rn (xr, __fadd_rn (__fmul_rn (w1, __fsub_rn (pr[i], xr)), 1e-20f));
+            plr = __fadd_rn (plr, __fmul_rn (w2, __fsub_rn (__fmul_rn (xl, xr), plr)));
+            pll = __fadd_rn (pll, __fmul_rn (w2, __fsub_rn (__fmul_rn (xl, xl), pll)));
+            prr = __fadd_rn (prr, __fmul_rn (w2, __fsub_rn (__fmul_rn (xr, xr), prr)));
+            Bq *= a2;
+        }
+        float B1 = Bq, B2 = Bq, B3 = Bq;
+        affine_scan (B1, plr, lane); affine_scan (B2, pll, lane); affine_scan (B3, prr, lane);
+        // block-end state = the composite of all 32 segments (lane 31) applied to the previous state
+        zlr = __shfl_sync (0xffffffffu, fmaf (B1, zlr, plr), 31);
+        zll = __shfl_sync (0xffffffffu, fmaf (B2, zll, pll), 31);
+        zrr = __shfl_sync (0xffffffffu, fmaf (B3, zrr, prr), 31);
+        zl = __shfl_sync (0xffffffffu, endl, 31); zr = __shfl_sync (0xffffffffu, endr, 31);
+    }
+    // end of process(): non-finite scrub, anti-denormal bias on the three products (:65-75)
+    zl = scrub (zl); zr = scrub (zr); zlr = scrub (zlr); zll = scrub (zll); zrr = scrub (zrr);
+    zlr = __fadd_rn (zlr, 1e-10f); zll = __fadd_rn (zll, 1e-10f); zrr = __fadd_rn (zrr, 1e-10f);
+    if (lane == 0) {
+        st[0 * (size_t)n_inst + inst] = zl;  st[1 * (size_t)n_inst + inst] = zr;
+        st[2 * (size_t)n_inst + inst] = zlr; st[3 * (size_t)n_inst + inst] = zll; st[4 * (size_t)n_inst + inst] = zrr;
+        res[inst] = __fdiv_rn (zlr, __fsqrt_rn (__fadd_rn (__fmul_rn (zll, zrr), 1e-10f)));          // Stcorrdsp::read (:79-82)
+    }
+}
+
 }  // namespace b200m
 
 using namespace b200m;
 
 struct b200m_cor {
     int device; uint32_t n_inst; float w1, w2;
+    int scan = 0;                          // B200M_PREC_FMA: time-parallel cor_scan_kernel
     float *d_st = nullptr, *d_res = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 
 static cudaStream_t cor_stream (b200m_cor* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
 
-static int cor_process (b200m_cor* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
+namespace b200m {
+int cor_feed (b200m_cor* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, float* ring, int N, int rboff)
 {
     const int aligned = ((uintptr_t)d_in % 16 == 0) && (stride % 4 == 0);
-    cor_kernel<<<(h->n_inst + 31) / 32, 32, 0, st>>> (d_in, stride, (int)h->n_inst, (int)nfram, aligned, h->w1, h->w2, h->d_st, h->d_res);
+    if (h->scan)
+        cor_scan_kernel<<<(h->n_inst + CSC_WARPS - 1) / CSC_WARPS, CSC_WARPS * 32, 0, st>>> (d_in, stride, (int)h->n_inst, (int)nfram, aligned, h->w1, h->w2,
+                                                                                              h->d_st, h->d_res, ring, N, rboff);
+    else
+        cor_kernel<<<(h->n_inst + 31) / 32, 32, 0, st>>> (d_in, stride, (int)h->n_inst, (int)nfram, aligned, h->w1, h->w2, h->d_st, h->d_res, ring, N, rboff);
     B200M_LAUNCHED (1);
     B200M_CUDA (cudaGetLastError ());
     return 0;
+}
+uint32_t cor_instances (const b200m_cor* h) { return h ? h->n_inst : 0; }
+}
+
+static int cor_process (b200m_cor* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st)
+{
+    return cor_feed (h, d_in, stride, nfram, st, nullptr, 0, 0);
 }
 
 extern "C" {
@@ -174,6 +315,13 @@ int b200m_cor_process_host (b200m_cor* h, const float* in, size_t stride, uint32
                                    (size_t)nfram * sizeof (float), (size_t)2 * h->n_inst, cudaMemcpyHostToDevice, h->own));
     h->last_host = true;
     return cor_process (h, h->stage.d, h->stage.cap, nfram, h->own);
+}
+
+int b200m_cor_set_precision (b200m_cor* h, int mode)
+{
+    if (!h || (mode != B200M_PREC_EXACT && mode != B200M_PREC_FMA)) return set_err (B200M_E_INVAL, "bad argument");
+    h->scan = mode == B200M_PREC_FMA;                       // takes effect with the next process call
+    return 0;
 }
 
 int b200m_cor_results (b200m_cor* h, float* out, void* stream)

@@ -1,17 +1,19 @@
-// pw.cu — phasewheel FFT analysis bank (cuFFT-free radix-4 Stockham kernel).
+// pw.cu — phasewheel / stereoscope FFT analysis bank (cuFFT-free mixed-radix Stockham kernel).
 //
 // Replaces, for N stereo instances, the GUI-side analysis of the phasewheel: fftx_init / fftx_run /
 // ft_analyze (gui/fft.c:208-361, Hann window :69-79,122-161) for the left and right channel plus
-// process_audio (gui/phasewheel.c:1307-1342).  The reference calls FFTW3 (fftwf_plan_r2r_1d R2HC,
-// gui/fft.c:234) which is neither vendored nor pinned; this kernel computes the same DFT
+// process_audio (gui/phasewheel.c:1307-1342; stereoscope: gui/stereoscope.c:705-741).  The reference calls FFTW3
+// (fftwf_plan_r2r_1d R2HC, gui/fft.c:234) which is neither vendored nor pinned; this kernel computes the same DFT
 // (X_k = sum x_n e^{-2 pi i nk/N}) in fp32 with its own algorithm, so parity for this bank is
-// tolerance-based against a double-precision DFT.
+// tolerance-based and pinned against an independent float64 FFT (numpy) in tests/test_pw_gpu.py.
+// Every size the reference GUI offers is provided: fft_bins 64 .. 8192 and 6144 (N = 128 .. 16384 and 12288 = 3 * 4096,
+// gui/phasewheel.c:1108-1116).
 //
 // B200 design: the ring buffers of all instances advance in lock step, so the host tracks the write
-// offset and the 25 Hz analysis clock; one CTA per instance packs z = L + iR, runs ONE complex
-// N-point autosort (Stockham) FFT in shared memory (radix-4 passes, one radix-2 pass when log2 N is
-// odd), splits it into the two real spectra, and writes phase difference / level bins with coalesced
-// stores.
+// offset and the 25 Hz analysis clock; one CTA per instance runs, per channel, an N/2-point complex autosort
+// (Stockham) FFT in shared memory (radix-3 pass when 3 | N, radix-4 passes, one radix-2 pass when needed), splits it
+// into the real spectrum, and writes phase difference / level bins with coalesced stores.  The block append can be
+// fused with the stereo-correlation bank (b200m_pw_attach_cor): the input is then read from HBM once for both meters.
 #include <math.h>
 #include <stdlib.h>
 #include "common.cuh"
@@ -27,97 +29,113 @@ __global__ void pw_append_kernel (const float* __restrict__ in, size_t stride, i
     const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (size_t)rows * nfram) return;
     const int row = (int)(idx / nfram), j = (int)(idx % nfram);
-    ring[(size_t)row * N + ((rboff + j) & (N - 1))] = in[(size_t)row * stride + j];
+    int o = rboff + j; if (o >= N) o -= N;                                    // nfram <= N, rboff < N
+    ring[(size_t)row * N + o] = in[(size_t)row * stride + j];
 }
 
 B200M_DEV float2 cmul (float2 a, float2 b) { return make_float2 (fmaf (a.x, b.x, -a.y * b.y), fmaf (a.x, b.y, a.y * b.x)); }
+B200M_DEV float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
+B200M_DEV float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
 
-// ring: [inst][2][N]; oldest sample sits at offset `start`.  tw[k] = exp(-2 pi i k / N).
+// One autosort (Stockham) pass of radix R over M complex points: n = current sub-transform length, s = M / n its stride.
+// tw[] holds the N = 2M-th roots of unity exp(-2 pi i k / N), so exp(-2 pi i p m / n) = tw[2 p m s].
+template <int R>
+B200M_DEV void stockham_pass (const float2* __restrict__ X, float2* __restrict__ Y, const float2* __restrict__ tw, int M, int n, int s, int tid)
+{
+    const int n1 = n / R;
+    for (int t = tid; t < M / R; t += PW_THREADS) {
+        const int p = t / s, q = t - p * s;
+        float2 a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = X[q + s * (p + j * n1)];
+        float2 y[R];
+        if (R == 2) { y[0] = cadd (a[0], a[1]); y[1] = csub (a[0], a[1]); }
+        else if (R == 3) {
+            const float2 t1 = cadd (a[1], a[2]);
+            const float2 t2 = make_float2 (fmaf (-0.5f, t1.x, a[0].x), fmaf (-0.5f, t1.y, a[0].y));
+            const float2 d = csub (a[1], a[2]);
+            const float2 t3 = make_float2 (0.86602540378443865f * d.y, -0.86602540378443865f * d.x);   // -i sin(pi/3) (a1 - a2)
+            y[0] = cadd (a[0], t1); y[1] = cadd (t2, t3); y[2] = csub (t2, t3);
+        } else {
+            const float2 apc = cadd (a[0], a[2]), amc = csub (a[0], a[2]), bpd = cadd (a[1], a[3]);
+            const float2 jbmd = make_float2 (-(a[1].y - a[3].y), a[1].x - a[3].x);                     // i (b - d)
+            y[0] = cadd (apc, bpd); y[1] = csub (amc, jbmd); y[2] = csub (apc, bpd); y[3] = cadd (amc, jbmd);
+        }
+        Y[q + s * (R * p)] = y[0];
+#pragma unroll
+        for (int m = 1; m < R; ++m) Y[q + s * (R * p + m)] = (p == 0) ? y[m] : cmul (tw[2 * p * m * s], y[m]);
+    }
+}
+
+// ring: [inst][2][N]; the oldest sample sits at offset `start`.  window: N floats.  tw[k] = exp(-2 pi i k / N), k < N.
+// One CTA per instance.  Each channel's N-point real transform is computed as an M = N/2-point complex transform of
+// z[n] = x[2n] + i x[2n+1] followed by the usual split  X[k] = E[k] + W_N^k O[k]  (E, O: transforms of the even / odd samples):
+// half the shared memory of packing L + iR into one N-point transform, which is what lets N = 16384 (gui/phasewheel.c:1116)
+// fit: 2 x M complex ping-pong buffers + the left channel's power / phase = 12 N bytes.
 __global__ void __launch_bounds__ (PW_THREADS)
-pw_analyze_kernel (const float* __restrict__ ring, int N, int log2n, int start, const float* __restrict__ window,
-                   const float2* __restrict__ tw, float db_thresh, float* __restrict__ rawp /* [inst][4][bins] */,
+pw_analyze_kernel (const float* __restrict__ ring, int N, int f3, int f4, int f2, int start, const float* __restrict__ window,
+                   const float2* __restrict__ tw, float db_thresh, float* __restrict__ rawp /* [inst][4][bins] or NULL */,
                    float* __restrict__ phase, float* __restrict__ level, float* __restrict__ peak, int mode)
 {
-    extern __shared__ __align__ (16) float2 sm[];          // two ping-pong buffers of N complex values
+    extern __shared__ __align__ (16) float2 sm[];          // X, Y: M complex each; then powL[bins], phL[bins]
     __shared__ float red[PW_THREADS / 32];
-    float2* X = sm; float2* Y = sm + N;
-    const int inst = blockIdx.x, tid = threadIdx.x, bins = N / 2;
-    const float* rl = ring + (size_t)inst * 2 * N;
-    const float* rr = rl + N;
-    // last N samples in time order, times the window (gui/fft.c:318-333)
-    for (int t = tid; t < N; t += PW_THREADS) {
-        const int src = (start + t) & (N - 1);
-        const float wv = window[t];
-        X[t] = make_float2 (__fmul_rn (rl[src], wv), __fmul_rn (rr[src], wv));
-    }
-    __syncthreads ();
-    // autosort FFT: n = current sub-transform length, s = stride = N / n
-    int n = N, s = 1;
-    int passes4 = log2n / 2;
-    for (int ps = 0; ps < passes4; ++ps) {
-        const int n1 = n >> 2;
-        for (int t = tid; t < (N >> 2); t += PW_THREADS) {
-            const int p = t / s, q = t - p * s;
-            const float2 a = X[q + s * p], b = X[q + s * (p + n1)], c = X[q + s * (p + 2 * n1)], d = X[q + s * (p + 3 * n1)];
-            const float2 apc = make_float2 (a.x + c.x, a.y + c.y), amc = make_float2 (a.x - c.x, a.y - c.y);
-            const float2 bpd = make_float2 (b.x + d.x, b.y + d.y);
-            const float2 jbmd = make_float2 (-(b.y - d.y), b.x - d.x);             // i * (b - d)
-            const float2 w1 = tw[p * s], w2 = tw[2 * p * s], w3 = tw[3 * p * s];
-            Y[q + s * (4 * p)] = make_float2 (apc.x + bpd.x, apc.y + bpd.y);
-            Y[q + s * (4 * p + 1)] = cmul (w1, make_float2 (amc.x - jbmd.x, amc.y - jbmd.y));
-            Y[q + s * (4 * p + 2)] = cmul (w2, make_float2 (apc.x - bpd.x, apc.y - bpd.y));
-            Y[q + s * (4 * p + 3)] = cmul (w3, make_float2 (amc.x + jbmd.x, amc.y + jbmd.y));
-        }
-        __syncthreads ();
-        float2* T = X; X = Y; Y = T;
-        n >>= 2; s <<= 2;
-    }
-    if (log2n & 1) {                                        // final radix-2 pass: n == 2, s == N/2, twiddle 1
-        for (int t = tid; t < (N >> 1); t += PW_THREADS) {
-            const float2 a = X[t], b = X[t + s];
-            Y[t] = make_float2 (a.x + b.x, a.y + b.y);
-            Y[t + s] = make_float2 (a.x - b.x, a.y - b.y);
-        }
-        __syncthreads ();
-        float2* T = X; X = Y; Y = T;
-    }
-    // split Z = FFT(L + iR) into the two half spectra, then ft_analyze (gui/fft.c:163-180) and
-    // process_audio (gui/phasewheel.c:1313-1331)
-    float* pwl = rawp + (size_t)inst * 4 * bins; float* pwr = pwl + bins; float* phl = pwr + bins; float* phr = phl + bins;
+    const int M = N / 2, bins = N / 2;
+    float2* bufA = sm; float2* bufB = sm + M;
+    float* sPL = reinterpret_cast<float*> (sm + 2 * M); float* sFL = sPL + bins;
+    const int inst = blockIdx.x, tid = threadIdx.x;
     float pk = 0.0f;
-    for (int k = tid; k < bins; k += PW_THREADS) {
-        float pl, pr, fl, fr;
-        if (k == 0) {
-            pl = X[0].x * X[0].x; pr = X[0].y * X[0].y; fl = 0.0f; fr = 0.0f;   // power[0] = out[0]^2, phase[0] = 0
-        } else if (k == bins - 1) {
-            pl = pwl[k]; pr = pwr[k]; fl = phl[k]; fr = phr[k];                  // never written by ft_analyze (i < data_size - 1)
-        } else {
-            const float2 zk = X[k], zn = X[N - k];
-            const float lre = 0.5f * (zk.x + zn.x), lim = 0.5f * (zk.y - zn.y);
-            const float rre = 0.5f * (zk.y + zn.y), rim = -0.5f * (zk.x - zn.x);
-            pl = fmaf (lre, lre, lim * lim); pr = fmaf (rre, rre, rim * rim);
-            fl = atan2f (lim, lre); fr = atan2f (rim, rre);
+    for (int ch = 0; ch < 2; ++ch) {
+        const float* rg = ring + ((size_t)inst * 2 + ch) * N;
+        float2* X = bufA; float2* Y = bufB;
+        // last N samples in time order, times the window (gui/fft.c:318-333), packed even / odd
+        for (int t = tid; t < M; t += PW_THREADS) {
+            int s0 = start + 2 * t; if (s0 >= N) s0 -= N;
+            int s1 = s0 + 1; if (s1 >= N) s1 -= N;
+            X[t] = make_float2 (__fmul_rn (rg[s0], window[2 * t]), __fmul_rn (rg[s1], window[2 * t + 1]));
         }
-        pwl[k] = pl; pwr[k] = pr; phl[k] = fl; phr[k] = fr;
-        if (mode == 1 && k >= 1 && k < bins - 1) {
-            // stereoscope process_audio (gui/stereoscope.c:713-739): phase[] holds ui->lr[], both outputs are smoothed state
-            float* lrp = phase + (size_t)inst * bins + k; float* lvp = level + (size_t)inst * bins + k;
-            if (pl < 1e-20f && pr < 1e-20f) { *lrp = 0.5f; *lvp = 0.0f; }
+        __syncthreads ();
+        int n = M, s = 1;
+        for (int i = 0; i < f3; ++i) { stockham_pass<3> (X, Y, tw, M, n, s, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 3; s *= 3; }
+        for (int i = 0; i < f4; ++i) { stockham_pass<4> (X, Y, tw, M, n, s, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 4; s *= 4; }
+        for (int i = 0; i < f2; ++i) { stockham_pass<2> (X, Y, tw, M, n, s, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 2; s *= 2; }
+        // ft_analyze (gui/fft.c:163-180) for this channel, then (right channel) process_audio (gui/phasewheel.c:1313-1331)
+        float* rp = rawp ? rawp + (size_t)inst * 4 * bins : nullptr;
+        for (int k = tid; k < bins; k += PW_THREADS) {
+            float pw_, ph_;
+            if (k == 0) { const float x0 = X[0].x + X[0].y; pw_ = x0 * x0; ph_ = 0.0f; }          // power[0] = out[0]^2, phase[0] = 0
+            else if (k == bins - 1) { pw_ = 0.0f; ph_ = 0.0f; }                                   // never written by ft_analyze (i < data_size - 1): stays as fftx_reset left it
             else {
-                const float lv = pl > pr ? pl : pr;
-                const float dq = __fsub_rn (__fsqrt_rn (pr), __fsqrt_rn (pl));
-                const float lr = __double2float_rn (.5 + __ddiv_rn (__dmul_rn (.5, (double)dq), (double)__fsqrt_rn (lv)));
-                const float l0 = *lvp, r0 = *lrp;
-                *lvp = __double2float_rn ((double)l0 + (__dmul_rn (.1, (double)__fsub_rn (lv, l0)) + 1e-20));
-                *lrp = __double2float_rn ((double)r0 + (__dmul_rn (.1, (double)__fsub_rn (lr, r0)) + 1e-10));
+                const float2 A = X[k], Bm = X[M - k], w = tw[k];
+                const float er = 0.5f * (A.x + Bm.x), ei = 0.5f * (A.y - Bm.y);
+                const float orr = 0.5f * (A.y + Bm.y), oi = -0.5f * (A.x - Bm.x);
+                const float re = er + fmaf (w.x, orr, -w.y * oi), im = ei + fmaf (w.x, oi, w.y * orr);
+                pw_ = fmaf (re, re, im * im); ph_ = atan2f (im, re);
             }
-        } else if (k >= 1 && k < bins - 1) {
-            float ph, lv;
-            if (pl < db_thresh || pr < db_thresh) { ph = 0.0f; lv = -100.0f; }
-            else { ph = __fsub_rn (fr, fl); lv = pl > pr ? pl : pr; if (lv > pk) pk = lv; }   // MAX(a,b) = a > b ? a : b
-            phase[(size_t)inst * bins + k] = ph;
-            level[(size_t)inst * bins + k] = lv;
+            if (rp) { rp[ch * bins + k] = pw_; rp[(2 + ch) * bins + k] = ph_; }
+            if (ch == 0) { sPL[k] = pw_; sFL[k] = ph_; continue; }
+            const float pl = sPL[k], fl = sFL[k], pr = pw_, fr = ph_;
+            if (k < 1 || k >= bins - 1) continue;
+            if (mode == 1) {
+                // stereoscope process_audio (gui/stereoscope.c:713-739): phase[] holds ui->lr[], both outputs are smoothed state
+                float* lrp = phase + (size_t)inst * bins + k; float* lvp = level + (size_t)inst * bins + k;
+                if (pl < 1e-20f && pr < 1e-20f) { *lrp = 0.5f; *lvp = 0.0f; }
+                else {
+                    const float lv = pl > pr ? pl : pr;
+                    const float dq = __fsub_rn (__fsqrt_rn (pr), __fsqrt_rn (pl));
+                    const float lr = __double2float_rn (.5 + __ddiv_rn (__dmul_rn (.5, (double)dq), (double)__fsqrt_rn (lv)));
+                    const float l0 = *lvp, r0 = *lrp;
+                    *lvp = __double2float_rn ((double)l0 + (__dmul_rn (.1, (double)__fsub_rn (lv, l0)) + 1e-20));
+                    *lrp = __double2float_rn ((double)r0 + (__dmul_rn (.1, (double)__fsub_rn (lr, r0)) + 1e-10));
+                }
+            } else {
+                float ph, lv;
+                if (pl < db_thresh || pr < db_thresh) { ph = 0.0f; lv = -100.0f; }
+                else { ph = __fsub_rn (fr, fl); lv = pl > pr ? pl : pr; if (lv > pk) pk = lv; }   // MAX(a,b) = a > b ? a : b
+                phase[(size_t)inst * bins + k] = ph;
+                level[(size_t)inst * bins + k] = lv;
+            }
         }
+        __syncthreads ();                                    // the buffers are reused by the right channel
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) pk = fmaxf (pk, __shfl_xor_sync (0xffffffffu, pk, o));
@@ -140,16 +158,26 @@ __global__ void pw_init_kernel (size_t n, float* level, float* phase, float ph0)
 
 using namespace b200m;
 
+struct b200m_cor;
+namespace b200m {
+// cor.cu: one Stcorrdsp::process block for every pair of the bank; when `ring` is given the block is also appended to the
+// phasewheel ring [pair][2][N] at offset rboff (fused feed: the input is read once)
+int cor_feed (b200m_cor* h, const float* d_in, size_t stride, uint32_t nfram, cudaStream_t st, float* ring, int N, int rboff);
+uint32_t cor_instances (const b200m_cor* h);
+}
+
 struct b200m_pw {
-    int device; uint32_t n_inst, bins, N; int log2n; double rate;
+    int device; uint32_t n_inst, bins, N; int f3, f4, f2; double rate;
     uint32_t rboff, smps, sps, step;                       // shared ring offset + 25 Hz analysis clock (gui/fft.c:43-64)
     int mode = 0;                                          // 0: phasewheel process_audio, 1: stereoscope process_audio
     float *d_ring = nullptr, *d_win = nullptr, *d_raw = nullptr, *d_phase = nullptr, *d_level = nullptr, *d_peak = nullptr;
     float2* d_tw = nullptr;
+    b200m_cor* cor = nullptr;                              // attached correlation bank (fused feed), not owned
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
 };
 
 static cudaStream_t pw_stream (b200m_pw* h, void* stream) { return h->last_host ? h->own : (cudaStream_t)stream; }
+static size_t pw_smem_bytes (uint32_t N) { return (size_t)12 * N; }   // 2 x N/2 float2 + 2 x N/2 float
 
 static int pw_process (b200m_pw* h, const float* d_in, size_t stride, uint32_t nfram, float db_thresh, int* fired, cudaStream_t st)
 {
@@ -165,16 +193,21 @@ static int pw_process (b200m_pw* h, const float* d_in, size_t stride, uint32_t n
     uint32_t done = 0; int step = 0;
     while (done < nfram) {
         const uint32_t n = (nfram - done) < h->N ? (nfram - done) : h->N;
-        const size_t total = (size_t)h->n_inst * 2 * n;
-        pw_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>> (d_in + done, stride, (int)(h->n_inst * 2), (int)n, (int)h->N, (int)h->rboff, h->d_ring);
-        B200M_LAUNCHED (1);
+        if (h->cor) {
+            // fused feed: the correlation kernel stages the block in shared memory anyway and appends it to the ring from there
+            if (int rc = cor_feed (h->cor, d_in + done, stride, n, st, h->d_ring, (int)h->N, (int)h->rboff)) return rc;
+        } else {
+            const size_t total = (size_t)h->n_inst * 2 * n;
+            pw_append_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>> (d_in + done, stride, (int)(h->n_inst * 2), (int)n, (int)h->N, (int)h->rboff, h->d_ring);
+            B200M_LAUNCHED (1);
+        }
         h->rboff = (h->rboff + n) % h->N;
         h->smps += n;
         if (h->smps >= h->sps) {                            // :308-313
             h->step = h->smps; h->smps = 0;
             if (step == last_fire) {
-                pw_analyze_kernel<<<h->n_inst, PW_THREADS, (size_t)2 * h->N * sizeof (float2), st>>> (
-                    h->d_ring, (int)h->N, h->log2n, (int)h->rboff, h->d_win, h->d_tw, db_thresh, h->d_raw, h->d_phase, h->d_level, h->d_peak, h->mode);
+                pw_analyze_kernel<<<h->n_inst, PW_THREADS, pw_smem_bytes (h->N), st>>> (
+                    h->d_ring, (int)h->N, h->f3, h->f4, h->f2, (int)h->rboff, h->d_win, h->d_tw, db_thresh, h->d_raw, h->d_phase, h->d_level, h->d_peak, h->mode);
                 B200M_LAUNCHED (1);
             }
             any = 1;
@@ -193,15 +226,20 @@ int b200m_pw_create (b200m_pw** out, int device, uint32_t n_inst, uint32_t fft_b
     if (!out) return set_err (B200M_E_INVAL, "NULL out pointer");
     *out = nullptr;
     if (n_inst == 0 || !(rate >= 1000.0)) return set_err (B200M_E_INVAL, "bad n_inst/rate");
-    if (fft_bins < 64 || fft_bins > 8192 || (fft_bins & (fft_bins - 1))) return set_err (B200M_E_INVAL, "fft_bins must be a power of two in 64..8192");
-    if (fft_bins > 4096) return set_err (B200M_E_UNSUPPORTED, "fft_bins %u: transforms above 8192 points are not provided", fft_bins);
+    // the sizes of the reference GUI's selector (gui/phasewheel.c:1108-1116): powers of two 64 .. 8192, and 6144
+    if (fft_bins < 64 || fft_bins > 8192 || ((fft_bins & (fft_bins - 1)) && fft_bins != 6144)) return set_err (B200M_E_INVAL, "fft_bins must be a power of two in 64..8192, or 6144");
     if (b200m_device_count () <= 0) return set_err (B200M_E_NODEVICE, "no CUDA device: b200meters has no CPU path");
     DeviceGuard g (device);
     if (!g.ok) return set_err (B200M_E_NODEVICE, "cannot select CUDA device %d", device);
     b200m_pw* h = new (std::nothrow) b200m_pw;
     if (!h) return set_err (B200M_E_NOMEM, "host allocation failed");
     h->device = device; h->n_inst = n_inst; h->bins = fft_bins; h->N = 2 * fft_bins; h->rate = rate;
-    h->log2n = 0; while ((1u << h->log2n) < h->N) ++h->log2n;
+    {   // factor the complex transform length M = N / 2 = fft_bins into radix-3 / radix-4 / radix-2 passes
+        uint32_t m = fft_bins; h->f3 = h->f4 = h->f2 = 0;
+        while (m % 3 == 0) { ++h->f3; m /= 3; }
+        while (m % 4 == 0) { ++h->f4; m /= 4; }
+        while (m % 2 == 0) { ++h->f2; m /= 2; }
+    }
     h->rboff = h->smps = h->step = 0;
     h->sps = (uint32_t)ceil (rate / 25);                    // fftx_init (..., rate, 25): gui/fft.c:219, phasewheel.c:193
     const uint32_t N = h->N;
@@ -220,14 +258,13 @@ int b200m_pw_create (b200m_pw** out, int device, uint32_t n_inst, uint32_t fft_b
     A ((void**)&h->d_ring, (size_t)n_inst * 2 * N * sizeof (float));
     A ((void**)&h->d_win, N * sizeof (float));
     A ((void**)&h->d_tw, N * sizeof (float2));
-    A ((void**)&h->d_raw, (size_t)n_inst * 4 * fft_bins * sizeof (float));
     A ((void**)&h->d_phase, (size_t)n_inst * fft_bins * sizeof (float));
     A ((void**)&h->d_level, (size_t)n_inst * fft_bins * sizeof (float));
     A ((void**)&h->d_peak, n_inst * sizeof (float));
     if (e == cudaSuccess) e = cudaMemcpy (h->d_win, win, N * sizeof (float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy (h->d_tw, tw, N * sizeof (float2), cudaMemcpyHostToDevice);
     free (win); free (tw);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute (pw_analyze_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * 8192 * sizeof (float2)));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (pw_analyze_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pw_smem_bytes (16384));
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         const size_t n = (size_t)n_inst * fft_bins;       // ui->level[i] = -100, ui->phase[i] = 0 (phasewheel.c:199-202)
@@ -301,9 +338,35 @@ int b200m_pw_results (b200m_pw* h, float* phase, float* level, float* peak, void
     return 0;
 }
 
+int b200m_pw_debug_capture (b200m_pw* h, int enable)
+{
+    // the per-channel power / phase planes (ft->power, ft->phase) are intermediate results: 16 bytes per bin and analysis that only
+    // tests read back, so they are written only while capture is on
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    DeviceGuard g (h->device);
+    B200M_CUDA (cudaDeviceSynchronize ());
+    if (enable && !h->d_raw) {
+        B200M_CUDA (cudaMalloc ((void**)&h->d_raw, (size_t)h->n_inst * 4 * h->bins * sizeof (float)));
+        B200M_CUDA (cudaMemset (h->d_raw, 0, (size_t)h->n_inst * 4 * h->bins * sizeof (float)));
+    }
+    if (!enable && h->d_raw) { cudaFree (h->d_raw); h->d_raw = nullptr; }
+    return 0;
+}
+
+int b200m_pw_attach_cor (b200m_pw* h, b200m_cor* cor)
+{
+    if (!h) return set_err (B200M_E_INVAL, "NULL handle");
+    if (cor && cor_instances (cor) != h->n_inst) return set_err (B200M_E_INVAL, "the correlation bank must have as many pairs as the phasewheel bank has instances");
+    DeviceGuard g (h->device);
+    B200M_CUDA (cudaDeviceSynchronize ());
+    h->cor = cor;
+    return 0;
+}
+
 int b200m_pw_raw (b200m_pw* h, uint32_t inst, float* powL, float* powR, float* phL, float* phR, void* stream)
 {
     if (!h || inst >= h->n_inst) return set_err (B200M_E_INVAL, "bad argument");
+    if (!h->d_raw) return set_err (B200M_E_INVAL, "raw spectra are only kept after b200m_pw_debug_capture (h, 1)");
     DeviceGuard g (h->device);
     cudaStream_t st = pw_stream (h, stream);
     float* dst[4] = {powL, powR, phL, phR};

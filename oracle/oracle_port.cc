@@ -528,12 +528,13 @@ struct Sdh {
 // =====================================================================================
 // Phasewheel FFT analysis — gui/fft.c, gui/phasewheel.c (FFTW replaced by a double-precision DFT)
 // =====================================================================================
-void dft_r2c (const float* in, int N, std::vector<std::complex<double>>& X)   // X_k = sum x_n e^{-2 pi i nk/N}
+static void fft_pow2 (std::vector<std::complex<double>>& X)           // in place, iterative radix-2, double precision
 {
-    // iterative radix-2 in double precision: error ~1e-16, i.e. exact at float resolution
-    X.resize (N);
+    const int N = (int)X.size ();
     int lg = 0; while ((1 << lg) < N) ++lg;
-    for (int i = 0; i < N; ++i) { int r = 0; for (int b = 0; b < lg; ++b) if (i & (1 << b)) r |= 1 << (lg - 1 - b); X[r] = in[i]; }
+    std::vector<std::complex<double>> T (N);
+    for (int i = 0; i < N; ++i) { int r = 0; for (int b = 0; b < lg; ++b) if (i & (1 << b)) r |= 1 << (lg - 1 - b); T[r] = X[i]; }
+    X.swap (T);
     for (int len = 2; len <= N; len <<= 1) {
         for (int i = 0; i < N; i += len)
             for (int k = 0; k < len / 2; ++k) {
@@ -541,6 +542,20 @@ void dft_r2c (const float* in, int N, std::vector<std::complex<double>>& X)   //
                 const std::complex<double> w (cos (a), sin (a)), u = X[i + k], v = X[i + k + len / 2] * w;
                 X[i + k] = u + v; X[i + k + len / 2] = u - v;
             }
+    }
+}
+void dft_r2c (const float* in, int N, std::vector<std::complex<double>>& X)   // X_k = sum x_n e^{-2 pi i nk/N}
+{
+    // double precision: error ~1e-16, i.e. exact at float resolution.  N = 2^a, or 3 * 2^a (the GUI's 12288-point window,
+    // gui/phasewheel.c:1115) by decimation in time: X_k = sum_r W_N^{rk} F_r[k mod N/3], F_r = DFT of x[3n + r]
+    if (N % 3) { X.resize (N); for (int i = 0; i < N; ++i) X[i] = in[i]; fft_pow2 (X); return; }
+    const int M = N / 3;
+    std::vector<std::complex<double>> F[3];
+    for (int r = 0; r < 3; ++r) { F[r].resize (M); for (int n = 0; n < M; ++n) F[r][n] = in[3 * n + r]; fft_pow2 (F[r]); }
+    X.resize (N);
+    for (int k = 0; k < N; ++k) {
+        const double a1 = -2.0 * M_PI * k / N;
+        X[k] = F[0][k % M] + std::complex<double> (cos (a1), sin (a1)) * F[1][k % M] + std::complex<double> (cos (2 * a1), sin (2 * a1)) * F[2][k % M];
     }
 }
 struct FftA {                                    // struct FFTAnalysis, gui/fft.c:43-64

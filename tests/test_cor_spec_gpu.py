@@ -105,3 +105,68 @@ def test_spec_nasty_input_host_path():
     z, v, m = g.state(2); oz, ov, om = o.state(2)
     assert np.array_equal(z.view(np.uint64), oz.view(np.uint64))
     assert np.array_equal(u32(g.read()), u32(o.read()))
+
+
+# ------------------------------------------------------------------ Stcorr: time-parallel mode and the fused phasewheel feed
+COR_TOL = 1e-5          # correlation is a ratio in [-1, 1]: the contract's +-1e-4 dB is 1.15e-5 relative
+
+
+@pytest.mark.parametrize("n_inst,blocks", [(70, [1024] * 30), (5, [64] * 10 + [480, 8192, 1, 3, 1023, 33, 2049] * 2), (3, [8192] * 4)])
+def test_cor_scan_mode_within_tolerance(n_inst, blocks):
+    """B200M_PREC_FMA: a warp owns one pair and scans over time (csrc/cor.cu cor_scan_kernel) instead of one lane per pair"""
+    import torch
+    import meters_lv2_b200 as B
+    x = S.white(2 * n_inst, sum(blocks), seed=22)
+    x[2] = x[3]; x[5] = -x[4]
+    g = B.Stcorrdsp(n_inst); g.set_precision(B.PREC_FMA); o = O.Stcorr(n_inst)
+    xd = torch.from_numpy(x).cuda()
+    pos, worst = 0, 0.0
+    for n in blocks:
+        g.process(xd[:, pos:pos + n]); o.process(np.ascontiguousarray(x[:, pos:pos + n]), nthreads=4)
+        pos += n
+        worst = max(worst, float(np.abs(g.read().astype(np.float64) - o.read()).max()))
+    assert worst <= COR_TOL, worst
+    gs, os_ = g.state().astype(np.float64), o.peek().astype(np.float64)
+    assert np.abs(gs - os_).max() <= 2e-6 * np.abs(os_).max()
+    r = g.read()
+    assert r[1] > 0.99 and r[2] < -0.99
+
+
+def test_cor_scan_mode_host_path_unaligned_and_nasty():
+    import meters_lv2_b200 as B
+    x = S.nasty(2 * 9, 1000 * 6 + 1)[:, 1:]                     # rows start 4 bytes off a 16-byte boundary
+    g = B.Stcorrdsp(9); g.set_precision(B.PREC_FMA); o = O.Stcorr(9)
+    for b in range(6):
+        blk = x[:, b * 1000:(b + 1) * 1000]
+        g.process(blk); o.process(np.ascontiguousarray(blk))
+    # NaN / Inf poison a whole segment composite instead of one sample: both end in the per-call scrub (stcorrdsp.cc:65-75)
+    assert np.isfinite(g.read()).all() and np.isfinite(g.state()).all()
+
+
+@pytest.mark.parametrize("prec", ["exact", "scan"])
+@pytest.mark.parametrize("bins,blocks", [(1024, [1024] * 9), (256, [480] * 12 + [8192, 33]), (6144, [8192] * 3)])
+def test_fused_phasewheel_feed(prec, bins, blocks):
+    """b200m_pw_attach_cor: one kernel reads the block once, runs Stcorrdsp and appends to the FFT ring.  The ring, hence every
+    spectrum, is identical to the unfused bank's; the correlation is bit-exact in exact mode and within tolerance in scan mode."""
+    import torch
+    import meters_lv2_b200 as B
+    n_inst = 37
+    x = S.white(2 * n_inst, sum(blocks), seed=24)
+    xd = torch.from_numpy(x).cuda()
+    fused = B.Phasewheel(n_inst, bins); co = B.Stcorrdsp(n_inst); fused.attach_cor(co)
+    if prec == "scan":
+        co.set_precision(B.PREC_FMA)
+    plain = B.Phasewheel(n_inst, bins); oc = O.Stcorr(n_inst)
+    pos = 0
+    for n in blocks:
+        f1 = fused.process(xd[:, pos:pos + n]); f2 = plain.process(xd[:, pos:pos + n])
+        oc.process(np.ascontiguousarray(x[:, pos:pos + n]), nthreads=4)
+        pos += n
+        assert f1 == f2
+        if f1:
+            for a, b in zip(fused.read(), plain.read()):
+                assert np.array_equal(u32(a), u32(b))
+        if prec == "exact":
+            assert np.array_equal(u32(co.read()), u32(oc.read()))
+        else:
+            assert np.abs(co.read().astype(np.float64) - oc.read()).max() <= COR_TOL

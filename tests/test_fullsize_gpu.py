@@ -4,7 +4,7 @@ The other GPU tests use <= 130 instances; these run the banks at the sizes bench
 the 4-slice host path of b200m_r128_run_host, the residue-class gate scheduling over 8192 instances, 32-bit index
 arithmetic at 16384 rows — and compare EVERY instance with oracle/_ref (the reference's own classes):
 
- * C2 + headline: 8192 stereo EBUr128 cycle, 136 blocks of 1024 frames (I and LRA gates live), device path, host path
+ * C2 + headline: 8192 stereo EBUr128 cycle, 480 blocks of 1024 frames (I and LRA gates live), device path, host path
    (b200m_r128_run_host, 4 copy/compute slices) and two half banks (the multi-GPU shard layout): nine floats, dBTP hold and
    every histogram bin of every instance, bit for bit;
  * C3: 8192 stereo TPnRMS (TruePeakdsp::process + Kmeterdsp::process, read every block), bit for bit;
@@ -44,7 +44,7 @@ def _blk_ptr(x, b):
 def test_c2_ebur128_8192_stereo_device_host_and_sharded():
     import torch
     import meters_lv2_b200 as B
-    n_inst, nb = 8192, 136
+    n_inst, nb = 8192, 480   # 480 blocks = 204 fragments: >= 50 M-points (integrated) and >= 20 S-points (LRA)
     x = _ring(2 * n_inst, seed=101)
     x[2 * 4000:2 * 4000 + 2] = 0.0                               # one silent instance (gates never open)
     x[2 * 77] *= 30.0                                            # one hot channel (+5 dB bins clamp, _error counts)
@@ -156,7 +156,7 @@ def test_c5_stcorr_and_phasewheel_2048_stereo():
     x = _ring(2 * n_inst, seed=107)
     xd = torch.from_numpy(x).cuda()
     co = B.Stcorrdsp(n_inst); oc = O.Stcorr(n_inst)
-    pw = B.Phasewheel(n_inst, 1024)
+    pw = B.Phasewheel(n_inst, 1024); pw.debug_capture(True)
     L = O.load("best"); thr = _threads()
     N = 2048
     hist = np.zeros((2 * n_inst, N), np.float32)                # the last N samples per row = what the ring holds

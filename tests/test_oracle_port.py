@@ -160,20 +160,29 @@ def test_dr14_port_equals_reference_plugins(nch, dr_mode, rate, block):
 
 
 @needs_port
-def test_port_phasewheel_against_numpy_fft():
-    """the FFT restatement (FFTW absent => parity unpinned) is at least a correct DFT of the windowed ring."""
-    x = S.white(2, 4096, seed=105)
-    p = O.Phasewheel(1, 1024, kind="port")
-    fired = [p.process(np.ascontiguousarray(x[:, i * 1024:(i + 1) * 1024])) for i in range(4)]
-    assert fired == [0, 1, 0, 1]                          # sps = 1920: every second 1024-block (SURVEY 3.5)
-    N = 2048
-    i = np.arange(N)
-    w = (0.5 - 0.5 * np.cos(2 * np.pi * i / (N - 1))).astype(np.float32)
-    w = (w * (2.0 / w.astype(np.float64).sum())).astype(np.float32)
-    X = np.fft.rfft((x[0, 2048:4096] * w).astype(np.float64))
+@pytest.mark.parametrize("bins", [64, 512, 1024, 4096, 6144, 8192])
+def test_port_phasewheel_against_numpy_fft(bins):
+    """the FFT restatement is pinned to an INDEPENDENT float64 FFT (numpy / pocketfft) for every size the GUI offers
+    (gui/phasewheel.c:1108-1116): powers AND phases, i.e. the half-complex layout and the sign convention of gui/fft.c:163-180."""
+    import _fftref as F
+    N = 2 * bins
+    total = max(3 * N, 6000)
+    x = S.white(2, total, seed=105)
+    x[1, :] = 0.5 * S.sine(total, 48000.0 * 37 / N, phase=0.7)         # a bin-centred tone with a known phase on the right channel
+    p = O.Phasewheel(1, bins, kind="port")
+    pos, fired_end = 0, -1
+    for n in [500] * (total // 500):
+        if p.process(np.ascontiguousarray(x[:, pos:pos + n])):
+            fired_end = pos + n
+        pos += n
+    assert fired_end >= N
+    X, P, PH = F.spectra(x[:, fired_end - N:fired_end])
     powL, powR, phL, phR = p.raw(0)
-    ref = (X.real.astype(np.float32) ** 2 + X.imag.astype(np.float32) ** 2)[1:1023]
-    assert np.allclose(powL[1:1023], ref, rtol=1e-5, atol=1e-12)
+    for ch, (pw, ph) in enumerate(((powL, phL), (powR, phR))):
+        rel, db, dph = F.compare(pw, ph, X[ch])
+        assert rel <= 2e-7 and db <= 1e-5 and dph <= 1e-6, (bins, ch, rel, db, dph)     # double DFT vs double FFT: float32 storage only
+    assert powL[0] == np.float32(X[0, 0].real) ** 2 or abs(powL[0] - X[0, 0].real ** 2) <= 1e-6 * max(1e-30, X[0, 0].real ** 2)
+    assert abs(phR[37] - np.angle(X[1, 37])) < 1e-5
 
 
 @needs_port
