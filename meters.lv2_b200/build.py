@@ -71,6 +71,13 @@ def build(force=False, verbose=False):
         if p.returncode != 0:
             sys.stderr.write(p.stdout + p.stderr)
             raise RuntimeError("link failed")
+    # the plain-C LV2 host used for per-instance throughput measurements (meters.lv2_b200/host/lv2_host.c)
+    hsrc, hbin = os.path.join(HERE, "host", "lv2_host.c"), os.path.join(HERE, "host", "lv2_host")
+    if os.path.exists(hsrc) and (force or _newer(hsrc, hbin)):
+        p = subprocess.run(["gcc", "-O2", "-Wall", "-o", hbin, hsrc, "-ldl", "-lpthread"], capture_output=True, text=True)
+        if p.returncode != 0:
+            sys.stderr.write(p.stdout + p.stderr)
+            raise RuntimeError("gcc failed on %s" % hsrc)
     return LIB
 
 

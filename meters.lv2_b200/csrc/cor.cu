@@ -114,6 +114,17 @@ cor_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram, 
 // A bank of 2048 pairs is 2048 warps instead of the 64 of cor_kernel, and 256 pairs per GPU (C5 over eight GPUs) still fill a chip.
 constexpr int CSC_WARPS = 4, CSC_SEG = 32, CSC_SUPER = 32 * CSC_SEG, CSC_PITCH = CSC_SEG + 1;
 
+// the product filters forget over 1 / w2 = 14400 samples: their composite multiplier (1 - w2)^n is carried in double, because
+// fl (1 - w2) is off by up to 3e-8 and that error would compound to 4e-4 over the filter's memory
+B200M_DEV void affine_scan_d (double& A, double& B, int lane)
+{
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double Ap = __shfl_up_sync (0xffffffffu, A, d), Bp = __shfl_up_sync (0xffffffffu, B, d);
+        if (lane >= d) { B = __fma_rn (A, Bp, B); A = __dmul_rn (A, Ap); }
+    }
+}
+
 B200M_DEV void affine_scan (float& A, float& B, int lane)
 {
 #pragma unroll
@@ -137,7 +148,8 @@ cor_scan_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nf
     const bool ring4 = aligned && (N % 4 == 0) && (rboff % 4 == 0);
     float zl = st[0 * (size_t)n_inst + inst], zr = st[1 * (size_t)n_inst + inst];
     float zlr = st[2 * (size_t)n_inst + inst], zll = st[3 * (size_t)n_inst + inst], zrr = st[4 * (size_t)n_inst + inst];
-    const float a1 = 1.0f - w1, a2 = 1.0f - w2;
+    const float a1 = 1.0f - w1;
+    const double a2 = 1.0 - (double)w2;                      // exact
 
     for (int s0 = 0; s0 < nfram; s0 += CSC_SUPER) {
         const int len = min (CSC_SUPER, nfram - s0);
@@ -193,21 +205,21 @@ cor_scan_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nf
         float sl0 = __shfl_up_sync (0xffffffffu, endl, 1), sr0 = __shfl_up_sync (0xffffffffu, endr, 1);
         if (lane == 0) { sl0 = zl; sr0 = zr; }
         // pass 2: from the true start state; the product filters from zero
-        float xl = sl0, xr = sr0, plr = 0.0f, pll = 0.0f, prr = 0.0f, Bq = 1.0f;
+        float xl = sl0, xr = sr0, plr = 0.0f, pll = 0.0f, prr = 0.0f; double Bq = 1.0;
         for (int i = 0; i < cnt; ++i) {
             xl = __fadd_rn (xl, __fadd_rn (__fmul_rn (w1, __fsub_rn (pl[i], xl)), 1e-20f));
             xr = __fadd_rn (xr, __fadd_rn (__fmul_rn (w1, __fsub_rn (pr[i], xr)), 1e-20f));
             plr = __fadd_rn (plr, __fmul_rn (w2, __fsub_rn (__fmul_rn (xl, xr), plr)));
             pll = __fadd_rn (pll, __fmul_rn (w2, __fsub_rn (__fmul_rn (xl, xl), pll)));
             prr = __fadd_rn (prr, __fmul_rn (w2, __fsub_rn (__fmul_rn (xr, xr), prr)));
-            Bq *= a2;
+            Bq = __dmul_rn (Bq, a2);
         }
-        float B1 = Bq, B2 = Bq, B3 = Bq;
-        affine_scan (B1, plr, lane); affine_scan (B2, pll, lane); affine_scan (B3, prr, lane);
+        double B1 = Bq, B2 = Bq, B3 = Bq, dlr = plr, dll = pll, drr = prr;
+        affine_scan_d (B1, dlr, lane); affine_scan_d (B2, dll, lane); affine_scan_d (B3, drr, lane);
         // block-end state = the composite of all 32 segments (lane 31) applied to the previous state
-        zlr = __shfl_sync (0xffffffffu, fmaf (B1, zlr, plr), 31);
-        zll = __shfl_sync (0xffffffffu, fmaf (B2, zll, pll), 31);
-        zrr = __shfl_sync (0xffffffffu, fmaf (B3, zrr, prr), 31);
+        zlr = __shfl_sync (0xffffffffu, __double2float_rn (__fma_rn (B1, (double)zlr, dlr)), 31);
+        zll = __shfl_sync (0xffffffffu, __double2float_rn (__fma_rn (B2, (double)zll, dll)), 31);
+        zrr = __shfl_sync (0xffffffffu, __double2float_rn (__fma_rn (B3, (double)zrr, drr)), 31);
         zl = __shfl_sync (0xffffffffu, endl, 31); zr = __shfl_sync (0xffffffffu, endr, 31);
     }
     // end of process(): non-finite scrub, anti-denormal bias on the three products (:65-75)

@@ -121,12 +121,14 @@ struct AtomObject {
     const AtomHead* get (LV2_URID key) const
     {
         const uint8_t* body = (const uint8_t*)(a + 1);
-        uint32_t off = 8;                                      // past {id, otype}
-        while (off + 16 <= a->size) {
+        uint64_t off = 8;                                      // past {id, otype}; 64-bit: a hostile size field must not wrap the walk
+        const uint64_t end = a->size;
+        while (off + 16 <= end) {
             const uint32_t* p = (const uint32_t*)(body + off);
             const AtomHead* val = (const AtomHead*)(p + 2);
+            if ((uint64_t)val->size > end - off - 16) return nullptr;      // the value runs past the object: malformed, matches nothing
             if (p[0] == key) return val;
-            off += 8 + atom_pad (8 + val->size);
+            off += 8 + (((uint64_t)8 + val->size + 7u) & ~(uint64_t)7u);
         }
         return nullptr;
     }
@@ -136,11 +138,11 @@ struct AtomObject {
 class AtomEvents {
 public:
     explicit AtomEvents (const void* seq) : seq_ ((const AtomHead*)seq), off_ (8) {}
-    bool valid () const { return seq_ && off_ + 16 <= seq_->size && off_ + 16 + body ()->size <= seq_->size + 0u; }
+    bool valid () const { return seq_ && off_ + 16 <= seq_->size && (uint64_t)body ()->size <= (uint64_t)seq_->size - off_ - 16; }
     const AtomHead* body () const { return (const AtomHead*)((const uint8_t*)(seq_ + 1) + off_ + 8); }
-    void next () { off_ += 8 + atom_pad (8 + body ()->size); }
+    void next () { off_ += 8 + (((uint64_t)8 + body ()->size + 7u) & ~(uint64_t)7u); }      // always advances by >= 16
 private:
-    const AtomHead* seq_; uint32_t off_;
+    const AtomHead* seq_; uint64_t off_;
 };
 
 }  // namespace b200m

@@ -70,7 +70,7 @@ void dr_run (LV2_Handle h, uint32_t n)
             const uint32_t ot = obj.otype ();
             if (ot == p->time_Position) {                      // parse_time_position (:260-280)
                 const AtomHead* speed = obj.get (p->time_speed);
-                if (speed && speed->type == p->atom_Float) {
+                if (speed && speed->type == p->atom_Float && speed->size >= 4) {
                     const float ts = *(const float*)(speed + 1);
                     if (ts != 0 && !p->transport_rolling && follow_host_transport) reset = true;
                     p->transport_rolling = ts != 0;

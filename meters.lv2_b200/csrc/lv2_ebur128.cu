@@ -208,7 +208,7 @@ void integrate (EbuPlugin* p, bool on)                       // ebu_integrate (:
 void on_position (EbuPlugin* p, const AtomObject& obj)       // update_position (:84-113)
 {
     const AtomHead* speed = obj.get (p->u.time_speed);
-    if (!speed || speed->type != p->u.atom_Float) return;
+    if (!speed || speed->type != p->u.atom_Float || speed->size < 4) return;
     const float ts = *(const float*)(speed + 1);
     if (ts != 0 && !p->transport_rolling && (p->follow_transport_mode & 1)) integrate (p, true);
     if (ts == 0 && p->transport_rolling && (p->follow_transport_mode & 1)) integrate (p, false);
@@ -219,7 +219,7 @@ void on_config (EbuPlugin* p, const AtomObject& obj, uint32_t n_samples)      //
 {
     const AtomHead* key = obj.get (p->u.cckey);
     const AtomHead* val = obj.get (p->u.ccval);
-    if (!key || !val) return;                                  // malformed message: key 0, ignored (src/uris.h:309-313)
+    if (!key || !val || key->size < 4 || val->size < 4) return;   // malformed message: key 0, ignored (src/uris.h:309-313)
     const int k = *(const int32_t*)(key + 1);
     const float v = *(const float*)(val + 1);
     switch (k) {

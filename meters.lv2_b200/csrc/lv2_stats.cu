@@ -51,7 +51,7 @@ bool read_cfg (StatsPlugin* p, const AtomObject& obj, int* k, float* v)
 {
     const AtomHead* key = obj.get (p->u.cckey);
     const AtomHead* val = obj.get (p->u.ccval);
-    if (!key || !val) return false;                            // malformed: key 0, ignored (src/uris.h:309-313)
+    if (!key || !val || key->size < 4 || val->size < 4) return false;   // malformed: key 0, ignored (src/uris.h:309-313)
     *k = *(const int32_t*)(key + 1); *v = *(const float*)(val + 1);
     return true;
 }
@@ -75,7 +75,7 @@ void sdh_integrate (StatsPlugin* p, bool on)
 void sdh_position (StatsPlugin* p, const AtomObject& obj)
 {
     const AtomHead* speed = obj.get (p->u.time_speed);
-    if (!speed || speed->type != p->u.atom_Float) return;
+    if (!speed || speed->type != p->u.atom_Float || speed->size < 4) return;
     const float ts = *(const float*)(speed + 1);
     if (ts != 0 && !p->transport_rolling && (p->follow_transport_mode & 1)) sdh_integrate (p, true);
     if (ts == 0 && p->transport_rolling && (p->follow_transport_mode & 1)) sdh_integrate (p, false);

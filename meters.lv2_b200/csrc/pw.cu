@@ -190,11 +190,15 @@ static int pw_process (b200m_pw* h, const float* d_in, size_t stride, uint32_t n
         uint32_t sm = h->smps, d = 0; int step = 0;
         while (d < nfram) { const uint32_t n = (nfram - d) < h->N ? (nfram - d) : h->N; sm += n; if (sm >= h->sps) { sm = 0; last_fire = step; } d += n; ++step; }
     }
+    // fused feed: the correlation kernel stages the block in shared memory anyway and appends it to the ring from there.  A block
+    // longer than the window is walked in window-sized steps below, but Stcorrdsp::process must see it as ONE call (its scrub and
+    // bias act per call, stcorrdsp.cc:65-75): such blocks run the correlation unfused, once, ahead of the steps.
+    const bool fuse = h->cor && nfram <= h->N;
+    if (h->cor && !fuse) { if (int rc = cor_feed (h->cor, d_in, stride, nfram, st, nullptr, 0, 0)) return rc; }
     uint32_t done = 0; int step = 0;
     while (done < nfram) {
         const uint32_t n = (nfram - done) < h->N ? (nfram - done) : h->N;
-        if (h->cor) {
-            // fused feed: the correlation kernel stages the block in shared memory anyway and appends it to the ring from there
+        if (fuse) {
             if (int rc = cor_feed (h->cor, d_in + done, stride, n, st, h->d_ring, (int)h->N, (int)h->rboff)) return rc;
         } else {
             const size_t total = (size_t)h->n_inst * 2 * n;

