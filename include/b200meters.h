@@ -347,6 +347,14 @@ int b200m_pw_attach_cor (b200m_pw* h, b200m_cor* cor);
 /* device pointers of the result planes, for callers that keep the spectra on the GPU */
 int b200m_pw_device_results (b200m_pw* h, const float** d_phase, const float** d_level, const float** d_peak);
 
+/* ======================================================================================
+ * LV2 facade: the library also exports `lv2_descriptor (index)` (the one symbol of the reference's meters.so,
+ * src/meters.cc:739-792) serving all 38 plugin URIs.  b200m_lv2_gon_layout lists, for tests, the offsets of the goniometer
+ * instance struct that the reference GUI reads through instance-access (src/goniometer.h:113-169): rb, ui_active,
+ * rb_overrun, s_sfact, s_linewidth, input, rate, ntfy, msg_thread_lock, map, sizeof; returns how many there are.
+ * ====================================================================================== */
+int b200m_lv2_gon_layout (size_t* out, int n);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

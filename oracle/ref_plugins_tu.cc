@@ -104,4 +104,16 @@ void refebu_snapshot (void* vp, float* out10)
     out10[8] = m->ebu->range_thr (); out10[9] = m->tp_max;
 }
 
+/* goniometer (src/goniometer.h:113-169): offsets of the struct the reference GUI reaches through instance-access -- the same list,
+ * in the same order, as b200m_lv2_gon_layout of the product (csrc/lv2_gon.cu) */
+int refgon_layout (size_t* out, int n)
+{
+    const size_t v[] = {offsetof (LV2gm, rb), offsetof (LV2gm, ui_active), offsetof (LV2gm, rb_overrun), offsetof (LV2gm, s_sfact),
+                        offsetof (LV2gm, s_linewidth), offsetof (LV2gm, input), offsetof (LV2gm, rate), offsetof (LV2gm, ntfy),
+                        offsetof (LV2gm, msg_thread_lock), offsetof (LV2gm, map), sizeof (LV2gm)};
+    const int m = (int)(sizeof (v) / sizeof (v[0]));
+    for (int i = 0; i < n && i < m; ++i) out[i] = v[i];
+    return m;
+}
+
 }  // extern "C"

@@ -56,24 +56,24 @@ def test_argument_errors_are_codes_not_crashes():
 
 
 def test_lv2_descriptor_table_and_instantiate_failures():
-    """the LV2 facade enumerates 37 of the reference's 38 URIs (src/meters.cc:745-792; goniometer excluded) and, like the
-    reference, answers instantiate() with NULL when it cannot run: no urid:map feature for the atom plugins, no GPU for any"""
+    """the LV2 facade enumerates all 38 URIs of the reference (src/meters.cc:745-792) and, like the reference, answers
+    instantiate() with NULL when it cannot run: no urid:map feature for the atom plugins, no GPU for any"""
     import torch
     import meters_lv2_b200 as B
     from test_lv2_shim_gpu import Feature, _feats, descriptors
     d, lib = descriptors(B.LIB_PATH)
     uris = set(d)
-    assert len(uris) == 37 and "goniometer" not in uris
-    for u in ("EBUr128", "dr14stereo", "TPnRMSmono", "SigDistHist", "bitmeter", "phasewheel", "stereoscope", "surround8", "K20stereo", "BBCM6"):
+    assert len(uris) == 38
+    for u in ("EBUr128", "dr14stereo", "TPnRMSmono", "SigDistHist", "bitmeter", "phasewheel", "stereoscope", "surround8", "K20stereo", "BBCM6", "goniometer"):
         assert u in uris, u
     if O.available("reference"):
         r, _ = descriptors(O.PATHS["reference"])
-        assert uris | {"goniometer"} == set(r)
+        assert uris == set(r)
     none = (C.POINTER(Feature) * 1)(None)
-    for u in ("EBUr128", "dr14mono", "SigDistHist", "bitmeter", "phasewheel"):
+    for u in ("EBUr128", "dr14mono", "SigDistHist", "bitmeter", "phasewheel", "goniometer"):
         assert not d[u].contents.instantiate(d[u], 48000.0, b"", none), u           # urid:map missing -> NULL
     if not torch.cuda.is_available():
-        for u in ("EBUr128", "K20stereo", "COR", "spectr30stereo", "surround5"):
+        for u in ("EBUr128", "K20stereo", "COR", "spectr30stereo", "surround5", "goniometer"):
             assert not d[u].contents.instantiate(d[u], 48000.0, b"", _feats), u     # no device, no CPU fallback -> NULL
 
 

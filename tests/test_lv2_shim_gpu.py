@@ -101,9 +101,9 @@ def test_descriptor_table():
     d, _ = descriptors(B.LIB_PATH)
     assert set(d) == {"COR", "spectr30mono", "spectr30stereo", "dBTPmono", "dBTPstereo", "K12mono", "K14mono", "K20mono",
                       "K12stereo", "K14stereo", "K20stereo", "TPnRMSmono", "TPnRMSstereo", "BBCM6", "EBUr128", "SigDistHist", "bitmeter", "dr14mono", "dr14stereo"} | {
-                          k + c for k in ("VU", "BBC", "EBU", "DIN", "NOR") for c in ("mono", "stereo")} | {"surround%d" % k for k in range(3, 9)} | {"phasewheel", "stereoscope"}
+                          k + c for k in ("VU", "BBC", "EBU", "DIN", "NOR") for c in ("mono", "stereo")} | {"surround%d" % k for k in range(3, 9)} | {"phasewheel", "stereoscope", "goniometer"}
     r, _ = descriptors(O.PATHS["reference"])
-    assert set(d) <= set(r) and len(r) == 38          # src/meters.cc:745-792
+    assert set(d) == set(r) and len(r) == 38          # src/meters.cc:745-792
 
 
 def _run_needle_family(name, ctl_ports, nch, script):
@@ -284,3 +284,58 @@ def test_audio_is_forwarded_whatever_the_cycle_length(name, level_port):
     # piecewise metering re-rounds a little (per-call scrubs / n mod 4 tails): the reading stays within the contract's 1e-4 dB
     assert abs(g.lvl[0] - r.lvl[0]) <= 1.2e-5 * abs(r.lvl[0]) + 1e-7, (g.lvl[0], r.lvl[0])
     g.close(); r.close()
+
+
+@pytest.mark.parametrize("name,ports,audio", [
+    ("COR", [0, 3], [(1, 2), (4, 5)]),
+    ("K20stereo", [0, 3, 6, 7, 8, 9], [(1, 2), (4, 5)]),
+    ("dBTPmono", [0, 3, 4, 5], [(1, 2)]),
+    ("VUstereo", [0, 3, 6], [(1, 2), (4, 5)]),
+    ("DINmono", [0, 3], [(1, 2)]),
+    ("spectr30stereo", list(range(64)), [(64, 65), (66, 67)]),
+])
+def test_batched_mode_of_the_control_port_plugins(name, ports, audio, monkeypatch):
+    """B200M_LV2_BATCH: the instances of one plugin type share one bank (csrc/lv2_shim.cu ShimHub).  What an instance's control
+    ports show after cycle k + 1 is bit for bit what the reference plugin shows after cycle k (one declared cycle of latency)."""
+    import meters_lv2_b200 as B
+    monkeypatch.setenv("B200M_LV2_BATCH", "8")
+    n, nb, blk = 5, 30, 1024
+    mine, l1 = descriptors(B.LIB_PATH)
+    ref, l2 = descriptors(O.PATHS["reference"])
+    gs = [Plugin(mine[name]) for _ in range(n)]; rs = [Plugin(ref[name]) for _ in range(n)]
+    x = S.white(2 * n, blk * nb, seed=97)
+    x[2] *= 0.1; x[5] = x[4]
+    spec = name.startswith("spectr30")
+    gp = [{i: np.zeros(1, np.float32) for i in ports} for _ in range(n)]; rp = [{i: np.zeros(1, np.float32) for i in ports} for _ in range(n)]
+    for plugs, pp in ((gs, gp), (rs, rp)):
+        for k, p in enumerate(plugs):
+            for i in ports:
+                p.port(i, pp[k][i])
+            if spec:
+                pp[k][60][0] = 1.0; pp[k][61][0] = -4.0; pp[k][62][0] = 0.0
+            else:
+                pp[k][0][0] = 20.0 if name[0] == "K" or name.startswith("dBTP") else -18.0      # no re-init handshake (|port 0| >= 3)
+    outs = [p for p in ports if p not in (0, 60, 61, 62, 63)]
+    prev = [None] * n
+    checked = 0
+    for b in range(nb):
+        for plugs, pp in ((gs, gp), (rs, rp)):
+            for k, p in enumerate(plugs):
+                bufs = [np.ascontiguousarray(x[2 * k + c, b * blk:(b + 1) * blk]) for c in range(len(audio))]
+                for c, (pi, po) in enumerate(audio):
+                    p.port(pi, bufs[c]); p.port(po, bufs[c])
+                p.run(blk)
+        for k in range(n):
+            now_ref = {i: rp[k][i][0] for i in outs}
+            if prev[k] is not None and b >= 2:
+                for i in outs:
+                    a, r_ = gp[k][i][0], prev[k][i]
+                    if spec and i >= 30 and r_ <= -500:
+                        assert a <= -500                                   # rand()-based "force redraw" values (src/spectrumlv2.c:243-246)
+                    else:
+                        assert u32(np.float32(a))[()] == u32(np.float32(r_))[()], (name, b, k, i, a, r_)
+                checked += 1
+            prev[k] = now_ref
+    assert checked >= n * (nb - 3)
+    for p in gs + rs:
+        p.close()

@@ -84,7 +84,7 @@ def test_fft_pinned_to_numpy_every_size(bins):
     g = B.Phasewheel(n_inst, bins); g.debug_capture(True)
     xd = torch.from_numpy(x).cuda()
     pos, fired_end = 0, -1
-    step = 2048 if N >= 2048 else 512
+    step = min(2048, N)                                                  # blocks no longer than the window: an analysis fires at a block end
     while pos + step <= total:
         if g.process(xd[:, pos:pos + step]):
             fired_end = pos + step
