@@ -93,14 +93,17 @@ typedef struct b200m_ebu_result {          /* getters, ebumeter/ebu_r128_proc.h:
     float   frag_power;                    /* last completed 50 ms fragment power (_power[_wrind-1]) */
 } b200m_ebu_result;
 
-/* Ebu_r128_proc() + init(nchan, fsamp) (:166-173) for n_inst instances.  nchan in {1,2}
- * (the EBUr128 plugin uses 2, src/ebulv2.cc:190); 3..5 -> B200M_E_UNSUPPORTED. */
+/* Ebu_r128_proc() + init(nchan, fsamp) (:166-173) for n_inst instances.  nchan 1..5 (the EBUr128 plugin uses 2, src/ebulv2.cc:190;
+ * 3..5: surround layouts with the channel gains 1 1 1 1.41 1.41 of ebu_r128_proc.cc:29). */
 int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nchan, float fsamp);
 int b200m_ebu_destroy (b200m_ebu* h);
 /* Ebu_r128_proc::reset (:176-190).  All instances share the 50 ms fragment clock, so only
  * inst = -1 (every instance) is accepted. */
 int b200m_ebu_reset (b200m_ebu* h, int32_t inst, void* stream);
 /* integr_start / integr_pause (ebu_r128_proc.h:77-78) / integr_reset (.cc:193-204); inst = -1: all */
+/* one instance back to its state after init(): integration off, filters, ring, loudness values and histograms cleared; the bank's
+ * shared fragment clock keeps running (slot reuse in shared banks) */
+int b200m_ebu_clear (b200m_ebu* h, int32_t inst, void* stream);
 int b200m_ebu_integr_start (b200m_ebu* h, int32_t inst, void* stream);
 int b200m_ebu_integr_pause (b200m_ebu* h, int32_t inst, void* stream);
 int b200m_ebu_integr_reset (b200m_ebu* h, int32_t inst, void* stream);
@@ -165,6 +168,8 @@ int b200m_tpk_read_device (b200m_tpk* h, void* stream);
 int b200m_tpk_results (b200m_tpk* h, b200m_tpk_result* out, void* stream);
 /* TruePeakdsp::reset (:140-145) / Kmeterdsp::reset (kmeterdsp.cc:157-162); chan = -1: all */
 int b200m_tpk_reset (b200m_tpk* h, int32_t chan, void* stream);
+/* reset() plus zero ballistics filters and oversampler history: the channel as a newly constructed meter leaves init(); chan = -1: all */
+int b200m_tpk_clear (b200m_tpk* h, int32_t chan, void* stream);
 /* Kmeterdsp::reset of every channel only (reset_peaks of the TPnRMS / DR14 plugin, src/dr14.c:241-258) */
 int b200m_tpk_reset_kmeter (b200m_tpk* h, void* stream);
 /* host-designed constants: w[4] = w1 w2 w3 g (truepeakdsp.cc:153-157); ctab[120] = zita table
@@ -188,7 +193,7 @@ int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t
  * One host->device copy per block feeds both meters.  Atom/radar/GUI messaging is out of scope.
  * ====================================================================================== */
 typedef struct b200m_r128 b200m_r128;
-enum { B200M_R128_START = 1, B200M_R128_PAUSE = 2, B200M_R128_RESET = 3, B200M_R128_CLEAR_TPMAX = 4 };   /* CTL_START/PAUSE/RESET, src/uris.h:187-203; RESET = ebu_reset
+enum { B200M_R128_START = 1, B200M_R128_PAUSE = 2, B200M_R128_RESET = 3, B200M_R128_CLEAR_TPMAX = 4, B200M_R128_CLEAR = 5 };   /* CLEAR: one slot back to a freshly created instance (inst >= 0) */   /* CTL_START/PAUSE/RESET, src/uris.h:187-203; RESET = ebu_reset
                                                                                 * (src/ebulv2.cc:45-61): integr_reset + tp_max hold cleared;
                                                                                 * CLEAR_TPMAX: the hold alone (a dBTP-disabled cycle, :365-366) */
 int b200m_r128_create (b200m_r128** out, int device, uint32_t n_inst, float fsamp, int dbtp_enable);

@@ -70,6 +70,8 @@ _PROTOS = {
     "b200m_tpk_read_device": (C.c_int, [_v, _v]),
     "b200m_selftest_log10f": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, _v, _v]),
     "b200m_lv2_gon_layout": (C.c_int, [_v, C.c_int]),
+    "b200m_ebu_clear": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_tpk_clear": (C.c_int, [_v, C.c_int32, _v]),
     "b200m_cor_set_precision": (C.c_int, [_v, C.c_int]),
     "b200m_pw_debug_capture": (C.c_int, [_v, C.c_int]),
     "b200m_pw_attach_cor": (C.c_int, [_v, _v]),

@@ -228,7 +228,14 @@ B200M_DEV void kw_warp (Stage& sg, int lane, int k, bool live, int nchans, int n
         z1 = scrub (z1); z2 = scrub (z2); z3 = scrub (z3); z4 = scrub (z4);
         float si;
         if (NCHAN == 1) si = __fmul_rn (2.0f, sj);
-        else si = __fadd_rn (sj, __shfl_xor_sync (0xffffffffu, sj, 1));   // 1.0f*sjL + 1.0f*sjR
+        else if (NCHAN == 2) si = __fadd_rn (sj, __shfl_xor_sync (0xffffffffu, sj, 1));   // 1.0f*sjL + 1.0f*sjR
+        else {
+            // si = sum_i _chan_gain[i] * sj_i in channel order, gains 1 1 1 1.41 1.41 (:29,328-329); the instance's lanes are contiguous
+            const int lead = lane - lane % NCHAN;
+            si = __fmul_rn (1.0f, __shfl_sync (0xffffffffu, sj, lead));
+#pragma unroll
+            for (int c = 1; c < NCHAN; ++c) si = __fadd_rn (si, __fmul_rn (c >= 3 ? 1.41f : 1.0f, __shfl_sync (0xffffffffu, sj, (lead + c) & 31)));
+        }
         fp = __fadd_rn (fp, si);
         if (cfrag) {
             if (live && (k % NCHAN) == 0) fragpw[(size_t)nfr * n_inst + inst] = __fdiv_rn (fp, fragm_f);
@@ -299,12 +306,163 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k
     // true-peak kernel of the EBUr128 cycle, r128.cu) may start as soon as every CTA of this grid is running
     if (pdl_trigger) asm volatile ("griddepcontrol.launch_dependents;");
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int k0 = k_first + (blockIdx.x * EBU_WARPS + warp) * 32;
+    constexpr int CPW = (32 / NCHAN) * NCHAN;          // channels per warp: whole instances only (30 lanes for 3- and 5-channel banks)
+    const int k0 = k_first + (blockIdx.x * EBU_WARPS + warp) * CPW;
     if (k0 >= k_end) return;                           // warp-uniform; warps never synchronise with each other
     PaddedStage<ALIGNED> sg;
     sg.init (in, stride, ebu_smem + warp * EBU_WARP_FLOATS, lane, k0, k_end, nfram);
-    kw_warp<NCHAN> (sg, lane, min (k0 + lane, k_end - 1) /* tail lanes shadow the last channel (no stores) */, (k0 + lane) < k_end,
+    kw_warp<NCHAN> (sg, lane, min (k0 + lane, k_end - 1) /* tail lanes shadow the last channel (no stores) */, lane < CPW && (k0 + lane) < k_end,
                     nchans, nfram, cf, ck, fragm_f, zst, frpwr, fragpw, n_inst);
+}
+
+// ---- K1 split over two warps per 32 channels -------------------------------------------------------------------------------
+// The recurrence is two biquad-like stages in series (:321-322): stage 1  x = p - b1 z1 - b2 z2 + 1e-15  feeds stage 2
+// y = a0 x + a1 z1 + a2 z2 - c3 z3 - c4 z4;  z4 += z3;  z3 += y;  sj += y y.  Each stage is a 16-cycle dependent chain per sample, and
+// one warp per SM sub-partition (all a 16384-channel bank offers) cannot hide either behind the other: 36 cycles per sample measured.
+// Here warp A runs stage 1 and hands the x stream to warp B (same sub-partition: warps w and w + 4 of the CTA) through a
+// double-buffered shared-memory tile; the two chains then interleave on one scheduler.  Every channel sees exactly the same
+// operations in the same order as in kw_warp, so the results stay bit-identical.  Named barriers (bar.arrive / bar.sync on 64
+// threads) hand the tiles over: a waiting warp is parked by the hardware and takes no issue slots from its partner.
+constexpr int EBU_SPLIT_PAIRS = 4;
+constexpr int EBU_SPLIT_PAIR_FLOATS = (EBU_STAGES + 2) * 32 * EBU_ROWP;
+constexpr int EBU_SPLIT_SMEM = EBU_SPLIT_PAIRS * EBU_SPLIT_PAIR_FLOATS * 4;
+
+B200M_DEV void bar_sync64 (int id) { asm volatile ("bar.sync %0, 64;" :: "r"(id) : "memory"); }
+B200M_DEV void bar_arrive64 (int id) { asm volatile ("bar.arrive %0, 64;" :: "r"(id) : "memory"); }
+
+B200M_DEV float kw_stage1 (float p, const EbuCoef& c, float& z1, float& z2)
+{
+    float x = __fsub_rn (p, __fmul_rn (c.b1, z1));
+    x = __fsub_rn (x, __fmul_rn (c.b2, z2));
+    x = __fadd_rn (x, 1e-15f);
+    z2 = z1; z1 = x;
+    return x;
+}
+B200M_DEV void kw_stage2 (float x, const EbuCoef& c, float& z1, float& z2, float& z3, float& z4, float& sj)
+{
+    float y = __fadd_rn (__fmul_rn (c.a0, x), __fmul_rn (c.a1, z1));       // z1, z2: the two x values before this one
+    y = __fadd_rn (y, __fmul_rn (c.a2, z2));
+    y = __fsub_rn (y, __fmul_rn (c.c3, z3));
+    y = __fsub_rn (y, __fmul_rn (c.c4, z4));
+    z2 = z1; z1 = x;
+    z4 = __fadd_rn (z4, z3);
+    z3 = __fadd_rn (z3, y);
+    sj = __fadd_rn (sj, __fmul_rn (y, y));
+}
+
+template <int NCHAN, bool ALIGNED>
+__global__ void __launch_bounds__ (2 * EBU_SPLIT_PAIRS * 32)
+ebu_kweight_split (const float* __restrict__ in, size_t stride, int nchans, int k_first, int k_end, int nfram, EbuCoef cf, EbuChunks ck,
+                   float fragm_f, float* __restrict__ zst, float* __restrict__ frpwr, float* __restrict__ fragpw, int n_inst, int pdl_trigger)
+{
+    extern __shared__ __align__ (16) float ebu_smem[];
+    if (pdl_trigger) asm volatile ("griddepcontrol.launch_dependents;");
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int pair = warp & (EBU_SPLIT_PAIRS - 1), role = warp / EBU_SPLIT_PAIRS;      // warps w and w + 4 share a sub-partition
+    const int k0 = k_first + (blockIdx.x * EBU_SPLIT_PAIRS + pair) * 32;
+    if (k0 >= k_end) return;                           // both warps of the pair leave together
+    float* pair_smem = ebu_smem + pair * EBU_SPLIT_PAIR_FLOATS;
+    float* xt = pair_smem + EBU_STAGES * 32 * EBU_ROWP;   // two x tiles [32][EBU_ROWP]
+    const int id_full = pair * 4, id_empty = pair * 4 + 2;
+    const int k = min (k0 + lane, k_end - 1);
+    const bool live = (k0 + lane) < k_end;
+    const int ntiles = (nfram + EBU_TILE - 1) / EBU_TILE;
+    float z1 = zst[0 * (size_t)nchans + k], z2 = zst[1 * (size_t)nchans + k];
+    int ci = 0;
+    int cend = (int)(ck.v[0] & 0x7fffffffu);
+
+    if (role == 0) {
+        // ---- warp A: stage 1, input tiles by cp.async, x tiles out
+        PaddedStage<ALIGNED> sg;
+        sg.init (in, stride, pair_smem, lane, k0, k_end, nfram);
+        sg.prologue ();
+        for (int t = 0; t < ntiles; ++t) {
+            sg.acquire (t);
+            if (t >= 2) bar_sync64 (id_empty + (t & 1));              // warp B is done with the x tile written two tiles ago
+            float* xrow = xt + (t & 1) * (32 * EBU_ROWP) + lane * EBU_ROWP;
+            int a = t * EBU_TILE;
+            const int b = min (a + EBU_TILE, nfram);
+            if (b - a == EBU_TILE && cend >= b) {
+                float4 cur = sg.ld4 (t, 0);
+#pragma unroll 4
+                for (int q = 0; q < EBU_TILE / 4; ++q) {
+                    const float4 nxt = sg.ld4 (t, (q + 1) & (EBU_TILE / 4 - 1));
+                    float4 o;
+                    o.x = kw_stage1 (cur.x, cf, z1, z2); o.y = kw_stage1 (cur.y, cf, z1, z2);
+                    o.z = kw_stage1 (cur.z, cf, z1, z2); o.w = kw_stage1 (cur.w, cf, z1, z2);
+                    reinterpret_cast<float4*> (xrow)[q] = o;
+                    cur = nxt;
+                }
+                a = b;
+                if (a == cend) { z1 = scrub (z1); z2 = scrub (z2); ++ci; cend = ci < ck.n ? (int)(ck.v[ci] & 0x7fffffffu) : 0x7fffffff; }
+            } else {
+                while (a < b) {
+                    const int e = min (b, cend);
+                    for (int j = a; j < e; ++j) xrow[j - t * EBU_TILE] = kw_stage1 (sg.ld (t, j - t * EBU_TILE), cf, z1, z2);
+                    a = e;
+                    if (a == cend) { z1 = scrub (z1); z2 = scrub (z2); ++ci; cend = ci < ck.n ? (int)(ck.v[ci] & 0x7fffffffu) : 0x7fffffff; }
+                }
+            }
+            bar_arrive64 (id_full + (t & 1));                        // x tile t is complete
+            sg.release (t);
+        }
+        sg.drain ();
+        if (live) { zst[0 * (size_t)nchans + k] = z1; zst[1 * (size_t)nchans + k] = z2; }
+    } else {
+        // ---- warp B: stage 2, power sums, fragment hand-over (the chunk_end of kw_warp)
+        float z3 = zst[2 * (size_t)nchans + k], z4 = zst[3 * (size_t)nchans + k];
+        const int inst = k / NCHAN;
+        float fp = frpwr[inst];
+        float sj = 0.0f;
+        int nfr = 0;
+        bool cfrag = (ck.v[0] >> 31) != 0;
+        auto chunk_end = [&] () {
+            z1 = scrub (z1); z2 = scrub (z2); z3 = scrub (z3); z4 = scrub (z4);
+            float si;
+            if (NCHAN == 1) si = __fmul_rn (2.0f, sj);
+            else si = __fadd_rn (sj, __shfl_xor_sync (0xffffffffu, sj, 1));
+            fp = __fadd_rn (fp, si);
+            if (cfrag) {
+                if (live && (k % NCHAN) == 0) fragpw[(size_t)nfr * n_inst + inst] = __fdiv_rn (fp, fragm_f);
+                fp = 1e-30f;
+                ++nfr;
+            }
+            sj = 0.0f;
+            ++ci;
+            if (ci < ck.n) { cend = (int)(ck.v[ci] & 0x7fffffffu); cfrag = (ck.v[ci] >> 31) != 0; }
+            else cend = 0x7fffffff;
+        };
+        for (int t = 0; t < ntiles; ++t) {
+            bar_sync64 (id_full + (t & 1));
+            const float* xrow = xt + (t & 1) * (32 * EBU_ROWP) + lane * EBU_ROWP;
+            int a = t * EBU_TILE;
+            const int b = min (a + EBU_TILE, nfram);
+            if (b - a == EBU_TILE && cend >= b) {
+                float4 cur = reinterpret_cast<const float4*> (xrow)[0];
+#pragma unroll 4
+                for (int q = 0; q < EBU_TILE / 4; ++q) {
+                    const float4 nxt = reinterpret_cast<const float4*> (xrow)[(q + 1) & (EBU_TILE / 4 - 1)];
+                    kw_stage2 (cur.x, cf, z1, z2, z3, z4, sj); kw_stage2 (cur.y, cf, z1, z2, z3, z4, sj);
+                    kw_stage2 (cur.z, cf, z1, z2, z3, z4, sj); kw_stage2 (cur.w, cf, z1, z2, z3, z4, sj);
+                    cur = nxt;
+                }
+                a = b;
+                if (a == cend) chunk_end ();
+            } else {
+                while (a < b) {
+                    const int e = min (b, cend);
+                    for (int j = a; j < e; ++j) kw_stage2 (xrow[j - t * EBU_TILE], cf, z1, z2, z3, z4, sj);
+                    a = e;
+                    if (a == cend) chunk_end ();
+                }
+            }
+            if (t + 2 < ntiles) bar_arrive64 (id_empty + (t & 1));       // x tile t may be overwritten (by tile t + 2)
+        }
+        if (live) {
+            zst[2 * (size_t)nchans + k] = z3; zst[3 * (size_t)nchans + k] = z4;
+            if ((k % NCHAN) == 0) frpwr[inst] = fp;
+        }
+    }
 }
 
 // the same kernel fed by TMA (16-byte aligned input with a 16-byte multiple row pitch: every bank-sized call in practice)
@@ -604,6 +762,7 @@ struct b200m_ebu {
     int *d_histM = nullptr, *d_histS = nullptr, *d_cnt = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
     bool use_tma = false;                // K1 tiles by TMA (opt-in, 16-byte aligned input only) instead of cp.async
+    bool split = true;                   // K1 as two warps per 32 channels (ebu_kweight_split); B200M_EBU_SPLIT=0: one warp (ebu_kweight_frag)
     // Host mirror of every instance's S-histogram period (_div2, :234-241), kept in O(1) per fragment: an
     // integrating instance has div2 = (G - base) mod 10 where G counts fragments; cnt10[r] = number of integrating
     // instances with base = r.  The gated-statistics kernel (K2b) is launched only for fragments where some
@@ -675,7 +834,6 @@ int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nch
     *out = nullptr;
     if (n_inst == 0 || !(fsamp >= 1000.0f)) return set_err (B200M_E_INVAL, "bad n_inst/fsamp");
     if (nchan < 1 || nchan > 5) return set_err (B200M_E_INVAL, "nchan %u outside 1..5", nchan);
-    if (nchan > 2) return set_err (B200M_E_UNSUPPORTED, "nchan %u: only mono and stereo banks are provided", nchan);
     if (b200m_device_count () <= 0) return set_err (B200M_E_NODEVICE, "no CUDA device: b200meters has no CPU path");
     DeviceGuard g (device);
     if (!g.ok) return set_err (B200M_E_NODEVICE, "cannot select CUDA device %d", device);
@@ -709,6 +867,7 @@ int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nch
 #define EBU_ATTR(NC, AL) if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_frag<NC, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SMEM_BYTES); \
     if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_frag<NC, AL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
     EBU_ATTR (1, true); EBU_ATTR (1, false); EBU_ATTR (2, true); EBU_ATTR (2, false);
+    EBU_ATTR (3, true); EBU_ATTR (3, false); EBU_ATTR (4, true); EBU_ATTR (4, false); EBU_ATTR (5, true); EBU_ATTR (5, false);
 #undef EBU_ATTR
     if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_TMA_SMEM);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_tma<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_TMA_SMEM);
@@ -717,6 +876,11 @@ int b200m_ebu_create (b200m_ebu** out, int device, uint32_t n_inst, uint32_t nch
     // TMA staging is bit-identical and removes ~120 address instructions per tile, but measured no faster standalone (26.0 vs
     // 25.8 us per block) and 3 % slower inside the EBUr128 cycle (the mbarrier try_wait spin takes issue slots from the
     // co-running true-peak kernel, a scoreboard wait does not): opt-in with B200M_EBU_TMA=1
+#define EBU_SATTR(NC, AL) if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_split<NC, AL>, cudaFuncAttributeMaxDynamicSharedMemorySize, EBU_SPLIT_SMEM); \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (ebu_kweight_split<NC, AL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)
+    EBU_SATTR (1, true); EBU_SATTR (1, false); EBU_SATTR (2, true); EBU_SATTR (2, false);
+#undef EBU_SATTR
+    if (const char* v = getenv ("B200M_EBU_SPLIT")) h->split = atoi (v) != 0;
     h->use_tma = false;
     if (const char* v = getenv ("B200M_EBU_TMA")) h->use_tma = atoi (v) != 0 && tma_encoder () != nullptr;
     if (e != cudaSuccess) { int rc = cuda_fail (e, "ebu_create allocations", __FILE__, __LINE__); b200m_ebu_destroy (h); return rc; }
@@ -748,6 +912,19 @@ int b200m_ebu_reset (b200m_ebu* h, int32_t inst, void* stream)
     h->frcnt = h->fragm; h->wrind = 0;
     return ebu_ctl (h, -1, 3, stream);
 }
+int b200m_ebu_clear (b200m_ebu* h, int32_t inst, void* stream)
+{
+    // what reset() does to ONE instance -- integration off, filter states, 64-fragment ring, loudness values, histograms -- without
+    // restarting the bank's shared 50 ms fragment clock
+    if (!h || inst < 0 || inst >= (int32_t)h->n_inst) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    h->phase_ctl (inst, 0); h->phase_ctl (inst, 2);
+    ebu_ctl_kernel<<<(h->n_inst + 127) / 128, 128, 0, h->last_host ? h->own : (cudaStream_t)stream>>> (
+        (int)h->n_inst, inst, 3, (int)h->nchan, h->d_z, h->d_frpwr, h->d_ring, h->d_ctl, h->d_res, h->d_histM, h->d_histS, h->d_cnt);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
 int b200m_ebu_integr_start (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 1, stream); }
 int b200m_ebu_integr_pause (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 0, stream); }
 int b200m_ebu_integr_reset (b200m_ebu* h, int32_t inst, void* stream) { return ebu_ctl (h, inst, 2, stream); }
@@ -776,16 +953,31 @@ int ebu_process_sliced (b200m_ebu* h, const float* d_in, size_t stride, uint32_t
         const float* src = d_in + done;
         const bool al = aligned && (done % 4 == 0);
         CUtensorMap tmap;
-        const bool tma = al && h->use_tma && tma_input_map (&tmap, src, stride, (uint32_t)nch, pos);
+        const bool tma = al && h->use_tma && h->nchan <= 2 && tma_input_map (&tmap, src, stride, (uint32_t)nch, pos);
         for (int sl = 0; sl < nsl; ++sl) {
             const int kf = (int)(bounds[sl] * h->nchan), ke = (int)(bounds[sl + 1] * h->nchan);
             if (ke <= kf) continue;
             if (ready && done == 0) B200M_CUDA (cudaStreamWaitEvent (st, ready[sl], 0));
-            const int nwarps = (ke - kf + 31) / 32;
+            const int cpw = (32 / (int)h->nchan) * (int)h->nchan;          // a warp takes whole instances only
+            const int nwarps = (ke - kf + cpw - 1) / cpw;
             dim3 grid ((nwarps + EBU_WARPS - 1) / EBU_WARPS), blk (EBU_WARPS * 32);
 #define EBU_K1(NC, AL) ebu_kweight_frag<NC, AL><<<grid, blk, EBU_SMEM_BYTES, st>>> (src, stride, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst, (after_k1 && done == 0) ? 1 : 0)
 #define EBU_K1T(NC) ebu_kweight_tma<NC><<<grid, blk, EBU_TMA_SMEM, st>>> (tmap, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst, (after_k1 && done == 0) ? 1 : 0)
-            if (tma) { if (h->nchan == 1) EBU_K1T (1); else EBU_K1T (2); }
+            if (h->nchan > 2) {                                  // surround banks (3..5 channels): the one-warp kernel, lanes grouped per instance
+                switch (h->nchan * 2 + (al ? 1 : 0)) {
+                case 7: EBU_K1 (3, true); break; case 6: EBU_K1 (3, false); break;
+                case 9: EBU_K1 (4, true); break; case 8: EBU_K1 (4, false); break;
+                case 11: EBU_K1 (5, true); break; default: EBU_K1 (5, false); break;
+                }
+            }
+            else if (h->split && !tma) {
+                dim3 sgrid ((nwarps + EBU_SPLIT_PAIRS - 1) / EBU_SPLIT_PAIRS), sblk (2 * EBU_SPLIT_PAIRS * 32);
+#define EBU_K1S(NC, AL) ebu_kweight_split<NC, AL><<<sgrid, sblk, EBU_SPLIT_SMEM, st>>> (src, stride, nch, kf, ke, (int)pos, h->cf, ck, (float)h->fragm, h->d_z, h->d_frpwr, h->d_fragpw, (int)h->n_inst, (after_k1 && done == 0) ? 1 : 0)
+                if (h->nchan == 1) { if (al) EBU_K1S (1, true); else EBU_K1S (1, false); }
+                else               { if (al) EBU_K1S (2, true); else EBU_K1S (2, false); }
+#undef EBU_K1S
+            }
+            else if (tma) { if (h->nchan == 1) EBU_K1T (1); else EBU_K1T (2); }
             else if (h->nchan == 1) { if (al) EBU_K1 (1, true); else EBU_K1 (1, false); }
             else               { if (al) EBU_K1 (2, true); else EBU_K1 (2, false); }
 #undef EBU_K1

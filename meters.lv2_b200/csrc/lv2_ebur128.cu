@@ -89,6 +89,11 @@ void hub_launch (EbuHub* hub)
     bool any_dbtp = false;
     for (EbuPlugin* m : hub->member) if (m && m->dbtp_enable) any_dbtp = true;
     b200m_r128_set_dbtp (hub->bank, any_dbtp);
+    // a forced launch (contract broken, see ebur_run): rows of members that did not submit this cycle still hold their previous
+    // block -- they meter silence rather than the same audio twice
+    if (hub->n_submitted < hub->members)
+        for (uint32_t i = 0; i < hub->slots; ++i)
+            if (hub->member[i] && !hub->submitted[i]) memset (hub->stage + (size_t)2 * i * B200M_MAX_BLOCK, 0, (size_t)2 * B200M_MAX_BLOCK * sizeof (float));
     if (hub->cycle_n && b200m_r128_run_host (hub->bank, hub->stage, B200M_MAX_BLOCK, hub->cycle_n) == 0) hub->inflight = true;
     std::fill (hub->submitted.begin (), hub->submitted.end (), 0);
     hub->n_submitted = 0; hub->cycle_n = 0;
@@ -132,9 +137,11 @@ void hub_leave (EbuPlugin* p)
         hub_fetch (hub);
         if (hub->submitted[p->slot]) { hub->submitted[p->slot] = 0; --hub->n_submitted; }
         hub->member[p->slot] = nullptr; --hub->members;
-        // the slot's next tenant starts from a reset instance and silence
-        b200m_r128_control (hub->bank, p->slot, B200M_R128_PAUSE, nullptr);
-        b200m_r128_control (hub->bank, p->slot, B200M_R128_RESET, nullptr);
+        // the slot's next tenant starts from a freshly created instance and silence: filters, 64-fragment ring, loudness values,
+        // histograms, true-peak history and hold all cleared; only the bank's shared 50 ms fragment phase is inherited
+        b200m_r128_control (hub->bank, p->slot, B200M_R128_CLEAR, nullptr);
+        hub->tp[p->slot] = -INFINITY;
+        { b200m_ebu_result z; memset (&z, 0, sizeof (z)); z.loudness_M = z.maxloudn_M = z.loudness_S = z.maxloudn_S = z.integrated = z.integ_thr = z.range_min = z.range_max = z.range_thr = -200.0f; hub->res[p->slot] = z; }
         memset (hub->stage + (size_t)2 * p->slot * B200M_MAX_BLOCK, 0, (size_t)2 * B200M_MAX_BLOCK * sizeof (float));
         empty = hub->members == 0;
     }
@@ -317,6 +324,14 @@ void ebur_run (LV2_Handle h, uint32_t n_samples)
         send_control (p, CTL_UISETTINGS, (float)p->ui_settings);
     }
 
+    if (p->hub && n_samples >= 1 && n_samples <= B200M_MAX_BLOCK) {
+        // contract broken (this instance already submitted, or the block size changed): close the open cycle as it is BEFORE this
+        // cycle's control messages reach the bank, so that a RESET / START meant for the new cycle does not land ahead of the old audio
+        EbuHub* hub = p->hub;
+        std::lock_guard<std::mutex> lh (hub->mu);
+        hub_fetch (hub);
+        if (hub->submitted[p->slot] || (hub->cycle_n && hub->cycle_n != n_samples)) { hub_launch (hub); hub_fetch (hub); }
+    }
     if (p->control) {                                          // messages from the GUI / host (:258-331)
         for (AtomEvents ev (p->control); ev.valid (); ev.next ()) {
             const AtomHead* a = ev.body ();

@@ -142,6 +142,16 @@ int b200m_r128_control (b200m_r128* h, int32_t inst, int cmd, void* stream)
         B200M_CUDA (cudaGetLastError ());
         return cmd == B200M_R128_RESET ? b200m_ebu_integr_reset (h->ebu, inst, st) : 0;
     }
+    case B200M_R128_CLEAR: {                                // a fresh instance in this slot (shared banks: a plugin left, another may join)
+        if (inst < 0 || inst >= (int32_t)h->n_inst) return set_err (B200M_E_INVAL, "bad instance %d", inst);
+        DeviceGuard g (h->device);
+        r128_fill_kernel<<<1, 32, 0, (cudaStream_t)st>>> (1, h->d_tpmax + inst, -INFINITY);
+        B200M_LAUNCHED (1);
+        B200M_CUDA (cudaGetLastError ());
+        if (int rc = b200m_ebu_clear (h->ebu, inst, st)) return rc;
+        if (int rc = b200m_tpk_clear (h->tpk, 2 * inst, st)) return rc;
+        return b200m_tpk_clear (h->tpk, 2 * inst + 1, st);
+    }
     default: return set_err (B200M_E_INVAL, "unknown control %d", cmd);
     }
 }

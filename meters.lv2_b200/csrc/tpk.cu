@@ -850,6 +850,10 @@ __global__ void tpk_reset_kernel (int n_chan, int sel, uint32_t flags, TpkState 
     if (i >= n_chan || (sel >= 0 && i != sel)) return;
     if (flags & B200M_TPK_TRUEPEAK) { st.tp_res[i] = 1; st.tp_m[i] = 0; st.tp_p[i] = 0; }                 // :140-145
     if (flags & B200M_TPK_KMETER) { st.km_z1[i] = st.km_z2[i] = st.km_rms[i] = st.km_peak[i] = 0; st.km_cnt[i] = 0; st.km_flag[i] = 0; }
+    if (flags & 4u) {                                       // b200m_tpk_clear: a fresh meter -- ballistics state and the oversampler's 48-sample history too
+        st.tp_z1[i] = st.tp_z2[i] = 0.0f;
+        for (int j = 0; j < 48; ++j) { st.hist[(size_t)i * 48 + j] = 0.0f; st.hist_alt[(size_t)i * 48 + j] = 0.0f; }
+    }
 }
 
 }  // namespace b200m
@@ -1100,6 +1104,18 @@ int b200m_tpk_reset (b200m_tpk* h, int32_t chan, void* stream)
     if (!h || chan >= (int32_t)h->n_chan) return set_err (B200M_E_INVAL, "bad argument");
     DeviceGuard g (h->device);
     tpk_reset_kernel<<<(h->n_chan + 127) / 128, 128, 0, tpk_stream (h, stream)>>> ((int)h->n_chan, chan, h->flags, h->st);
+    B200M_LAUNCHED (1);
+    B200M_CUDA (cudaGetLastError ());
+    return 0;
+}
+
+int b200m_tpk_clear (b200m_tpk* h, int32_t chan, void* stream)
+{
+    // reset() plus what a newly constructed meter has: zero ballistics filters and an all-zero resampler history (the state after
+    // TruePeakdsp::init's pre-roll, truepeakdsp.cc:159-168).  For slot reuse in shared banks.
+    if (!h || chan >= (int32_t)h->n_chan) return set_err (B200M_E_INVAL, "bad argument");
+    DeviceGuard g (h->device);
+    tpk_reset_kernel<<<(h->n_chan + 127) / 128, 128, 0, tpk_stream (h, stream)>>> ((int)h->n_chan, chan, h->flags | 4u, h->st);
     B200M_LAUNCHED (1);
     B200M_CUDA (cudaGetLastError ());
     return 0;

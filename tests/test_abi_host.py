@@ -48,7 +48,6 @@ def test_argument_errors_are_codes_not_crashes():
     h = C.c_void_p()
     assert L.b200m_ebu_create(C.byref(h), 0, 0, 2, 48000.0) == -1          # n_inst = 0
     assert L.b200m_ebu_create(C.byref(h), 0, 4, 7, 48000.0) == -1          # nchan outside 1..5
-    assert L.b200m_ebu_create(C.byref(h), 0, 4, 5, 48000.0) == -4          # valid in the reference, unsupported here
     assert L.b200m_pw_create(C.byref(h), 0, 4, 1000, 48000.0) == -1        # not a power of two
     assert L.b200m_ebu_process_device(None, None, 0, 0, None) == -1
     assert b"NULL" in L.b200m_last_error()

@@ -73,10 +73,12 @@ def test_white_noise_bit_exact(n_inst, blocks):
     _assert_equal(g, o, gr, orr, n_inst)
 
 
-def test_tma_staging_is_bit_identical(monkeypatch):
-    """the opt-in TMA staging of the K-weighting kernel (B200M_EBU_TMA=1: 128B-swizzled boxes, mbarrier) produces the same
-    bits as the default cp.async staging, incl. ragged blocks (partial tiles, fragment cuts inside a tile) and a mono bank"""
-    monkeypatch.setenv("B200M_EBU_TMA", "1")
+@pytest.mark.parametrize("env", ["B200M_EBU_TMA=1", "B200M_EBU_SPLIT=0"])
+def test_alternative_k1_kernels_are_bit_identical(monkeypatch, env):
+    """the K-weighting kernel exists in three forms: two warps per 32 channels (default, ebu_kweight_split), one warp with cp.async
+    staging (B200M_EBU_SPLIT=0) and one warp with TMA staging (B200M_EBU_TMA=1: 128B-swizzled boxes, mbarrier).  All produce the
+    same bits, incl. ragged blocks (partial tiles, fragment cuts inside a tile) and a mono bank"""
+    monkeypatch.setenv(*env.split("="))
     blocks = [1024] * 40 + [64] * 30 + [480] * 20 + [8192] * 3 + [4, 8, 1020, 2404, 4800]
     x = S.white(2 * 37, sum(blocks), seed=31)
     g, o, gr, orr = _run_both(x, blocks)
@@ -84,6 +86,19 @@ def test_tma_staging_is_bit_identical(monkeypatch):
     x1 = S.white(40, 1024 * 30, seed=32)
     g, o, gr, orr = _run_both(x1, [1024] * 30, nchan=1)
     _assert_equal(g, o, gr, orr, 40, nchan=1)
+
+
+@pytest.mark.parametrize("nchan", [3, 4, 5])
+def test_surround_banks(nchan):
+    """Ebu_r128_proc::init (nchan = 3..5): channel gains 1 1 1 1.41 1.41 summed in channel order (ebu_r128_proc.cc:29,328-329);
+    instances do not align with warps (30 of 32 lanes busy for 3 and 5 channels), ragged blocks, host path"""
+    n_inst = 45
+    blocks = [1024] * 118 + [480, 4800, 8192, 7, 64, 2401]
+    x = S.white(n_inst * nchan, sum(blocks), seed=40 + nchan)
+    g, o, gr, orr = _run_both(x, blocks, nchan=nchan)
+    _assert_equal(g, o, gr, orr, n_inst, nchan=nchan)
+    g, o, gr, orr = _run_both(x[:, :1000 * 20 + 1][:, 1:], [1000] * 20, nchan=nchan, host=True)       # unaligned rows through the host path
+    _assert_equal(g, o, gr, orr, n_inst, nchan=nchan)
 
 
 def test_mono_bank():
