@@ -323,6 +323,12 @@ ebu_kweight_frag (const float* __restrict__ in, size_t stride, int nchans, int k
 // double-buffered shared-memory tile; the two chains then interleave on one scheduler.  Every channel sees exactly the same
 // operations in the same order as in kw_warp, so the results stay bit-identical.  Named barriers (bar.arrive / bar.sync on 64
 // threads) hand the tiles over: a waiting warp is parked by the hardware and takes no issue slots from its partner.
+// MEASURED (round 2, profiles/r2_ncu_ebu_kweight_split.txt): 27.2 us under ncu against 22.8 us for the one-warp kernel, 28.6 vs 26.2 us
+// live -- slower, so it is opt-in (B200M_EBU_SPLIT=1) and kept for the record.  The premise was wrong: ncu's stall breakdown of
+// the one-warp kernel shows 21.5 issue cycles + 6.5 dependency-wait cycles + 8 other per sample, i.e. the warp is limited by the
+// ~21.5 instructions it must ISSUE per sample on its scheduler, not by the 16-cycle chains; a second warp on the SAME scheduler
+// adds hand-over instructions and barrier waits (0.54 cycles per instruction) without adding issue slots, and every scheduler of
+// the 128 SMs in use already hosts a warp.  Only more channels per scheduler help (0.65 of HBM at 32768 instances).
 constexpr int EBU_SPLIT_PAIRS = 4;
 constexpr int EBU_SPLIT_PAIR_FLOATS = (EBU_STAGES + 2) * 32 * EBU_ROWP;
 constexpr int EBU_SPLIT_SMEM = EBU_SPLIT_PAIRS * EBU_SPLIT_PAIR_FLOATS * 4;
@@ -762,7 +768,7 @@ struct b200m_ebu {
     int *d_histM = nullptr, *d_histS = nullptr, *d_cnt = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
     bool use_tma = false;                // K1 tiles by TMA (opt-in, 16-byte aligned input only) instead of cp.async
-    bool split = true;                   // K1 as two warps per 32 channels (ebu_kweight_split); B200M_EBU_SPLIT=0: one warp (ebu_kweight_frag)
+    bool split = false;                  // K1 as two warps per 32 channels (ebu_kweight_split), opt-in with B200M_EBU_SPLIT=1: measured slower, see the kernel
     // Host mirror of every instance's S-histogram period (_div2, :234-241), kept in O(1) per fragment: an
     // integrating instance has div2 = (G - base) mod 10 where G counts fragments; cnt10[r] = number of integrating
     // instances with base = r.  The gated-statistics kernel (K2b) is launched only for fragments where some

@@ -32,5 +32,10 @@ if which in ("all", "pw"):
     pw = B.Phasewheel(2048, 1024); co = B.Stcorrdsp(2048)
     for i in range(n):
         co.process_ptr(p + 4096 * (i % 4), s, 1024); pw.process_ptr(p + 4096 * (i % 4), s, 1024)
+if which in ("all", "pwf"):
+    # C5 as bench.py runs it: fused feed (Stcorrdsp in its time-parallel mode + FFT ring append) + the 25 Hz analysis
+    pwf = B.Phasewheel(2048, 1024); cof = B.Stcorrdsp(2048); cof.set_precision(B.PREC_FMA); pwf.attach_cor(cof)
+    for i in range(n):
+        pwf.process_ptr(p + 4096 * (i % 4), s, 1024)
 torch.cuda.synchronize()
 print("done", B.launch_count())
