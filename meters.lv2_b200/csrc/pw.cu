@@ -39,12 +39,17 @@ B200M_DEV float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y 
 
 // One autosort (Stockham) pass of radix R over M complex points: n = current sub-transform length, s = M / n its stride.
 // tw[] holds the N = 2M-th roots of unity exp(-2 pi i k / N), so exp(-2 pi i p m / n) = tw[2 p m s].
+// The stride is always s = s3 * 2^sh with s3 in {1, 3} (the radix-3 pass, if any, runs first), so t = p s + q splits with a
+// shift, a mask and at most a division by the constant 3 instead of a run-time integer division.
 template <int R>
-B200M_DEV void stockham_pass (const float2* __restrict__ X, float2* __restrict__ Y, const float2* __restrict__ tw, int M, int n, int s, int tid)
+B200M_DEV void stockham_pass (const float2* __restrict__ X, float2* __restrict__ Y, const float2* __restrict__ tw, int M, int n, int s3, int sh, int tid)
 {
     const int n1 = n / R;
+    const int s = s3 << sh;
     for (int t = tid; t < M / R; t += PW_THREADS) {
-        const int p = t / s, q = t - p * s;
+        int p, q;
+        if (s3 == 1) { p = t >> sh; q = t & ((1 << sh) - 1); }
+        else { const int u = t >> sh; p = u / 3; q = ((u - 3 * p) << sh) | (t & ((1 << sh) - 1)); }
         float2 a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = X[q + s * (p + j * n1)];
@@ -61,9 +66,20 @@ B200M_DEV void stockham_pass (const float2* __restrict__ X, float2* __restrict__
             const float2 jbmd = make_float2 (-(a[1].y - a[3].y), a[1].x - a[3].x);                     // i (b - d)
             y[0] = cadd (apc, bpd); y[1] = csub (amc, jbmd); y[2] = csub (apc, bpd); y[3] = cadd (amc, jbmd);
         }
-        Y[q + s * (R * p)] = y[0];
+        if (p != 0) {
 #pragma unroll
-        for (int m = 1; m < R; ++m) Y[q + s * (R * p + m)] = (p == 0) ? y[m] : cmul (tw[2 * p * m * s], y[m]);
+            for (int m = 1; m < R; ++m) y[m] = cmul (tw[2 * p * m * s], y[m]);
+        }
+        if (R == 4 && s == 1) {
+            // first pass of a power-of-two transform: the four outputs are contiguous -> two 16-byte stores instead of four 8-byte
+            // stores at a 32-byte lane stride (4-way bank conflicts)
+            float4* d = reinterpret_cast<float4*> (Y + 4 * p);
+            d[0] = make_float4 (y[0].x, y[0].y, y[1].x, y[1].y);
+            d[1] = make_float4 (y[2].x, y[2].y, y[3].x, y[3].y);
+        } else {
+#pragma unroll
+            for (int m = 0; m < R; ++m) Y[q + s * (R * p + m)] = y[m];
+        }
     }
 }
 
@@ -94,10 +110,10 @@ pw_analyze_kernel (const float* __restrict__ ring, int N, int f3, int f4, int f2
             X[t] = make_float2 (__fmul_rn (rg[s0], window[2 * t]), __fmul_rn (rg[s1], window[2 * t + 1]));
         }
         __syncthreads ();
-        int n = M, s = 1;
-        for (int i = 0; i < f3; ++i) { stockham_pass<3> (X, Y, tw, M, n, s, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 3; s *= 3; }
-        for (int i = 0; i < f4; ++i) { stockham_pass<4> (X, Y, tw, M, n, s, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 4; s *= 4; }
-        for (int i = 0; i < f2; ++i) { stockham_pass<2> (X, Y, tw, M, n, s, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 2; s *= 2; }
+        int n = M, s3 = 1, sh = 0;                             // stride s = s3 << sh
+        for (int i = 0; i < f3; ++i) { stockham_pass<3> (X, Y, tw, M, n, s3, sh, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 3; s3 *= 3; }
+        for (int i = 0; i < f4; ++i) { stockham_pass<4> (X, Y, tw, M, n, s3, sh, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 4; sh += 2; }
+        for (int i = 0; i < f2; ++i) { stockham_pass<2> (X, Y, tw, M, n, s3, sh, tid); __syncthreads (); float2* T = X; X = Y; Y = T; n /= 2; sh += 1; }
         // ft_analyze (gui/fft.c:163-180) for this channel, then (right channel) process_audio (gui/phasewheel.c:1313-1331)
         float* rp = rawp ? rawp + (size_t)inst * 4 * bins : nullptr;
         for (int k = tid; k < bins; k += PW_THREADS) {
@@ -109,7 +125,8 @@ pw_analyze_kernel (const float* __restrict__ ring, int N, int f3, int f4, int f2
                 const float er = 0.5f * (A.x + Bm.x), ei = 0.5f * (A.y - Bm.y);
                 const float orr = 0.5f * (A.y + Bm.y), oi = -0.5f * (A.x - Bm.x);
                 const float re = er + fmaf (w.x, orr, -w.y * oi), im = ei + fmaf (w.x, oi, w.y * orr);
-                pw_ = fmaf (re, re, im * im); ph_ = atan2f (im, re);
+                pw_ = fmaf (re, re, im * im);
+                ph_ = (mode == 0 || rp) ? atan2f (im, re) : 0.0f;            // the stereoscope's process_audio never reads ft->phase
             }
             if (rp) { rp[ch * bins + k] = pw_; rp[(2 + ch) * bins + k] = ph_; }
             if (ch == 0) { sPL[k] = pw_; sFL[k] = ph_; continue; }
