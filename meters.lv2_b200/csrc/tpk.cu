@@ -377,21 +377,34 @@ B200M_DEV void fir16_fma (const float (&w)[52], float (&o)[16])
 // 16 channels x {z1 filter, z2 filter} = 32 busy lanes (the two one-pole attack filters are independent until
 // the per-sample m = max (m, z1 + z2), which costs one shuffle), so the serial part issues ~1/4 of the
 // instructions it would with one channel per lane.
+// shared-memory geometry of tpk_kernel.  Row pitch of the x tile: lanes of a quarter warp that read 16-byte groups of DIFFERENT rows
+// must land in different banks; with LPR = 128 / CH lanes per row that needs a pitch of 4 * LPR mod 32 floats when LPR < 8.
+template <int CH, int TC, bool BAL>
+struct TpkGeom {
+    static constexpr int XP = (CH == 64) ? (48 + TC + 4 + 31) / 32 * 32 + 8 : 48 + TC + 4;
+    static constexpr int OP = 4 * TC + 4;
+    static constexpr size_t BYTES = (size_t)(2 * CH * XP + (BAL ? CH * OP : 4)) * sizeof (float);
+};
+
 template <int CH, int TC, bool TP, bool TPMAX, bool KM, bool IMM, bool DR, bool FMA = false>
 __global__ void __launch_bounds__ (TPK_THREADS)
 tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, int elide0, TpkParams prm,
             TpkState st, float* __restrict__ dbg, float* __restrict__ r128_tpmax, TpkDr dr)
 {
     // processes channels [c_first, n_chan): `n_chan` is the END of the slice (absolute channel index)
-    constexpr int XP = 48 + TC + 4;               // x row pitch (floats): 16-byte multiple
+    constexpr int XP = TpkGeom<CH, TC, TP && !TPMAX>::XP;   // x row pitch (floats): 16-byte multiple
     constexpr int OP = 4 * TC + 4;                // |out| row pitch
     constexpr int GPC = TC / 4;                   // 4-sample groups per channel per chunk
     constexpr bool BAL = TP && !TPMAX;
-    static_assert (!BAL || CH == 16, "split ballistics lanes assume 16 channels per CTA");
+    // ballistics lanes come in groups of 16 channels x 2 filters = one warp: a 16-channel CTA has one such warp (the other three do the
+    // K-meter / DR roles or idle during the serial phase), a 64-channel CTA ("wide") keeps ALL four warps busy in the serial phase
+    static_assert (!BAL || CH == 16 || CH == 64, "split ballistics lanes assume 16 channels per warp");
+    constexpr bool ALLW = BAL && CH == 64;
     constexpr int LPR = TPK_THREADS / CH;         // lanes that share one channel row in the FIR phase (an aligned lane group)
-    static_assert (CH <= 32 && TPK_THREADS % CH == 0 && LPR <= 32 && GPC % LPR == 0, "tile geometry");
-    __shared__ __align__ (16) float xs[2][CH][XP];
-    __shared__ __align__ (16) float ob[BAL ? CH : 1][BAL ? OP : 4];
+    static_assert (CH <= 64 && TPK_THREADS % CH == 0 && LPR <= 32 && GPC % LPR == 0, "tile geometry");
+    extern __shared__ __align__ (16) float tpk_smem[];        // xs[2][CH][XP], then ob[BAL ? CH : 1][BAL ? OP : 4]
+    float (*xs)[CH][XP] = reinterpret_cast<float (*)[CH][XP]> (tpk_smem);
+    float (*ob)[BAL ? OP : 4] = reinterpret_cast<float (*)[BAL ? OP : 4]> (tpk_smem + 2 * CH * XP);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c0 = c_first + blockIdx.x * CH;
     const int nchunks = (nfram + TC - 1) / TC;
@@ -431,11 +444,13 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     // the serial roles rotate over the CTA's warps with blockIdx: warp w of every CTA lives on SM sub-partition w % 4, so a
     // fixed role assignment would pile all ballistics work (18 % of the instructions) onto sub-partition 0
     const int wrole = (warp + blockIdx.x) & 3;
-    const bool is_tp = BAL && wrole == 0;
+    const int wbase = ALLW ? 16 * warp : 0;               // wide CTA: warp w serves channels 16 w .. 16 w + 15 in every serial role
+    const bool is_tp = BAL && (ALLW || wrole == 0);
     const int tch = lane & 15, filt = lane >> 4;
-    const bool is_km = KM && wrole == 1 && lane < CH;
-    const int chs = min (c0 + (is_tp ? tch : lane), n_chan - 1);
-    const bool live = (c0 + (is_tp ? tch : lane)) < n_chan;
+    const bool is_km = KM && (ALLW ? lane < 16 : (wrole == 1 && lane < CH));
+    const int srow = wbase + (is_tp ? tch : lane);         // tile row of this lane's serial channel
+    const int chs = min (c0 + srow, n_chan - 1);
+    const bool live = (c0 + srow) < n_chan;
     float z = 0, m = 0, p = 0, wf = 0; int res = 0;
     float kz1 = 0, kz2 = 0, kt = 0;
     if (is_tp) {
@@ -452,9 +467,10 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
         kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
     }
     // role 2 (idle otherwise while the serial lanes run): DR-14 sums, lane = channel
-    const bool dr_warp = DR && BAL && KM && dr.rms_sum != nullptr && wrole == 2;
-    const int dch = min (c0 + (lane & (CH - 1)), n_chan - 1);
-    const bool dr_live = dr_warp && lane < CH && (c0 + lane) < n_chan;
+    const bool dr_warp = DR && BAL && KM && dr.rms_sum != nullptr && (ALLW || wrole == 2);
+    const int drow = wbase + (lane & 15);
+    const int dch = min (c0 + drow, n_chan - 1);
+    const bool dr_live = dr_warp && lane < 16 && (c0 + drow) < n_chan;
     float drs = 0, drp = 0;
     if (dr_warp) { drs = dr.rms_sum[dch]; drp = dr.peak_cur[dch]; }
     float vmax = 0.0f;                                                    // process_max: plain running max (:109-122), per FIR lane
@@ -542,7 +558,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
         if (is_tp) {
             // PPM ballistics over the 4*len oversampled magnitudes (truepeakdsp.cc:57-84); this lane owns one of the
             // two attack filters of channel tch
-            const float4* b4 = reinterpret_cast<const float4*> (&ob[BAL ? tch : 0][0]);
+            const float4* b4 = reinterpret_cast<const float4*> (&ob[BAL ? wbase + tch : 0][0]);
             for (int j = 0; j < len; ++j) {
                 const float4 v4 = b4[(j & 3) * GPC + (j >> 2)];
                 z = __fmul_rn (z, prm.w3);
@@ -560,7 +576,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
         if (is_km) {
             // kmeterdsp.cc:80-97: z1 every sample, z2 every 4th; the block's last n%4 samples are ignored
             const int e = min (len, km_n - s0);
-            const float4* x4 = reinterpret_cast<const float4*> (&xs[buf][lane][48]);
+            const float4* x4 = reinterpret_cast<const float4*> (&xs[buf][wbase + lane][48]);
             const float om4 = __fmul_rn (4.0f, prm.omega);
             for (int j = 0; j + 4 <= e; j += 4) {
                 const float4 v4 = x4[j >> 2];
@@ -575,7 +591,7 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
             }
         }
         if (dr_warp) {
-            const float* xr = &xs[buf][lane & (CH - 1)][48];
+            const float* xr = &xs[buf][drow][48];
             for (int j = 0; j < len; ++j) {
                 const float v = xr[j];
                 drs = __fadd_rn (drs, __fmul_rn (v, v));
@@ -867,6 +883,7 @@ struct b200m_tpk {
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
     int imm = 0;                            // host table == literal table: use the immediate-coefficient kernels
     int elide0 = 0;                         // phase 0 of the table is the unit-tap delay fir16's guard assumes
+    int wide = 1, wide_min = 64 * 148;      // process(): 64-channel CTAs once the bank fills the chip with them (B200M_TPK_WIDE=0 / =<min channels>)
     int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
     int fma = 0;                            // B200M_PREC_FMA: tolerance-mode FIR (fir16_fma); needs the literal table (imm)
     TpkDr dr{}; bool dr_on = false;         // DR-14 accumulation of the next process() call (set by dr14.cu)
@@ -936,7 +953,7 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; at[0].val.programmaticStreamSerializationAllowed = 1;
         cudaLaunchConfig_t cfg = {};
         cfg.blockDim = blk; cfg.dynamicSmemBytes = 0; cfg.stream = st; cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
-#define TPK_GO(CH, TC, TP, MX, KM, DRM) do { cfg.gridDim = dim3 ((ce - cf + CH - 1) / CH); \
+#define TPK_GO(CH, TC, TP, MX, KM, DRM) do { cfg.gridDim = dim3 ((ce - cf + CH - 1) / CH); cfg.dynamicSmemBytes = TpkGeom<CH, TC, (TP) && !(MX)>::BYTES; \
             if (h->imm && h->fma) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true, DRM, true>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); \
             else if (h->imm) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); \
             else B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, false, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); } while (0)
@@ -950,8 +967,12 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
             swap_hist = true;
         }
         else if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true, false); else TPK_GO (8, 256, true, true, false, false); }
+        else if (tp && h->wide && (ce - cf) >= h->wide_min) {
+            // wide CTAs (64 channels x 32-sample chunks): every warp has ballistics lanes, so none idles through the serial phase
+            if (km) { if (drp.rms_sum) TPK_GO (64, 32, true, false, true, true); else TPK_GO (64, 32, true, false, true, false); } else TPK_GO (64, 32, true, false, false, false);
+        }
         else if (tp) { if (km) { if (drp.rms_sum) TPK_GO (16, 64, true, false, true, true); else TPK_GO (16, 64, true, false, true, false); } else TPK_GO (16, 64, true, false, false, false); }
-        else tpk_kernel<16, 64, false, false, true, false, false><<<(ce - cf + 15) / 16, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp);
+        else tpk_kernel<16, 64, false, false, true, false, false><<<(ce - cf + 15) / 16, blk, TpkGeom<16, 64, false>::BYTES, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp);
 #undef TPK_GO
         B200M_LAUNCHED (1);
     }
@@ -1021,6 +1042,14 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     A ((void**)&h->st.hist_alt, n * 48 * sizeof (float));
     A ((void**)&h->st.blk_max, n * 4); A ((void**)&h->st.grp_cnt, n * 4);
     if (const char* v = getenv ("B200M_TPK_CHUNKED")) h->chunked = atoi (v) != 0;
+    if (const char* v = getenv ("B200M_TPK_WIDE")) { const int w = atoi (v); h->wide = w != 0; if (w > 1) h->wide_min = w; }
+    // the wide process() kernels need 87 KB of dynamic shared memory
+#define TPK_WATTR(KMF, DRF, FMAF) if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<64, 32, true, false, KMF, true, DRF, FMAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpkGeom<64, 32, true>::BYTES)
+    TPK_WATTR (true, true, true); TPK_WATTR (true, true, false); TPK_WATTR (true, false, true); TPK_WATTR (true, false, false); TPK_WATTR (false, false, true); TPK_WATTR (false, false, false);
+#undef TPK_WATTR
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<64, 32, true, false, true, false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpkGeom<64, 32, true>::BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<64, 32, true, false, true, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpkGeom<64, 32, true>::BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<64, 32, true, false, false, false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpkGeom<64, 32, true>::BYTES);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->own, cudaStreamNonBlocking);
     if (e == cudaSuccess) {
         // constructors: TruePeakdsp _res(true) (:29); Kmeterdsp _flag(false), all zero (kmeterdsp.cc:30-40);

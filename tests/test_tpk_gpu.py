@@ -105,6 +105,17 @@ def test_process_bit_exact(C, blocks, read_every):
     _drive(x, blocks, read_every)
 
 
+@pytest.mark.parametrize("flags", [3, 1])
+def test_wide_ctas_bit_exact(flags, monkeypatch):
+    """process() with 64-channel CTAs (the form banks of >= 9472 channels use; forced here with B200M_TPK_WIDE=2): 70 and 150
+    channels (partial last CTA), ragged blocks, reads every block or never"""
+    monkeypatch.setenv("B200M_TPK_WIDE", "2")
+    blocks = [1024] * 20 + [64] * 6 + [480, 8192, 1, 3, 1023, 33, 4097]
+    _drive(S.white(70, sum(blocks), seed=12), blocks, read_every=1, flags=flags)
+    _drive(S.white(150, 1024 * 10, seed=13), [1024] * 10, read_every=0, flags=flags)
+    _drive(S.nasty(66, 1024 * 4), [1024] * 4, read_every=2, flags=flags)
+
+
 def test_process_max_mode():
     x = S.white(21, 1024 * 12, seed=3)
     _drive(x, [1024] * 12, read_every=1, mode=1, flags=1)
