@@ -156,24 +156,30 @@ cor_scan_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nf
         __syncwarp ();
         // stage the superchunk: frame f of the chunk -> slot (f / 32) * 33 + f % 32 (lane j then walks its own 33-float row)
         if (aligned) {
+            // all sixteen 16-byte loads of the superchunk are issued before the first one is used (32 KB in flight per CTA)
+            float4 vl[CSC_SUPER / 128], vr[CSC_SUPER / 128];
 #pragma unroll
             for (int i = 0; i < CSC_SUPER / 128; ++i) {
                 const int f = 4 * (i * 32 + lane);
-                if (f < len) {                                // len - f may be 1..3 on the last group of a ragged block
-                    float4 vl, vr;
-                    if (f + 4 <= len) { vl = *reinterpret_cast<const float4*> (gl + s0 + f); vr = *reinterpret_cast<const float4*> (gr + s0 + f); }
-                    else {
-                        vl = make_float4 (gl[s0 + f], f + 1 < len ? gl[s0 + f + 1] : 0.f, f + 2 < len ? gl[s0 + f + 2] : 0.f, 0.f);
-                        vr = make_float4 (gr[s0 + f], f + 1 < len ? gr[s0 + f + 1] : 0.f, f + 2 < len ? gr[s0 + f + 2] : 0.f, 0.f);
-                    }
+                vl[i] = make_float4 (0.f, 0.f, 0.f, 0.f); vr[i] = vl[i];
+                if (f + 4 <= len) { vl[i] = *reinterpret_cast<const float4*> (gl + s0 + f); vr[i] = *reinterpret_cast<const float4*> (gr + s0 + f); }
+                else if (f < len) {                            // the last group of a ragged block: 1..3 valid samples
+                    vl[i] = make_float4 (gl[s0 + f], f + 1 < len ? gl[s0 + f + 1] : 0.f, f + 2 < len ? gl[s0 + f + 2] : 0.f, 0.f);
+                    vr[i] = make_float4 (gr[s0 + f], f + 1 < len ? gr[s0 + f + 1] : 0.f, f + 2 < len ? gr[s0 + f + 2] : 0.f, 0.f);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < CSC_SUPER / 128; ++i) {
+                const int f = 4 * (i * 32 + lane);
+                if (f < len) {
                     const int slot = (f >> 5) * CSC_PITCH + (f & 31);
-                    sl[slot] = vl.x; sl[slot + 1] = vl.y; sl[slot + 2] = vl.z; sl[slot + 3] = vl.w;
-                    sr[slot] = vr.x; sr[slot + 1] = vr.y; sr[slot + 2] = vr.z; sr[slot + 3] = vr.w;
+                    sl[slot] = vl[i].x; sl[slot + 1] = vl[i].y; sl[slot + 2] = vl[i].z; sl[slot + 3] = vl[i].w;
+                    sr[slot] = vr[i].x; sr[slot + 1] = vr[i].y; sr[slot + 2] = vr[i].z; sr[slot + 3] = vr[i].w;
                     if (rl) {
                         int o = rboff + s0 + f; o %= N;
-                        if (ring4 && f + 4 <= len) { *reinterpret_cast<float4*> (rl + o) = vl; *reinterpret_cast<float4*> (rr + o) = vr; }
+                        if (ring4 && f + 4 <= len) { *reinterpret_cast<float4*> (rl + o) = vl[i]; *reinterpret_cast<float4*> (rr + o) = vr[i]; }
                         else {
-                            const float al[4] = {vl.x, vl.y, vl.z, vl.w}, ar[4] = {vr.x, vr.y, vr.z, vr.w};
+                            const float al[4] = {vl[i].x, vl[i].y, vl[i].z, vl[i].w}, ar[4] = {vr[i].x, vr[i].y, vr[i].z, vr[i].w};
                             for (int c = 0; c < 4 && f + c < len; ++c) { int oc = o + c; if (oc >= N) oc -= N; rl[oc] = al[c]; rr[oc] = ar[c]; }
                         }
                     }

@@ -705,7 +705,7 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
     constexpr int XP = 48 + TC + 4;
     constexpr int GPC = TC / 4, LPR = TPK_THREADS / CH;
     __shared__ __align__ (16) float xs[CH][XP];
-    __shared__ int s_last;
+    __shared__ float s_rowmax[CH];
     const int tid = threadIdx.x, lane = tid & 31;
     const int grp = blockIdx.x / nchunks, chunk = blockIdx.x - grp * nchunks;
     const int c0 = c_first + grp * CH;
@@ -796,8 +796,7 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
     vmax = fmaxf (vmax, __fmul_rn (0.5f, vmax2));
 #pragma unroll
     for (int o = LPR / 2; o; o >>= 1) vmax = fmaxf (vmax, __shfl_xor_sync (0xffffffffu, vmax, o));
-    const int ch = c0 + r;
-    if (ql == 0 && ch < n_chan && vmax > 0.0f) atomicMax (st.blk_max + ch, __float_as_uint (vmax));
+    if (ql == 0) s_rowmax[r] = vmax;
 
     // history of the next block = the 48 samples that end this one (the last chunk holds them: prefix + chunk >= 48 samples)
     if (chunk == nchunks - 1)
@@ -805,15 +804,18 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
             const int rr = idx / 48, j = idx % 48;
             if (c0 + rr < n_chan) st.hist_alt[(size_t)(c0 + rr) * 48 + j] = xs[rr][len + j];
         }
+    __syncthreads ();
+    if (tid >= 32) return;                                  // the group / grid book-keeping is warp 0's: one fence per CTA, not one per warp
 
-    __threadfence ();                                       // this CTA's atomicMax results are visible before its arrival is
-    __syncthreads ();
-    if (tid == 0) s_last = (atomicAdd (st.grp_cnt + c0, 1u) == (unsigned)(nchunks - 1));
-    __syncthreads ();
-    if (s_last && tid < 32) {
+    const int cc = c0 + lane;
+    const bool own = lane < CH && cc < n_chan;
+    if (own && s_rowmax[lane] > 0.0f) atomicMax (st.blk_max + cc, __float_as_uint (s_rowmax[lane]));
+    __threadfence ();                                       // the maxima are visible before this CTA's arrival is
+    unsigned prev = 0;
+    if (lane == 0) prev = atomicAdd (st.grp_cnt + c0, 1u);
+    prev = __shfl_sync (0xffffffffu, prev, 0);
+    if (prev == (unsigned)(nchunks - 1)) {                  // last chunk of this channel group to finish
         __threadfence ();
-        const int cc = c0 + lane;
-        const bool own = lane < CH && cc < n_chan;
         float mm = 0.0f;
         if (own) {
             const float bm = __uint_as_float (atomicExch (st.blk_max + cc, 0u));
@@ -833,14 +835,11 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
         }
         if (lane == 0) st.grp_cnt[c0] = 0u;
     }
-    if (r128_tpmax) {
+    if (r128_tpmax && lane == 0) {
         // launched with programmatic serialization behind the K-weighting kernel (r128.cu): the grid must not complete before
         // that one has.  Only the LAST CTA waits (a no-op in a plain launch); see tpk_kernel's epilogue.
-        __syncthreads ();
-        if (tid == 0) {
-            const unsigned prev = atomicAdd (st.done_cnt, 1u);
-            if (prev == gridDim.x - 1) { *st.done_cnt = 0u; asm volatile ("griddepcontrol.wait;" ::: "memory"); }
-        }
+        const unsigned done = atomicAdd (st.done_cnt, 1u);
+        if (done == gridDim.x - 1) { *st.done_cnt = 0u; asm volatile ("griddepcontrol.wait;" ::: "memory"); }
     }
 }
 
