@@ -397,7 +397,10 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     constexpr int GPC = TC / 4;                   // 4-sample groups per channel per chunk
     constexpr bool BAL = TP && !TPMAX;
     // ballistics lanes come in groups of 16 channels x 2 filters = one warp: a 16-channel CTA has one such warp (the other three do the
-    // K-meter / DR roles or idle during the serial phase), a 64-channel CTA ("wide") keeps ALL four warps busy in the serial phase
+    // K-meter / DR roles or idle during the serial phase), a 64-channel CTA ("wide") keeps ALL four warps busy in the serial phase.
+    // MEASURED (round 2, 16384 channels x 1024): wide 220 us (tolerance) / 318 us (exact) against 173 / 250 us for the 16-channel form:
+    // 87 KB of shared memory per CTA leave two CTAs = eight warps per SM, far too few to hide the FIR's latencies (the 16-channel form
+    // keeps seven CTAs resident and lets other CTAs' FIR phases run under a CTA's serial phase).  Kept opt-in, bit-identical, tested.
     static_assert (!BAL || CH == 16 || CH == 64, "split ballistics lanes assume 16 channels per warp");
     constexpr bool ALLW = BAL && CH == 64;
     constexpr int LPR = TPK_THREADS / CH;         // lanes that share one channel row in the FIR phase (an aligned lane group)
@@ -882,7 +885,7 @@ struct b200m_tpk {
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
     int imm = 0;                            // host table == literal table: use the immediate-coefficient kernels
     int elide0 = 0;                         // phase 0 of the table is the unit-tap delay fir16's guard assumes
-    int wide = 1, wide_min = 64 * 148;      // process(): 64-channel CTAs once the bank fills the chip with them (B200M_TPK_WIDE=0 / =<min channels>)
+    int wide = 0, wide_min = 64 * 148;      // process() with 64-channel CTAs: opt-in (B200M_TPK_WIDE=1, or =<min channels of a bank>); measured slower, see below
     int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
     int fma = 0;                            // B200M_PREC_FMA: tolerance-mode FIR (fir16_fma); needs the literal table (imm)
     TpkDr dr{}; bool dr_on = false;         // DR-14 accumulation of the next process() call (set by dr14.cu)
