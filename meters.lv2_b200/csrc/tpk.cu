@@ -19,6 +19,7 @@
 // bit-identical to the reference build, not merely within tolerance.
 #include <math.h>
 #include <stdlib.h>
+#include <algorithm>
 #include "common.cuh"
 #include "tpk_internal.cuh"
 
@@ -41,6 +42,7 @@ struct TpkState {                           // SoA, one entry per channel
     float* hist_alt;                        // tpmax_kernel writes the next block's history here; the host swaps hist / hist_alt
     unsigned* blk_max;                      // [n_chan] running |v| maximum of the block being processed (float bits), tpmax_kernel
     unsigned* grp_cnt;                      // [n_chan] finished chunks of the channel group starting at this channel, tpmax_kernel
+    float* tmp;                             // [7][n_chan] serial-meter state between the slabs of one block (tpbal_kernel): z1 z2 m p kz1 kz2 kt
 };
 
 // The zita table depends only on (hl = 24, np = 4, fr = 1.0), not on the sample rate, so its 120 floats are universal
@@ -846,6 +848,302 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
     }
 }
 
+// ---- process() as a two-stage pipeline over time slabs ---------------------------------------------------------------------
+// TruePeakdsp::process (truepeakdsp.cc:41-99) = a time-parallel FIR followed by non-linear ballistics that are strictly serial in
+// time.  Fused in one CTA (tpk_kernel<16,64>) the FIR warps wait through every serial phase.  Here the block is cut into slabs
+// (sized so that two slabs of |out| fit the L2: 2 x n_chan x slab x 16 B <= 64 MB) and two kernels alternate on two streams:
+//   tpfir_kernel  slab s  : one CTA per [8 channels x 64 samples], writes the four |oversampled| values of every input sample to a
+//                           scratch slab (float4 per sample, 64 contiguous bytes per thread) -- chip-filling, issue-bound;
+//   tpbal_kernel  slab s-1: one CTA per 16 channels: warp 0 = 16 channels x {z1, z2} ballistics lanes reading the scratch slab
+//                           (from L2) through cp.async tiles, warp 1 = K-meter lanes (+ DR-14 sums) reading the input block --
+//                           latency-bound on its serial chain, runs UNDER the next slab's FIR kernel.
+// The per-sample operations and their order are those of tpk_kernel (hence of the reference): results are bit-identical in exact
+// mode.  Meter state travels between the slabs of a block through st.tmp; block-begin / block-end transformations (clamp, +1e-20,
+// m *= g, read latches) are applied by the first / last slab only.
+constexpr int TPF_CH = 8, TPF_TC = 64;
+
+template <bool IMM, bool FMA>
+__global__ void __launch_bounds__ (TPK_THREADS)
+tpfir_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int s_begin, int s_len, int aligned, int elide0,
+              TpkState st, float4* __restrict__ scr, int scr_pitch /* samples per channel row of the slab */, float* __restrict__ dbg)
+{
+    constexpr int CH = TPF_CH, TC = TPF_TC;
+    constexpr int XP = 48 + TC + 4 + 8;                       // LPR = 16 lanes per row: any pitch is conflict free; 8 more keep rows 16-byte aligned
+    constexpr int GPC = TC / 4, LPR = TPK_THREADS / CH;       // 16 groups per row, 16 lanes per row: one item per thread
+    __shared__ __align__ (16) float xs[CH][XP];
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int nchunks = (s_len + TC - 1) / TC;
+    const int grp = blockIdx.x / nchunks, chunk = blockIdx.x - grp * nchunks;
+    const int c0 = c_first + grp * CH;
+    const int s0 = s_begin + chunk * TC;                      // absolute sample index inside the block
+    const int len = min (TC, s_begin + s_len - s0);
+    if (s0 == 0) {
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
+            const int r = idx / 48, j = idx % 48;
+            cp_async4 (&xs[r][j], st.hist + (size_t)min (c0 + r, n_chan - 1) * 48 + j, 4);
+        }
+    } else if (aligned) {
+        if (tid < CH * 12) {
+            const int r = tid / 12, c4 = (tid % 12) * 4;
+            cp_async16 (&xs[r][c4], in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 - 48 + c4, 16);
+        }
+    } else {
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
+            const int r = idx / 48, j = idx % 48;
+            cp_async4 (&xs[r][j], in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 - 48 + j, 4);
+        }
+    }
+    if (aligned) {
+        const int r = tid / GPC, c4 = (tid % GPC) * 4;        // CH * GPC = 128 = one 16-byte piece per thread
+        const int left = (len - c4) * 4;
+        const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+        cp_async16 (&xs[r][48 + c4], nb ? in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 + c4 : in, nb);
+    } else {
+        for (int idx = tid; idx < CH * TC; idx += TPK_THREADS) {
+            const int r = idx / TC, cc = idx % TC;
+            const bool ok = cc < len;
+            cp_async4 (&xs[r][48 + cc], ok ? in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 + cc : in, ok ? 4 : 0);
+        }
+    }
+    cp_async_commit ();
+    cp_async_wait<0> ();
+    __syncthreads ();
+
+    const int r = tid / LPR, q = tid % LPR;
+    const bool act = 4 * q < len;
+    float M = 0.0f;
+    if (elide0) M = row_absmax<LPR, 12 + GPC> (reinterpret_cast<const float4*> (&xs[r][0]), lane);
+    const bool silent_rows = elide0 && __all_sync (0xffffffffu, M == 0.0f);
+    bool full0 = !FMA;
+    if (!FMA && elide0 && !silent_rows) {
+        const float4 xm = *reinterpret_cast<const float4*> (&xs[r][act ? 4 * q + 24 : 0]);
+        full0 = !__all_sync (0xffffffffu, !act || phase0_is_delay (xm, M));
+    }
+    if (act && (c0 + r) < n_chan) {
+        float o[16];
+        if (silent_rows) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = 0.0f;
+        } else {
+            float w[52];
+            const float4* xr = reinterpret_cast<const float4*> (&xs[r][4 * q]);
+#pragma unroll
+            for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+            if (FMA) fir16_fma<IMM> (w, o); else fir16<IMM> (w, &xs[r][4 * q], o, full0);
+        }
+        if (dbg) {
+            float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
+#pragma unroll
+            for (int i = 0; i < 4; ++i) d[i] = make_float4 (o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+        // |out| of input samples s0 + 4q .. + 3 (positions beyond the block's end are never read by the ballistics kernel)
+        float4* d = scr + (size_t)(c0 + r - c_first) * scr_pitch + (s0 - s_begin) + 4 * q;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[i] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
+    }
+    // history of the next block = the 48 samples that end this one
+    if (s0 + len == nfram)
+        for (int idx = tid; idx < CH * 48; idx += TPK_THREADS) {
+            const int rr = idx / 48, j = idx % 48;
+            if (c0 + rr < n_chan) st.hist_alt[(size_t)(c0 + rr) * 48 + j] = xs[rr][len + j];
+        }
+}
+
+constexpr int TPB_TILE = 32;                                  // samples per scratch tile: 16 channels x 32 samples x 16 B = 8 KB
+constexpr int TPB_PITCH = 4 * TPB_TILE + 4;                   // floats per channel row: = 4 mod 32
+constexpr int TPB_STAGES = 3;
+
+template <bool KM, bool DR>
+__global__ void __launch_bounds__ (64)
+tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nch_total, int nfram,
+              int s_begin, int s_len, int first, int last, int aligned, int tp_on, TpkParams prm, TpkState st, TpkDr dr)
+{
+    __shared__ __align__ (16) float tile[TPB_STAGES][16 * TPB_PITCH];       // |out| tiles (warp 0)
+    __shared__ __align__ (16) float xin[TPB_STAGES][16 * (TPB_TILE + 4)];   // input tiles (warp 1)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = c_first + blockIdx.x * 16;
+    const int ntiles = (s_len + TPB_TILE - 1) / TPB_TILE;
+    const size_t N = (size_t)nch_total;                      // st.tmp is [7][channels of the bank]
+    if (warp == 0) {
+        if (!tp_on) return;
+        // ---- true-peak ballistics: lane = filter * 16 + channel (truepeakdsp.cc:52-99)
+        const int tch = lane & 15, filt = lane >> 4;
+        const int ch = min (c0 + tch, n_chan - 1);
+        const bool live = (c0 + tch) < n_chan;
+        float z, m, p; int res = 0;
+        const float wf = filt ? prm.w2 : prm.w1;
+        if (first) {
+            res = st.tp_res[ch];
+            m = res ? 0.0f : st.tp_m[ch];
+            p = res ? 0.0f : st.tp_p[ch];
+            const float a = filt ? st.tp_z2[ch] : st.tp_z1[ch];
+            z = a > 20 ? 20 : (a < 0 ? 0 : a);
+        } else {
+            z = st.tmp[(size_t)(filt ? 1 : 0) * N + ch]; m = st.tmp[2 * N + ch]; p = st.tmp[3 * N + ch];
+        }
+        auto issue = [&] (int t) {
+            if (t < ntiles) {
+                float* dst = tile[t % TPB_STAGES];
+                const int t0 = t * TPB_TILE;
+                // 16 rows x 32 float4 = 512 pieces of 16 bytes, 16 per lane: lane l takes pieces l, l + 32, ...
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int pc = i * 32 + lane, row = pc >> 5, col = pc & 31;
+                    const int chr = min (c0 + row, n_chan - 1) - c_first;
+                    const bool ok = (t0 + col) < s_len;
+                    cp_async16 (dst + row * TPB_PITCH + 4 * col, ok ? (const void*)(scr + (size_t)chr * scr_pitch + t0 + col) : (const void*)scr, ok ? 16 : 0);
+                }
+            }
+            cp_async_commit ();
+        };
+#pragma unroll
+        for (int t = 0; t < TPB_STAGES - 1; ++t) issue (t);
+        for (int t = 0; t < ntiles; ++t) {
+            cp_async_wait<TPB_STAGES - 2> ();
+            __syncwarp ();
+            const float4* b4 = reinterpret_cast<const float4*> (tile[t % TPB_STAGES] + tch * TPB_PITCH);
+            const int len = min (TPB_TILE, s_len - t * TPB_TILE);
+            for (int j = 0; j < len; ++j) {
+                const float4 v4 = b4[j];
+                z = __fmul_rn (z, prm.w3);
+                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float v = vv[i];
+                    if (v > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v, z)));
+                    p = fmaxf (p, v);
+                }
+                const float tt = __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16));
+                if (tt > m) m = tt;
+            }
+            __syncwarp ();
+            issue (t + TPB_STAGES - 1);
+        }
+        cp_async_wait<0> ();
+        if (live) {
+            if (last) {
+                if (first == 0) res = st.tp_res[ch];
+                if (filt) st.tp_z2[ch] = __fadd_rn (z, 1e-20f);
+                else {
+                    st.tp_z1[ch] = __fadd_rn (z, 1e-20f);
+                    m = __fmul_rn (m, prm.g);
+                    if (res) { st.tp_m[ch] = m; st.tp_p[ch] = p; st.tp_res[ch] = 0; }
+                    else {
+                        if (m > st.tp_m[ch]) st.tp_m[ch] = m;
+                        if (p > st.tp_p[ch]) st.tp_p[ch] = p;
+                    }
+                }
+            } else {
+                st.tmp[(size_t)(filt ? 1 : 0) * N + ch] = z;
+                if (!filt) { st.tmp[2 * N + ch] = m; st.tmp[3 * N + ch] = p; }
+            }
+        }
+    } else {
+        if (!KM) return;
+        // ---- warp 1: K-meter on lanes 0..15 (kmeterdsp.cc:74-139), DR-14 window sums on lanes 16..31 (src/dr14.c:401-416)
+        const int kch = lane & 15;
+        const int ch = min (c0 + kch, n_chan - 1);
+        const bool live = (c0 + kch) < n_chan;
+        const bool is_km = lane < 16;
+        const bool is_dr = DR && dr.rms_sum != nullptr && lane >= 16;
+        float kz1 = 0, kz2 = 0, kt = 0, drs = 0, drp = 0;
+        if (is_km) {
+            if (first) {
+                const float a = st.km_z1[ch], b = st.km_z2[ch];
+                kz1 = a > 50 ? 50 : (a < 0 ? 0 : a);
+                kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
+            } else { kz1 = st.tmp[4 * N + ch]; kz2 = st.tmp[5 * N + ch]; kt = st.tmp[6 * N + ch]; }
+        }
+        if (is_dr) { drs = dr.rms_sum[ch]; drp = dr.peak_cur[ch]; }
+        const int km_n = (nfram / 4) * 4;
+        constexpr int XPI = TPB_TILE + 4;
+        auto issue = [&] (int t) {
+            if (t < ntiles) {
+                float* dst = xin[t % TPB_STAGES];
+                const int t0 = s_begin + t * TPB_TILE;
+                if (aligned) {
+                    // 16 rows x 8 pieces of 16 bytes = 128 pieces, 4 per lane
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int pc = i * 32 + lane, row = pc >> 3, c4 = (pc & 7) * 4;
+                        const int left = (s_begin + s_len - (t0 + c4)) * 4;
+                        const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+                        cp_async16 (dst + row * XPI + c4, nb ? in + (size_t)min (c0 + row, n_chan - 1) * stride + t0 + c4 : in, nb);
+                    }
+                } else {
+                    for (int row = 0; row < 16; ++row) {
+                        const bool ok = (t0 + lane) < s_begin + s_len;
+                        cp_async4 (dst + row * XPI + lane, ok ? in + (size_t)min (c0 + row, n_chan - 1) * stride + t0 + lane : in, ok ? 4 : 0);
+                    }
+                }
+            }
+            cp_async_commit ();
+        };
+#pragma unroll
+        for (int t = 0; t < TPB_STAGES - 1; ++t) issue (t);
+        const float om4 = __fmul_rn (4.0f, prm.omega);
+        for (int t = 0; t < ntiles; ++t) {
+            cp_async_wait<TPB_STAGES - 2> ();
+            __syncwarp ();
+            const float* xr = xin[t % TPB_STAGES] + kch * XPI;
+            const int a0 = s_begin + t * TPB_TILE;                     // absolute index of the tile's first sample (a multiple of 4)
+            const int len = min (TPB_TILE, s_begin + s_len - a0);
+            if (is_km) {
+                const int e = min (len, km_n - a0);
+                for (int j = 0; j + 4 <= e; j += 4) {
+                    const float4 v4 = *reinterpret_cast<const float4*> (xr + j);
+                    const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float sq = __fmul_rn (vv[i], vv[i]);
+                        if (kt < sq) kt = sq;
+                        kz1 = __fadd_rn (kz1, __fmul_rn (prm.omega, __fsub_rn (sq, kz1)));
+                    }
+                    kz2 = __fadd_rn (kz2, __fmul_rn (om4, __fsub_rn (kz1, kz2)));
+                }
+            }
+            if (DR && dr.rms_sum != nullptr) {                      // both half warps take the branch: the window close shuffles within lanes 16..31
+                for (int j = 0; j < len; ++j) {
+                    const float v = xr[j];
+                    if (is_dr) { drs = __fadd_rn (drs, __fmul_rn (v, v)); drp = drp > v ? drp : v; }
+                    if (a0 + j == dr.cut) {
+                        const float other = dr.nch == 2 ? __shfl_xor_sync (0xffffffffu, drs, 1) : drs;
+                        const bool silent = !((double)drs > dr.silent_thr) && !((double)other > dr.silent_thr);
+                        if (is_dr && live) {
+                            dr.emit_valid[ch] = silent ? 0 : 1;
+                            if (!silent) { dr.emit_rms[ch] = drs; dr.emit_peak[ch] = drp; }
+                        }
+                        if (is_dr) { drs = 0.0f; if (!silent) drp = 0.0f; }
+                    }
+                }
+            }
+            __syncwarp ();
+            issue (t + TPB_STAGES - 1);
+        }
+        cp_async_wait<0> ();
+        if (is_dr && live) { dr.rms_sum[ch] = drs; dr.peak_cur[ch] = drp; }
+        if (is_km && live) {
+            if (last) {
+                if (isnan (kz1)) kz1 = 0;
+                if (isnan (kz2)) kz2 = 0;
+                if (!finitef_ (kt)) kt = 0;
+                st.km_z1[ch] = __fadd_rn (kz1, 1e-20f);
+                st.km_z2[ch] = __fadd_rn (kz2, 1e-20f);
+                const float sr = __fsqrt_rn (__fmul_rn (2.0f, kz2));
+                const float tr = __fsqrt_rn (kt);
+                if (st.km_flag[ch]) { st.km_rms[ch] = sr; st.km_flag[ch] = 0; }
+                else if (sr > st.km_rms[ch]) st.km_rms[ch] = sr;
+                float pk = st.km_peak[ch]; int cnt = st.km_cnt[ch];
+                if (tr >= pk) { pk = tr; cnt = prm.hold; }
+                else if (cnt > 0) cnt -= nfram;
+                else { pk = __fmul_rn (pk, prm.fall); pk = __fadd_rn (pk, 1e-10f); }
+                st.km_peak[ch] = pk; st.km_cnt[ch] = cnt;
+                st.km_fall[ch] = prm.fall; st.km_fpp[ch] = nfram;
+            } else { st.tmp[4 * N + ch] = kz1; st.tmp[5 * N + ch] = kz2; st.tmp[6 * N + ch] = kt; }
+        }
+    }
+}
+
 // Tried and dropped (round 1): a warp-specialised pipeline for process() — four FIR warps + a K-meter warp in lock
 // step, the ballistics warp one chunk behind on a double-buffered |out| tile with full/empty named barriers.  It was
 // bit-exact but slower (372 us vs 286 us per 16384 x 1024 block): 48 KB of shared memory and 80 registers x 192 threads
@@ -885,6 +1183,9 @@ struct b200m_tpk {
     TpkState st{}; b200m_tpk_result* d_res = nullptr; float* d_dbg = nullptr;
     int imm = 0;                            // host table == literal table: use the immediate-coefficient kernels
     int elide0 = 0;                         // phase 0 of the table is the unit-tap delay fir16's guard assumes
+    int split = 1;                          // process() with true peak as the FIR / ballistics slab pipeline (tpfir_kernel + tpbal_kernel); B200M_TPK_SPLIT=0: fused tpk_kernel<16,64>
+    float4* d_scr = nullptr; uint32_t slab = 0;       // two slabs of |out|: [2][n_chan][slab] float4
+    cudaStream_t sb = nullptr; cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_bal[2] = {nullptr, nullptr};
     int wide = 0, wide_min = 64 * 148;      // process() with 64-channel CTAs: opt-in (B200M_TPK_WIDE=1, or =<min channels of a bank>); measured slower, see below
     int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
     int fma = 0;                            // B200M_PREC_FMA: tolerance-mode FIR (fir16_fma); needs the literal table (imm)
@@ -969,6 +1270,33 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
             swap_hist = true;
         }
         else if (tp && tp_mode == B200M_TP_MODE_MAX) { if (km) TPK_GO (8, 256, true, true, true, false); else TPK_GO (8, 256, true, true, false, false); }
+        else if (tp && h->split && h->d_scr) {
+            // FIR / ballistics slab pipeline: FIR kernels on `st`, ballistics kernels on the bank's second stream, one slab behind
+            const int nslab = ((int)nfram + (int)h->slab - 1) / (int)h->slab;
+            const int ngrp = (ce - cf + TPF_CH - 1) / TPF_CH, nb16 = (ce - cf + 15) / 16;
+            // the ballistics stream must not start before everything queued on `st` so far (previous block's state, controls)
+            for (int sidx = 0; sidx < nslab; ++sidx) {
+                const int sb0 = sidx * (int)h->slab, sl_len = std::min ((int)h->slab, (int)nfram - sb0), b = sidx & 1;
+                float4* scr = h->d_scr + (size_t)b * h->n_chan * h->slab + (size_t)cf * h->slab;
+                if (sidx >= 2) B200M_CUDA (cudaStreamWaitEvent (st, h->ev_bal[b], 0));          // the slab buffer is free again
+                const int nch = (sl_len + TPF_TC - 1) / TPF_TC;
+                if (h->imm && h->fma) tpfir_kernel<true, true><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg);
+                else if (h->imm) tpfir_kernel<true, false><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg);
+                else tpfir_kernel<false, false><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg);
+                B200M_CUDA (cudaEventRecord (h->ev_fir[b], st));
+                B200M_CUDA (cudaStreamWaitEvent (h->sb, h->ev_fir[b], 0));
+                const int first = sidx == 0, last = sidx == nslab - 1;
+                if (km && drp.rms_sum) tpbal_kernel<true, true><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp);
+                else if (km) tpbal_kernel<true, false><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp);
+                else tpbal_kernel<false, false><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp);
+                B200M_CUDA (cudaEventRecord (h->ev_bal[b], h->sb));
+                B200M_LAUNCHED (2);
+            }
+            B200M_CUDA (cudaStreamWaitEvent (st, h->ev_bal[(nslab - 1) & 1], 0));              // the caller's stream sees the block complete
+            if (nslab >= 2) B200M_CUDA (cudaStreamWaitEvent (st, h->ev_bal[(nslab - 2) & 1], 0));
+            swap_hist = true;
+            continue;
+        }
         else if (tp && h->wide && (ce - cf) >= h->wide_min) {
             // wide CTAs (64 channels x 32-sample chunks): every warp has ballistics lanes, so none idles through the serial phase
             if (km) { if (drp.rms_sum) TPK_GO (64, 32, true, false, true, true); else TPK_GO (64, 32, true, false, true, false); } else TPK_GO (64, 32, true, false, false, false);
@@ -1044,6 +1372,24 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     A ((void**)&h->st.hist_alt, n * 48 * sizeof (float));
     A ((void**)&h->st.blk_max, n * 4); A ((void**)&h->st.grp_cnt, n * 4);
     if (const char* v = getenv ("B200M_TPK_CHUNKED")) h->chunked = atoi (v) != 0;
+    // banks too small to fill the chip keep the fused kernel (one launch per block instead of two launches + three event operations
+    // per slab: the per-instance banks of the LV2 facade); B200M_TPK_SPLIT = 0: never, 1: default rule, 2: always
+    h->split = n_chan >= 512;
+    if (const char* v = getenv ("B200M_TPK_SPLIT")) { const int q = atoi (v); h->split = q == 0 ? 0 : (q >= 2 ? 1 : h->split); }
+    A ((void**)&h->st.tmp, 7 * n * sizeof (float));
+    if ((flags & B200M_TPK_TRUEPEAK) && h->split) {
+        // slab length: two slabs of |out| (16 B per sample and channel) within 64 MB, so that the ballistics kernel reads them from L2
+        uint32_t slab = 64;
+        while (slab < B200M_MAX_BLOCK && (size_t)2 * n * (2 * slab) * 16 <= ((size_t)64 << 20)) slab *= 2;
+        if (const char* v = getenv ("B200M_TPK_SLAB")) { const int q = atoi (v); if (q >= 64 && q <= (int)B200M_MAX_BLOCK && q % 64 == 0) slab = (uint32_t)q; }
+        h->slab = slab;
+        A ((void**)&h->d_scr, (size_t)2 * n * slab * sizeof (float4));
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->sb, cudaStreamNonBlocking);
+        for (int i = 0; i < 2; ++i) {
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags (&h->ev_fir[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags (&h->ev_bal[i], cudaEventDisableTiming);
+        }
+    }
     if (const char* v = getenv ("B200M_TPK_WIDE")) { const int w = atoi (v); h->wide = w != 0; if (w > 1) h->wide_min = w; }
     // the wide process() kernels need 87 KB of dynamic shared memory
 #define TPK_WATTR(KMF, DRF, FMAF) if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<64, 32, true, false, KMF, true, DRF, FMAF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TpkGeom<64, 32, true>::BYTES)
@@ -1071,8 +1417,10 @@ int b200m_tpk_destroy (b200m_tpk* h)
     DeviceGuard g (h->device);
     cudaDeviceSynchronize ();
     void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms,
-                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt};
+                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt, h->st.tmp, h->d_scr};
     for (void* p : ps) cudaFree (p);
+    if (h->sb) cudaStreamDestroy (h->sb);
+    for (int i = 0; i < 2; ++i) { if (h->ev_fir[i]) cudaEventDestroy (h->ev_fir[i]); if (h->ev_bal[i]) cudaEventDestroy (h->ev_bal[i]); }
     h->stage.release ();
     if (h->own) cudaStreamDestroy (h->own);
     delete h;

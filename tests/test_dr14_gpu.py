@@ -100,14 +100,16 @@ def test_tpnrms_plugins():
     _side_by_side("TPnRMSmono", 1, 30, 777)
 
 
-@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("wide", [False, True, "slabs"])
 def test_dr14_bank_vs_reference_instances(wide, monkeypatch):
     """the batch API: 5 stereo instances in one bank vs 5 reference plugin instances; `wide` forces the 64-channel CTA form of the
     process() kernel (csrc/tpk.cu: every warp carries ballistics / K-meter / DR lanes) that large banks get by default"""
     import torch
     import meters_lv2_b200 as B
-    if wide:
-        monkeypatch.setenv("B200M_TPK_WIDE", "2")
+    if wide == "slabs":
+        monkeypatch.setenv("B200M_TPK_SLAB", "192"); monkeypatch.setenv("B200M_TPK_SPLIT", "2")   # 8192-frame blocks in 43 slabs: DR window ends fall inside slabs
+    elif wide:
+        monkeypatch.setenv("B200M_TPK_WIDE", "2"); monkeypatch.setenv("B200M_TPK_SPLIT", "0")
     ref, l2 = descriptors(O.PATHS["reference"])
     ninst, nblocks, blk = 5, 150, 8192
     gains = [0.9, 0.3, 0.05, 1e-5, 0.6]                          # instance 3 stays below the silence gate

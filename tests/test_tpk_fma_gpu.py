@@ -54,6 +54,14 @@ def test_fma_stream_within_tolerance(n, block):
         assert err <= 0.2 * TOL_REL, (ch, err)                 # measured ~2e-7; the bound leaves 5x margin to the contract
 
 
+@pytest.fixture(autouse=True, params=["default", "slabs"])
+def process_form(request, monkeypatch):
+    """process() runs fused for small banks; "slabs" forces the FIR / ballistics slab pipeline that large banks use"""
+    if request.param == "slabs":
+        monkeypatch.setenv("B200M_TPK_SLAB", "256"); monkeypatch.setenv("B200M_TPK_SPLIT", "2")
+    return request.param
+
+
 @pytest.mark.parametrize("mode", [0, 1])
 def test_fma_readings_within_tolerance(mode):
     """process_max (mode 1) and process (mode 0) readings, 40 blocks of 1024, read every block"""

@@ -8,13 +8,18 @@ import _signals as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["shortcut", "full"])
+@pytest.fixture(autouse=True, params=["shortcut", "full", "slabs", "fused"])
 def phase0_mode(request, monkeypatch):
-    """every test runs twice: with the exact phase-0 shortcut of the FIR (default) and with phase 0 always evaluated."""
+    """every test runs four times: with the exact phase-0 shortcut of the FIR (default) and with phase 0 always evaluated; with
+    process() cut into 128-sample slabs (the FIR / ballistics pipeline of large banks: small banks would otherwise run one slab per
+    block); and with the fused one-kernel form of process() (B200M_TPK_SPLIT=0)."""
+    monkeypatch.delenv("B200M_TPK_ELIDE0", raising=False)
     if request.param == "full":
         monkeypatch.setenv("B200M_TPK_ELIDE0", "0")
-    else:
-        monkeypatch.delenv("B200M_TPK_ELIDE0", raising=False)
+    elif request.param == "slabs":
+        monkeypatch.setenv("B200M_TPK_SLAB", "128"); monkeypatch.setenv("B200M_TPK_SPLIT", "2")
+    elif request.param == "fused":
+        monkeypatch.setenv("B200M_TPK_SPLIT", "0")
     return request.param
 
 
@@ -109,7 +114,7 @@ def test_process_bit_exact(C, blocks, read_every):
 def test_wide_ctas_bit_exact(flags, monkeypatch):
     """process() with 64-channel CTAs (the form banks of >= 9472 channels use; forced here with B200M_TPK_WIDE=2): 70 and 150
     channels (partial last CTA), ragged blocks, reads every block or never"""
-    monkeypatch.setenv("B200M_TPK_WIDE", "2")
+    monkeypatch.setenv("B200M_TPK_WIDE", "2"); monkeypatch.setenv("B200M_TPK_SPLIT", "0")
     blocks = [1024] * 20 + [64] * 6 + [480, 8192, 1, 3, 1023, 33, 4097]
     _drive(S.white(70, sum(blocks), seed=12), blocks, read_every=1, flags=flags)
     _drive(S.white(150, 1024 * 10, seed=13), [1024] * 10, read_every=0, flags=flags)
