@@ -570,8 +570,10 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    // `if (v > z) z += w (v - z)` (truepeakdsp.cc:66-71) without the predicate on the dependency chain: for v <= z, or a
+                    // NaN v, the increment is w * max (v - z, 0) = +0 and z + 0 = z exactly (z >= +0 always); otherwise the same three ops
                     const float v = vv[i];
-                    if (v > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v, z)));
+                    z = __fadd_rn (z, __fmul_rn (wf, fmaxf (__fsub_rn (v, z), 0.0f)));
                     p = fmaxf (p, v);                       // == `if (v > p) p = v`: p is never NaN, a NaN v leaves it unchanged
                 }
                 const float t = __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16));    // z1 + z2
@@ -860,7 +862,7 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
 // The per-sample operations and their order are those of tpk_kernel (hence of the reference): results are bit-identical in exact
 // mode.  Meter state travels between the slabs of a block through st.tmp; block-begin / block-end transformations (clamp, +1e-20,
 // m *= g, read latches) are applied by the first / last slab only.
-constexpr int TPF_CH = 8, TPF_TC = 64;
+constexpr int TPF_CH = 8, TPF_TC = 256;
 
 template <bool IMM, bool FMA>
 __global__ void __launch_bounds__ (TPK_THREADS)
@@ -868,8 +870,8 @@ tpfir_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
               TpkState st, float4* __restrict__ scr, int scr_pitch /* samples per channel row of the slab */, float* __restrict__ dbg)
 {
     constexpr int CH = TPF_CH, TC = TPF_TC;
-    constexpr int XP = 48 + TC + 4 + 8;                       // LPR = 16 lanes per row: any pitch is conflict free; 8 more keep rows 16-byte aligned
-    constexpr int GPC = TC / 4, LPR = TPK_THREADS / CH;       // 16 groups per row, 16 lanes per row: one item per thread
+    constexpr int XP = 48 + TC + 4;                           // LPR = 16 lanes per row: any pitch is conflict free
+    constexpr int GPC = TC / 4, LPR = TPK_THREADS / CH;       // 64 groups per row, 16 lanes per row: up to four items per thread
     __shared__ __align__ (16) float xs[CH][XP];
     const int tid = threadIdx.x, lane = tid & 31;
     const int nchunks = (s_len + TC - 1) / TC;
@@ -894,10 +896,13 @@ tpfir_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
         }
     }
     if (aligned) {
-        const int r = tid / GPC, c4 = (tid % GPC) * 4;        // CH * GPC = 128 = one 16-byte piece per thread
-        const int left = (len - c4) * 4;
-        const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
-        cp_async16 (&xs[r][48 + c4], nb ? in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 + c4 : in, nb);
+#pragma unroll
+        for (int idx = tid; idx < CH * GPC; idx += TPK_THREADS) {
+            const int r = idx / GPC, c4 = (idx % GPC) * 4;
+            const int left = (len - c4) * 4;
+            const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+            cp_async16 (&xs[r][48 + c4], nb ? in + (size_t)min (c0 + r, n_chan - 1) * stride + s0 + c4 : in, nb);      // zero fill beyond the chunk's end
+        }
     } else {
         for (int idx = tid; idx < CH * TC; idx += TPK_THREADS) {
             const int r = idx / TC, cc = idx % TC;
@@ -909,17 +914,20 @@ tpfir_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
     cp_async_wait<0> ();
     __syncthreads ();
 
-    const int r = tid / LPR, q = tid % LPR;
-    const bool act = 4 * q < len;
+    const int r = tid / LPR, ql = tid % LPR;
     float M = 0.0f;
     if (elide0) M = row_absmax<LPR, 12 + GPC> (reinterpret_cast<const float4*> (&xs[r][0]), lane);
     const bool silent_rows = elide0 && __all_sync (0xffffffffu, M == 0.0f);
-    bool full0 = !FMA;
-    if (!FMA && elide0 && !silent_rows) {
-        const float4 xm = *reinterpret_cast<const float4*> (&xs[r][act ? 4 * q + 24 : 0]);
-        full0 = !__all_sync (0xffffffffu, !act || phase0_is_delay (xm, M));
-    }
-    if (act && (c0 + r) < n_chan) {
+    const bool rowok = (c0 + r) < n_chan;
+#pragma unroll 1
+    for (int q = ql; q < GPC && 4 * (q - ql) < len; q += LPR) {
+        const bool act = 4 * q < len;
+        bool full0 = !FMA;
+        if (!FMA && elide0 && !silent_rows) {
+            const float4 xm = *reinterpret_cast<const float4*> (&xs[r][act ? 4 * q + 24 : 0]);
+            full0 = !__all_sync (0xffffffffu, !act || phase0_is_delay (xm, M));
+        }
+        if (!act) continue;
         float o[16];
         if (silent_rows) {
 #pragma unroll
@@ -931,6 +939,7 @@ tpfir_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
             for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
             if (FMA) fir16_fma<IMM> (w, o); else fir16<IMM> (w, &xs[r][4 * q], o, full0);
         }
+        if (!rowok) continue;
         if (dbg) {
             float4* d = reinterpret_cast<float4*> (dbg + (size_t)(c0 + r) * (4 * B200M_MAX_BLOCK) + 4 * (s0 + 4 * q));
 #pragma unroll
@@ -1003,14 +1012,19 @@ tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __rest
             __syncwarp ();
             const float4* b4 = reinterpret_cast<const float4*> (tile[t % TPB_STAGES] + tch * TPB_PITCH);
             const int len = min (TPB_TILE, s_len - t * TPB_TILE);
+            float4 nxt = b4[0];
+#pragma unroll 4
             for (int j = 0; j < len; ++j) {
-                const float4 v4 = b4[j];
+                const float4 v4 = nxt;
+                nxt = b4[min (j + 1, TPB_TILE - 1)];               // the chain below is ~70 cycles per sample: keep the load off it
                 z = __fmul_rn (z, prm.w3);
                 const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
+                    // `if (v > z) z += w (v - z)` without the predicate on the dependency chain: for v <= z (or a NaN v) the increment is
+                    // w * max (v - z, 0) = +0 and z + 0 = z exactly (z >= +0 always), otherwise the very same three operations
                     const float v = vv[i];
-                    if (v > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v, z)));
+                    z = __fadd_rn (z, __fmul_rn (wf, fmaxf (__fsub_rn (v, z), 0.0f)));
                     p = fmaxf (p, v);
                 }
                 const float tt = __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16));
@@ -1384,7 +1398,11 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
         if (const char* v = getenv ("B200M_TPK_SLAB")) { const int q = atoi (v); if (q >= 64 && q <= (int)B200M_MAX_BLOCK && q % 64 == 0) slab = (uint32_t)q; }
         h->slab = slab;
         A ((void**)&h->d_scr, (size_t)2 * n * slab * sizeof (float4));
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->sb, cudaStreamNonBlocking);
+        // the ballistics kernels are latency-bound and small: highest stream priority, so that SM slots freed by retiring FIR CTAs go to
+        // them first (at equal priority the FIR grid keeps the register file full and lets one ballistics CTA per SM in at a time)
+        int prio_lo = 0, prio_hi = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange (&prio_lo, &prio_hi);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority (&h->sb, cudaStreamNonBlocking, prio_hi);
         for (int i = 0; i < 2; ++i) {
             if (e == cudaSuccess) e = cudaEventCreateWithFlags (&h->ev_fir[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags (&h->ev_bal[i], cudaEventDisableTiming);
