@@ -958,12 +958,15 @@ tpfir_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
         }
 }
 
-constexpr int TPB_TILE = 32;                                  // samples per scratch tile: 16 channels x 32 samples x 16 B = 8 KB
+// samples per scratch tile: 16 channels x 16 samples x 16 B = 4 KB.  Small on purpose: with three stages a CTA holds 17 KB of shared
+// memory, so that the seven ballistics CTAs an SM gets (1024 CTAs / 148 SMs) leave room for the FIR kernel's CTAs of the next slab --
+// with 32-sample tiles (32 KB per CTA) whichever kernel was placed first kept the other one off the SM and the two stages ran serially
+constexpr int TPB_TILE = 16;
 constexpr int TPB_PITCH = 4 * TPB_TILE + 4;                   // floats per channel row: = 4 mod 32
 constexpr int TPB_STAGES = 3;
 
 template <bool KM, bool DR>
-__global__ void __launch_bounds__ (64)
+__global__ void __launch_bounds__ (64, 24)                   // <= 42 registers: seven of these CTAs must leave the register file to the FIR kernel's
 tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nch_total, int nfram,
               int s_begin, int s_len, int first, int last, int aligned, int tp_on, TpkParams prm, TpkState st, TpkDr dr)
 {
@@ -994,10 +997,10 @@ tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __rest
             if (t < ntiles) {
                 float* dst = tile[t % TPB_STAGES];
                 const int t0 = t * TPB_TILE;
-                // 16 rows x 32 float4 = 512 pieces of 16 bytes, 16 per lane: lane l takes pieces l, l + 32, ...
+                // 16 rows x TPB_TILE float4 pieces of 16 bytes: lane l takes pieces l, l + 32, ...
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int pc = i * 32 + lane, row = pc >> 5, col = pc & 31;
+                for (int i = 0; i < 16 * TPB_TILE / 32; ++i) {
+                    const int pc = i * 32 + lane, row = pc / TPB_TILE, col = pc % TPB_TILE;
                     const int chr = min (c0 + row, n_chan - 1) - c_first;
                     const bool ok = (t0 + col) < s_len;
                     cp_async16 (dst + row * TPB_PITCH + 4 * col, ok ? (const void*)(scr + (size_t)chr * scr_pitch + t0 + col) : (const void*)scr, ok ? 16 : 0);
@@ -1076,18 +1079,19 @@ tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __rest
                 float* dst = xin[t % TPB_STAGES];
                 const int t0 = s_begin + t * TPB_TILE;
                 if (aligned) {
-                    // 16 rows x 8 pieces of 16 bytes = 128 pieces, 4 per lane
+                    // 16 rows x TPB_TILE / 4 pieces of 16 bytes
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int pc = i * 32 + lane, row = pc >> 3, c4 = (pc & 7) * 4;
+                    for (int i = 0; i < 16 * (TPB_TILE / 4) / 32; ++i) {
+                        const int pc = i * 32 + lane, row = pc / (TPB_TILE / 4), c4 = (pc % (TPB_TILE / 4)) * 4;
                         const int left = (s_begin + s_len - (t0 + c4)) * 4;
                         const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
                         cp_async16 (dst + row * XPI + c4, nb ? in + (size_t)min (c0 + row, n_chan - 1) * stride + t0 + c4 : in, nb);
                     }
                 } else {
-                    for (int row = 0; row < 16; ++row) {
-                        const bool ok = (t0 + lane) < s_begin + s_len;
-                        cp_async4 (dst + row * XPI + lane, ok ? in + (size_t)min (c0 + row, n_chan - 1) * stride + t0 + lane : in, ok ? 4 : 0);
+                    for (int pc = lane; pc < 16 * TPB_TILE; pc += 32) {
+                        const int row = pc / TPB_TILE, col = pc % TPB_TILE;
+                        const bool ok = (t0 + col) < s_begin + s_len;
+                        cp_async4 (dst + row * XPI + col, ok ? in + (size_t)min (c0 + row, n_chan - 1) * stride + t0 + col : in, ok ? 4 : 0);
                     }
                 }
             }
