@@ -862,6 +862,13 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
 // The per-sample operations and their order are those of tpk_kernel (hence of the reference): results are bit-identical in exact
 // mode.  Meter state travels between the slabs of a block through st.tmp; block-begin / block-end transformations (clamp, +1e-20,
 // m *= g, read latches) are applied by the first / last slab only.
+// MEASURED (round 2, 16384 channels x 1024 frames, tolerance-mode FIR): one slab per block, i.e. the two kernels back to back:
+// tpfir 99 us (the 268 MB of |out| stores cost 18 us over tpmax_kernel's 81 us) + tpbal 102 us = 203 us, against 174-177 us for the
+// fused tpk_kernel<16,64>; with 2 / 4 / 8 slabs per block 230 / 250 / 263 us -- more slabs made it slower, i.e. the stages did not
+// overlap (first because each kernel's CTAs, whichever were placed first, kept the other's off the SMs -- 32 KB ballistics CTAs fill the
+// shared memory, FIR CTAs the register file -- and after shrinking both, for reasons not profiled in this round: no nsys here).  The
+// ballistics kernel alone runs at ~200 cycles per input sample and warp where its dependency chain suggests ~80.  Opt-in, bit-identical,
+// covered by tests/test_tpk_gpu.py (fixture mode "slabs"); the fused kernel stays the default.
 constexpr int TPF_CH = 8, TPF_TC = 256;
 
 template <bool IMM, bool FMA>
@@ -1390,10 +1397,9 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     A ((void**)&h->st.hist_alt, n * 48 * sizeof (float));
     A ((void**)&h->st.blk_max, n * 4); A ((void**)&h->st.grp_cnt, n * 4);
     if (const char* v = getenv ("B200M_TPK_CHUNKED")) h->chunked = atoi (v) != 0;
-    // banks too small to fill the chip keep the fused kernel (one launch per block instead of two launches + three event operations
-    // per slab: the per-instance banks of the LV2 facade); B200M_TPK_SPLIT = 0: never, 1: default rule, 2: always
-    h->split = n_chan >= 512;
-    if (const char* v = getenv ("B200M_TPK_SPLIT")) { const int q = atoi (v); h->split = q == 0 ? 0 : (q >= 2 ? 1 : h->split); }
+    // the slab pipeline is opt-in (B200M_TPK_SPLIT=2; =1: for banks of >= 512 channels): MEASURED slower than the fused kernel, see below
+    h->split = 0;
+    if (const char* v = getenv ("B200M_TPK_SPLIT")) { const int q = atoi (v); h->split = q >= 2 ? 1 : (q == 1 ? n_chan >= 512 : 0); }
     A ((void**)&h->st.tmp, 7 * n * sizeof (float));
     if ((flags & B200M_TPK_TRUEPEAK) && h->split) {
         // slab length: two slabs of |out| (16 B per sample and channel) within 64 MB, so that the ballistics kernel reads them from L2
