@@ -282,6 +282,7 @@ LV2_Handle ebur_instantiate (const LV2_Descriptor* d, double rate, const char*, 
     forget_sent_histogram (p);
     p->hub = hub_join (p, rate);
     if (!p->hub && b200m_r128_create (&p->bank, 0, 1, (float)rate, 0)) { delete p; return nullptr; }     // ebu->init (2, rate); 2 x TruePeakdsp (:189-196)
+    if (!p->hub && b200m_host_alloc ((void**)&p->stage, (size_t)2 * B200M_MAX_BLOCK * sizeof (float)) == 0) p->stage_cap = B200M_MAX_BLOCK;   // pinned staging for the largest cycle, allocated here so that run() never allocates (it stays lazy only as a fallback)
     return p;
 }
 

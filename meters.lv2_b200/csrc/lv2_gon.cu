@@ -93,6 +93,7 @@ LV2_Handle gon_instantiate (const LV2_Descriptor*, double rate, const char*, con
     if (rb) { rb->c0 = (float*)malloc (rbsize * sizeof (float)); rb->c1 = (float*)malloc (rbsize * sizeof (float)); rb->len = rbsize; rb->rp = 0; rb->wp = 0; }
     if (!rb || !rb->c0 || !rb->c1) { if (rb) { free (rb->c0); free (rb->c1); free (rb); } b200m_cor_destroy (p->bank); free (p); return nullptr; }
     g.rb = rb;
+    if (b200m_host_alloc ((void**)&p->stage, (size_t)2 * B200M_MAX_BLOCK * sizeof (float)) == 0) p->stage_cap = B200M_MAX_BLOCK;   // pinned staging for the largest cycle, allocated here so that run() never allocates (it stays lazy only as a fallback)
     return p;
 }
 

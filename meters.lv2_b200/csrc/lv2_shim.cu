@@ -235,6 +235,10 @@ LV2_Handle shim_instantiate (const LV2_Descriptor* d, double rate, const char*, 
         }
     }
     if (rc) { delete s; return nullptr; }                  // instantiate() -> NULL, as the reference does on failure
+    if (!s->hub) {   // pinned staging for the largest cycle, allocated here so that run() never allocates (it stays lazy only as a fallback)
+        if (b200m_host_alloc ((void**)&s->stage, (size_t)s->chn * B200M_MAX_BLOCK * sizeof (float)) == 0) s->stage_cap = B200M_MAX_BLOCK;
+        if (s->kind == K_SUR && b200m_host_alloc ((void**)&s->stage2, (size_t)8 * B200M_MAX_BLOCK * sizeof (float)) == 0) s->stage2_cap = B200M_MAX_BLOCK;
+    }
     return s;
 }
 

@@ -113,6 +113,7 @@ LV2_Handle stats_instantiate (const LV2_Descriptor* d, double rate, const char*,
     if (is_bim) { p->integrating = true; rc = b200m_bim_create (&p->bim, 0, 1, rate); }       // src/bitmeter.c:150-151
     else rc = b200m_sdh_create (&p->sdh, 0, 1, rate);
     if (rc) { delete p; return nullptr; }
+    if (b200m_host_alloc ((void**)&p->stage, (size_t)B200M_MAX_BLOCK * sizeof (float)) == 0) p->stage_cap = B200M_MAX_BLOCK;   // pinned staging for the largest cycle, allocated here so that run() never allocates (it stays lazy only as a fallback)
     return p;
 }
 

@@ -42,6 +42,7 @@ LV2_Handle xfer_instantiate (const LV2_Descriptor* d, double rate, const char*, 
     p->out.t_float = M (B200M_LV2_ATOM "Float"); p->out.t_int = M (B200M_LV2_ATOM "Int");
     p->rawstereo = M (MTR_URI "rawstereo"); p->audioleft = M (MTR_URI "audioleft"); p->audioright = M (MTR_URI "audioright");
     p->samplerate = M (MTR_URI "samplerate"); p->ui_on = M (MTR_URI "ui_on"); p->ui_off = M (MTR_URI "ui_off"); p->ui_state = M (MTR_URI "ui_state");
+    if (p->cor && b200m_host_alloc ((void**)&p->stage, (size_t)2 * B200M_MAX_BLOCK * sizeof (float)) == 0) p->stage_cap = B200M_MAX_BLOCK;   // pinned staging for the largest cycle, allocated here so that run() never allocates (it stays lazy only as a fallback)
     return p;
 }
 

@@ -43,6 +43,7 @@ struct TpkState {                           // SoA, one entry per channel
     unsigned* blk_max;                      // [n_chan] running |v| maximum of the block being processed (float bits), tpmax_kernel
     unsigned* grp_cnt;                      // [n_chan] finished chunks of the channel group starting at this channel, tpmax_kernel
     float* tmp;                             // [7][n_chan] serial-meter state between the slabs of one block (tpbal_kernel): z1 z2 m p kz1 kz2 kt
+    unsigned* sm_arr;                       // [256] process() CTAs that have arrived on each SM (phase stagger); NULL = no stagger
 };
 
 // The zita table depends only on (hl = 24, np = 4, fr = 1.0), not on the sample rate, so its 120 floats are universal
@@ -412,11 +413,27 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     float (*ob)[BAL ? OP : 4] = reinterpret_cast<float (*)[BAL ? OP : 4]> (tpk_smem + 2 * CH * XP);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int c0 = c_first + blockIdx.x * CH;
-    const int nchunks = (nfram + TC - 1) / TC;
+    // Chunk schedule.  Co-resident CTAs of process() start together and would run their FIR phases (issue-bound, every warp busy) and
+    // their serial phases (latency-bound, one or two warps busy) in lock step, leaving the SM idle through every serial phase.  Every
+    // second CTA to arrive on an SM therefore shortens its FIRST chunk to TC / 2 samples, which shifts all its later phases by half a
+    // period against its neighbours'.  Chunk boundaries stay multiples of 4 samples (the K-meter's stride) and every per-sample
+    // operation is unchanged, so the results do not depend on which CTAs shift.
+    __shared__ int s_lead;
+    if (BAL && st.sm_arr != nullptr) {
+        if (tid == 0) {
+            unsigned smid; asm ("mov.u32 %0, %%smid;" : "=r"(smid));
+            s_lead = (atomicAdd (st.sm_arr + (smid & 255u), 1u) & 1u) ? TC / 2 : 0;
+        }
+        __syncthreads ();
+    }
+    const int lead = (BAL && st.sm_arr != nullptr) ? s_lead : 0;
+    const int nchunks = (nfram + lead + TC - 1) / TC;
+    auto chunk_start = [&] (int c) { return max (0, c * TC - lead); };
+    auto chunk_end = [&] (int c) { return min (nfram, (c + 1) * TC - lead); };
 
     auto load_chunk = [&] (int c, int buf) {
         if (c < nchunks) {
-            const int s0 = c * TC;
+            const int s0 = chunk_start (c);
             if (aligned) {
 #pragma unroll
                 for (int idx = tid; idx < CH * GPC; idx += TPK_THREADS) {      // CH rows x GPC 16-byte pieces
@@ -483,8 +500,8 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
 
     for (int c = 0; c < nchunks; ++c) {
         const int buf = c & 1;
-        const int s0 = c * TC;
-        const int len = min (TC, nfram - s0);
+        const int s0 = chunk_start (c);
+        const int len = chunk_end (c) - s0;
         cp_async_wait<0> ();
         __syncthreads ();                                   // chunk c (and its 48-sample prefix) is in xs[buf]
         // prefix of the next chunk = last 48 samples of this one; start the next load
@@ -1401,6 +1418,7 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     h->split = 0;
     if (const char* v = getenv ("B200M_TPK_SPLIT")) { const int q = atoi (v); h->split = q >= 2 ? 1 : (q == 1 ? n_chan >= 512 : 0); }
     A ((void**)&h->st.tmp, 7 * n * sizeof (float));
+    { const char* v = getenv ("B200M_TPK_STAGGER"); if (!(v && atoi (v) == 0)) A ((void**)&h->st.sm_arr, 256 * sizeof (unsigned)); }
     if ((flags & B200M_TPK_TRUEPEAK) && h->split) {
         // slab length: two slabs of |out| (16 B per sample and channel) within 64 MB, so that the ballistics kernel reads them from L2
         uint32_t slab = 64;
@@ -1445,7 +1463,7 @@ int b200m_tpk_destroy (b200m_tpk* h)
     DeviceGuard g (h->device);
     cudaDeviceSynchronize ();
     void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms,
-                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt, h->st.tmp, h->d_scr};
+                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt, h->st.tmp, h->d_scr, h->st.sm_arr};
     for (void* p : ps) cudaFree (p);
     if (h->sb) cudaStreamDestroy (h->sb);
     for (int i = 0; i < 2; ++i) { if (h->ev_fir[i]) cudaEventDestroy (h->ev_fir[i]); if (h->ev_bal[i]) cudaEventDestroy (h->ev_bal[i]); }

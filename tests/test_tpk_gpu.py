@@ -8,18 +8,18 @@ import _signals as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["shortcut", "full", "slabs", "fused"])
+@pytest.fixture(autouse=True, params=["shortcut", "full", "slabs", "nostagger"])
 def phase0_mode(request, monkeypatch):
     """every test runs four times: with the exact phase-0 shortcut of the FIR (default) and with phase 0 always evaluated; with
-    process() cut into 128-sample slabs (the FIR / ballistics pipeline of large banks: small banks would otherwise run one slab per
-    block); and with the fused one-kernel form of process() (B200M_TPK_SPLIT=0)."""
+    process() as the opt-in FIR / ballistics slab pipeline cut into 128-sample slabs; and with the phase stagger of co-resident
+    process() CTAs switched off (every CTA then uses the same chunk boundaries)."""
     monkeypatch.delenv("B200M_TPK_ELIDE0", raising=False)
     if request.param == "full":
         monkeypatch.setenv("B200M_TPK_ELIDE0", "0")
     elif request.param == "slabs":
         monkeypatch.setenv("B200M_TPK_SLAB", "128"); monkeypatch.setenv("B200M_TPK_SPLIT", "2")
-    elif request.param == "fused":
-        monkeypatch.setenv("B200M_TPK_SPLIT", "0")
+    elif request.param == "nostagger":
+        monkeypatch.setenv("B200M_TPK_STAGGER", "0")
     return request.param
 
 
