@@ -417,7 +417,9 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
     // their serial phases (latency-bound, one or two warps busy) in lock step, leaving the SM idle through every serial phase.  Every
     // second CTA to arrive on an SM therefore shortens its FIRST chunk to TC / 2 samples, which shifts all its later phases by half a
     // period against its neighbours'.  Chunk boundaries stay multiples of 4 samples (the K-meter's stride) and every per-sample
-    // operation is unchanged, so the results do not depend on which CTAs shift.
+    // operation is unchanged, so the results do not depend on which CTAs shift.  MEASURED (round 2, tolerance-mode FIR where the two
+    // phases are of similar length): 174.6 us with, 173.0 us without -- no gain, as in round 1 with the exact FIR; the CTAs evidently
+    // do not stay in lock step on their own.  Opt-in (B200M_TPK_STAGGER=1), covered by tests.
     __shared__ int s_lead;
     if (BAL && st.sm_arr != nullptr) {
         if (tid == 0) {
@@ -1418,7 +1420,7 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     h->split = 0;
     if (const char* v = getenv ("B200M_TPK_SPLIT")) { const int q = atoi (v); h->split = q >= 2 ? 1 : (q == 1 ? n_chan >= 512 : 0); }
     A ((void**)&h->st.tmp, 7 * n * sizeof (float));
-    { const char* v = getenv ("B200M_TPK_STAGGER"); if (!(v && atoi (v) == 0)) A ((void**)&h->st.sm_arr, 256 * sizeof (unsigned)); }
+    { const char* v = getenv ("B200M_TPK_STAGGER"); if (v && atoi (v) != 0) A ((void**)&h->st.sm_arr, 256 * sizeof (unsigned)); }      // opt-in: measured no gain
     if ((flags & B200M_TPK_TRUEPEAK) && h->split) {
         // slab length: two slabs of |out| (16 B per sample and channel) within 64 MB, so that the ballistics kernel reads them from L2
         uint32_t slab = 64;

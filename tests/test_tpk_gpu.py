@@ -8,18 +8,18 @@ import _signals as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["shortcut", "full", "slabs", "nostagger"])
+@pytest.fixture(autouse=True, params=["shortcut", "full", "slabs", "stagger"])
 def phase0_mode(request, monkeypatch):
     """every test runs four times: with the exact phase-0 shortcut of the FIR (default) and with phase 0 always evaluated; with
-    process() as the opt-in FIR / ballistics slab pipeline cut into 128-sample slabs; and with the phase stagger of co-resident
-    process() CTAs switched off (every CTA then uses the same chunk boundaries)."""
+    process() as the opt-in FIR / ballistics slab pipeline cut into 128-sample slabs; and with the opt-in phase stagger of co-resident
+    process() CTAs (every second CTA of an SM shortens its first chunk)."""
     monkeypatch.delenv("B200M_TPK_ELIDE0", raising=False)
     if request.param == "full":
         monkeypatch.setenv("B200M_TPK_ELIDE0", "0")
     elif request.param == "slabs":
         monkeypatch.setenv("B200M_TPK_SLAB", "128"); monkeypatch.setenv("B200M_TPK_SPLIT", "2")
-    elif request.param == "nostagger":
-        monkeypatch.setenv("B200M_TPK_STAGGER", "0")
+    elif request.param == "stagger":
+        monkeypatch.setenv("B200M_TPK_STAGGER", "1")
     return request.param
 
 
