@@ -388,8 +388,15 @@ def other_configs(torch, dist, B, x, K, W, hbm_peak, ws, local):
             sp.process_ptr(blk(s), stride, NFRAM)
         ms = timed_loop(torch, dist, 1, lambda s: sp.process_ptr(blk(s), stride, NFRAM), k4)
         fr = 4096 * NFRAM
+        c4x = {"frames_per_s": fr * k4 / (ms * 1e-3), "ms_per_block": ms / k4, "hbm_frac": fr * 8 * k4 / (ms * 1e-3) / 1e9 / hbm_peak,
+               "fp64_frac": fr * 30 * 39.0 * k4 / (ms * 1e-3) / 1e9 / fp64_peak, "fp64_ops_per_frame_and_band": 39}
+        sp.set_precision(B.PREC_FMA)                          # fused multiply-adds: 25 fp64 instructions per frame and band, levels within +-1e-4 dB
+        for s in range(2):
+            sp.process_ptr(blk(s), stride, NFRAM)
+        ms = timed_loop(torch, dist, 1, lambda s: sp.process_ptr(blk(s), stride, NFRAM), k4)
         cfg["C4_spectr30_4096st"] = {"frames_per_s": fr * k4 / (ms * 1e-3), "ms_per_block": ms / k4, "hbm_frac": fr * 8 * k4 / (ms * 1e-3) / 1e9 / hbm_peak,
-                                     "fp64_frac": fr * 30 * 39.0 * k4 / (ms * 1e-3) / 1e9 / fp64_peak, "fp64_peak_glops": fp64_peak}
+                                     "fp64_frac": fr * 30 * 25.0 * k4 / (ms * 1e-3) / 1e9 / fp64_peak, "fp64_ops_per_frame_and_band": 25,
+                                     "precision": "B200M_PREC_FMA (band levels within +-1e-4 dB)", "fp64_peak_glops": fp64_peak, "bit_exact": c4x}
         del sp
 
     # C5: 2048 stereo phasewheel 2048-pt FFT + Stcorr in total (unit: stereo frames)

@@ -72,6 +72,7 @@ _PROTOS = {
     "b200m_lv2_gon_layout": (C.c_int, [_v, C.c_int]),
     "b200m_ebu_clear": (C.c_int, [_v, C.c_int32, _v]),
     "b200m_tpk_clear": (C.c_int, [_v, C.c_int32, _v]),
+    "b200m_spec_set_precision": (C.c_int, [_v, C.c_int]),
     "b200m_cor_set_precision": (C.c_int, [_v, C.c_int]),
     "b200m_pw_debug_capture": (C.c_int, [_v, C.c_int]),
     "b200m_pw_attach_cor": (C.c_int, [_v, _v]),
@@ -630,6 +631,10 @@ class Spectr30(_Bank):
             p, s, rows, n = _dev_ptr(x)
             assert rows == self.n_inst * self.nchan
             _ck(lib().b200m_spec_process_device(self.h, p, s, n, speed, reset, _stream_ptr(stream)))
+
+    def set_precision(self, mode):
+        """PREC_EXACT: ports bit-identical to the reference; PREC_FMA: fused multiply-adds, band levels within +-1e-4 dB"""
+        _ck(lib().b200m_spec_set_precision(self.h, int(mode)))
 
     def process_ptr(self, ptr, stride, nfram, speed=1.0, reset=-4.0, stream=None):
         _ck(lib().b200m_spec_process_device(self.h, C.c_void_p(ptr), stride, nfram, speed, reset, _stream_ptr(stream)))

@@ -23,6 +23,10 @@ constexpr int SPEC_WARPS = 4;             // instances per CTA
 struct SpecRun { float omega; int ac0; int clear_max; int reinit_gui; int nchan; };
 
 // coef[band][16]: stage0 {b0,b1,b2,a1,a2}, stages 1..5 {a1,a2}; pad to 16
+// FMA = B200M_PREC_FMA: the same transposed-DF-II cascade with fused multiply-adds (25 instead of 39 fp64 instructions per frame and
+// band).  Band levels feed no integer result and the filters run in double precision, so the ports move by ~1e-12 dB, far inside the
+// contract's +-1e-4 dB (tests/test_cor_spec_gpu.py::test_spec_fma_mode_within_tolerance).
+template <bool FMA>
 __global__ void __launch_bounds__ (SPEC_WARPS * 32)
 spec_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram, SpecRun rp, const double* __restrict__ coef,
              double* __restrict__ zst /* [inst][12][32] */, float* __restrict__ valf /* [inst][2][32] */, float* __restrict__ ports /* [inst][60] */)
@@ -85,6 +89,21 @@ spec_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram,
 #pragma unroll 2
         for (int j = 0; j < len; ++j) {
             double x = dd[w][j];
+            if (FMA) {
+                {
+                    const double y = __fma_rn (b0, x, z1[0]);
+                    z1[0] = __fma_rn (b1, x, __fma_rn (-a1[0], y, z2[0]));
+                    z2[0] = __fma_rn (-a2[0], y, __dmul_rn (b2, x));
+                    x = y;
+                }
+#pragma unroll
+                for (int s = 1; s < 6; ++s) {
+                    const double y = __dadd_rn (x, z1[s]);
+                    z1[s] = __fma_rn ((s & 1) ? -2.0 : 2.0, x, __fma_rn (-a1[s], y, z2[s]));
+                    z2[s] = __fma_rn (-a2[s], y, x);
+                    x = y;
+                }
+            } else {
             // stage 0: general numerator (carries the pass-band normalisation, spectr.c:191-194)
             {
                 const double y = __dadd_rn (__dmul_rn (b0, x), z1[0]);
@@ -101,6 +120,7 @@ spec_kernel (const float* __restrict__ in, size_t stride, int n_inst, int nfram,
                 z1[s] = __dadd_rn (u, z2[s]);
                 z2[s] = __dsub_rn (x, __dmul_rn (a2[s], y));
                 x = y;
+            }
             }
             const float v = __double2float_rn (x);
             const float sq = __fmul_rn (v, v);
@@ -143,6 +163,7 @@ struct b200m_spec {
     double W[30][6][6];                                   // a0 a1 a2 b0 b1 b2 per stage, as the reference stores them
     double *d_coef = nullptr, *d_z = nullptr; float *d_val = nullptr, *d_ports = nullptr;
     cudaStream_t own = nullptr; HostStage stage; bool last_host = false;
+    int fma = 0;                                          // B200M_PREC_FMA
 };
 
 typedef std::complex<double> cplx;
@@ -239,7 +260,9 @@ static int spec_process (b200m_spec* h, const float* d_in, size_t stride, uint32
     rp.omega = h->omega;
     rp.ac0 = (int)(h->frames & 1);
     h->frames += nfram;
-    spec_kernel<<<(h->n_inst + SPEC_WARPS - 1) / SPEC_WARPS, SPEC_WARPS * 32, 0, st>>> (
+    if (h->fma) spec_kernel<true><<<(h->n_inst + SPEC_WARPS - 1) / SPEC_WARPS, SPEC_WARPS * 32, 0, st>>> (
+        d_in, stride, (int)h->n_inst, (int)nfram, rp, h->d_coef, h->d_z, h->d_val, h->d_ports);
+    else spec_kernel<false><<<(h->n_inst + SPEC_WARPS - 1) / SPEC_WARPS, SPEC_WARPS * 32, 0, st>>> (
         d_in, stride, (int)h->n_inst, (int)nfram, rp, h->d_coef, h->d_z, h->d_val, h->d_ports);
     B200M_LAUNCHED (1);
     B200M_CUDA (cudaGetLastError ());
@@ -318,6 +341,13 @@ int b200m_spec_process_host (b200m_spec* h, const float* in, size_t stride, uint
                                    (size_t)nfram * sizeof (float), nch, cudaMemcpyHostToDevice, h->own));
     h->last_host = true;
     return spec_process (h, h->stage.d, h->stage.cap, nfram, speed, reset, h->own);
+}
+
+int b200m_spec_set_precision (b200m_spec* h, int mode)
+{
+    if (!h || (mode != B200M_PREC_EXACT && mode != B200M_PREC_FMA)) return set_err (B200M_E_INVAL, "bad argument");
+    h->fma = mode == B200M_PREC_FMA;                       // takes effect with the next process call
+    return 0;
 }
 
 int b200m_spec_results (b200m_spec* h, float* out60, void* stream)

@@ -76,6 +76,29 @@ def test_spec_bit_exact(n_inst, nchan, blocks):
     assert np.array_equal(u32(gp), u32(op)), float(np.abs(gp - op).max())      # dB ports, glibc-exact log10f
 
 
+@pytest.mark.parametrize("n_inst,nchan,blocks", [(9, 2, [1024] * 24), (2, 2, [64] * 8 + [480, 8192, 1, 3, 1023, 777])])
+def test_spec_fma_mode_within_tolerance(n_inst, nchan, blocks):
+    """B200M_PREC_FMA: fused multiply-adds in the fp64 biquad cascade.  Band levels and maxima (dB ports) within the contract's
+    +-1e-4 dB of the reference; the filters run in double precision, so the measured deviation is ~1e-6 dB (float32 port rounding)"""
+    import torch
+    import meters_lv2_b200 as B
+    x = S.white(nchan * n_inst, sum(blocks), seed=35)
+    x[1] *= 1e-3
+    g = B.Spectr30(n_inst, nchan); g.set_precision(B.PREC_FMA); o = O.Spectr30(n_inst, nchan)
+    xd = torch.from_numpy(x).cuda()
+    pos, worst = 0, 0.0
+    for n in blocks:
+        g.process(xd[:, pos:pos + n]); o.process(np.ascontiguousarray(x[:, pos:pos + n]), nthreads=8)
+        pos += n
+        gp, op = g.read().astype(np.float64), o.read().astype(np.float64)
+        live = op > -100
+        assert np.array_equal(live, gp > -100)
+        worst = max(worst, float(np.abs(gp[live] - op[live]).max()))
+    assert worst <= 1e-4, worst
+    z, v, m = g.state(0); oz, ov, om = o.state(0)
+    assert np.allclose(z, oz, rtol=1e-9, atol=1e-18 + 1e-9 * np.abs(oz).max())
+
+
 def test_spec_speed_and_peak_reset_controls():
     import torch
     import meters_lv2_b200 as B
