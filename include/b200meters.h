@@ -185,6 +185,9 @@ int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float
  * only kept when enabled with b200m_tpk_debug_capture(h,1): FIR bit-exactness tests */
 int b200m_tpk_debug_capture (b200m_tpk* h, int enable);
 int b200m_tpk_debug_upsampled (b200m_tpk* h, uint32_t chan, float* out, uint32_t n_out, void* stream);
+/* launch timeline of the opt-in slab pipeline (B200M_TPK_SPLIT=2 with B200M_TPK_TIMELINE=1): up to n slots of
+ * {first CTA start, last CTA end} in %globaltimer ns, two slots (filter, ballistics) per slab; returns the count, -1 = off */
+int b200m_tpk_debug_timeline (b200m_tpk* h, unsigned long long* out, int n);
 
 /* ======================================================================================
  * EBUr128 plugin cycle — the audio part of ebur128_run (src/ebulv2.cc:341-367) for N stereo

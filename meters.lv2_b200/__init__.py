@@ -84,6 +84,7 @@ _PROTOS = {
     "b200m_tpk_coeffs": (C.c_int, [_v, _v, _v, _v]),
     "b200m_tpk_state": (C.c_int, [_v, _v, _v, _v, _v, _v, _v, _v]),
     "b200m_tpk_debug_capture": (C.c_int, [_v, C.c_int]),
+    "b200m_tpk_debug_timeline": (C.c_int, [_v, _v, C.c_int]),
     "b200m_tpk_debug_upsampled": (C.c_int, [_v, C.c_uint32, _v, C.c_uint32, _v]),
     # EBUr128 plugin cycle
     "b200m_r128_create": (C.c_int, [C.POINTER(_v), C.c_int, C.c_uint32, C.c_float, C.c_int]),

@@ -294,6 +294,13 @@ B200M_DEV void fir16 (const float (&w)[52], const float* xw, float (&o)[16], con
 #ifndef B200M_TPK_SYM
 #define B200M_TPK_SYM 1
 #endif
+B200M_DEV float fmax3 (float a, float b, float c)                    // fmaxf (fmaxf (a, b), c) as one FMNMX3: NaN operands ignored
+{
+    float d;
+    asm ("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 B200M_DEV float max3_abs (float a, float b, float c)                 // max (|a|, |b|, |c|), NaN operands ignored like fmaxf
 {
     float d;
@@ -581,23 +588,54 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
 
         if (is_tp) {
             // PPM ballistics over the 4*len oversampled magnitudes (truepeakdsp.cc:57-84); this lane owns one of the
-            // two attack filters of channel tch
+            // two attack filters of channel tch.  Samples are taken four at a time (the tile's float4 slots i * GPC + g of group g
+            // sit at constant offsets from one moving base, and the next group's loads are issued before this group's chain).
             const float4* b4 = reinterpret_cast<const float4*> (&ob[BAL ? wbase + tch : 0][0]);
-            for (int j = 0; j < len; ++j) {
-                const float4 v4 = b4[(j & 3) * GPC + (j >> 2)];
-                z = __fmul_rn (z, prm.w3);
-                const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
+            // tolerance mode: z <- max (z, (1 - w) z + w v) is `if (v > z) z += w (v - z)` in real arithmetic; with w' = 1 - fl (1 - w)
+            // the pair (1 - w, w') sums to one exactly, so a settled filter sits on its input, and the time constant moves by < 2e-6
+            // relative.  Two dependent instructions per oversampled value instead of four: 41 cycles per input sample instead of 102.
+            const float omw = __fsub_rn (1.0f, wf), wq = __fsub_rn (1.0f, omw), omw3 = __fmul_rn (omw, prm.w3);
+            auto step = [&] (const float4 v4) {
+                if (FMA) {
+                    const float zd = __fmul_rn (z, prm.w3);
+                    z = fmaxf (zd, fmaf (omw3, z, __fmul_rn (wq, v4.x)));
+                    z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.y)));
+                    z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.z)));
+                    z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.w)));
+                } else {
+                    z = __fmul_rn (z, prm.w3);
                     // (a predicate-free form, z += w * max (v - z, 0), is bit-identical but no faster: a micro-probe measured 102 vs 103
                     // cycles per input sample for this chain of 17 dependent instructions, 87 without the shuffle and the maxima)
-                    const float v = vv[i];
-                    if (v > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v, z)));
-                    p = fmaxf (p, v);                       // == `if (v > p) p = v`: p is never NaN, a NaN v leaves it unchanged
+                    if (v4.x > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.x, z)));
+                    if (v4.y > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.y, z)));
+                    if (v4.z > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.z, z)));
+                    if (v4.w > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.w, z)));
                 }
+                // == four times `if (v > p) p = v`: p is never NaN, NaN values leave it unchanged (3-input FMNMX ignores NaN operands)
+                p = fmax3 (p, fmax3 (v4.x, v4.y, v4.z), v4.w);
                 const float t = __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16));    // z1 + z2
-                if (t > m) m = t;
+                m = fmaxf (m, t);                           // == `if (t > m) m = t`: m is never NaN, a NaN t leaves it unchanged
+            };
+            const int ng = len >> 2;
+            // two register sets in turn (no copies): group g + 1 is loaded while group g is on the chain
+            float4 va[4], vb[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) va[i] = b4[i * GPC];
+#pragma unroll 1
+            for (int g = 0; g < ng; g += 2) {
+                const int g1 = min (g + 1, GPC - 1), g2 = min (g + 2, GPC - 1);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) vb[i] = b4[i * GPC + g1];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) step (va[i]);
+                if (g + 1 < ng) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) va[i] = b4[i * GPC + g2];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) step (vb[i]);
+                }
             }
+            for (int j = 4 * ng; j < len; ++j) step (b4[(j & 3) * GPC + (j >> 2)]);       // a block that does not end on a multiple of 4
         }
         if (is_km) {
             // kmeterdsp.cc:80-97: z1 every sample, z2 every 4th; the block's last n%4 samples are ignored
@@ -611,9 +649,12 @@ tpk_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan
                 for (int i = 0; i < 4; ++i) {
                     const float s = __fmul_rn (vv[i], vv[i]);
                     if (kt < s) kt = s;
-                    kz1 = __fadd_rn (kz1, __fmul_rn (prm.omega, __fsub_rn (s, kz1)));
+                    // tolerance mode keeps omega itself (1 - omega would move the 9.72 rad/s corner by 3e-4) and contracts mul + add
+                    if (FMA) kz1 = fmaf (prm.omega, __fsub_rn (s, kz1), kz1);
+                    else kz1 = __fadd_rn (kz1, __fmul_rn (prm.omega, __fsub_rn (s, kz1)));
                 }
-                kz2 = __fadd_rn (kz2, __fmul_rn (om4, __fsub_rn (kz1, kz2)));
+                if (FMA) kz2 = fmaf (om4, __fsub_rn (kz1, kz2), kz2);
+                else kz2 = __fadd_rn (kz2, __fmul_rn (om4, __fsub_rn (kz1, kz2)));
             }
         }
         if (dr_warp) {
@@ -890,11 +931,26 @@ tpmax_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
 // covered by tests/test_tpk_gpu.py (fixture mode "slabs"); the fused kernel stays the default.
 constexpr int TPF_CH = 8, TPF_TC = 256;
 
+// debugging aid of the slab pipeline (B200M_TPK_TIMELINE=1): every thread 0 stamps %globaltimer into [slot] = {min start, max end}
+struct TimelineProbe {
+    unsigned long long* p;
+    B200M_DEV TimelineProbe (unsigned long long* tl, int slot) : p (tl ? tl + 2 * slot : nullptr)
+    {
+        if (p && threadIdx.x == 0) { unsigned long long t; asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMin (p, t); }
+    }
+    B200M_DEV ~TimelineProbe ()
+    {
+        if (p && threadIdx.x == 0) { unsigned long long t; asm volatile ("mov.u64 %0, %%globaltimer;" : "=l"(t)); atomicMax (p + 1, t); }
+    }
+};
+
 template <bool IMM, bool FMA>
 __global__ void __launch_bounds__ (TPK_THREADS)
 tpfir_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int s_begin, int s_len, int aligned, int elide0,
-              TpkState st, float4* __restrict__ scr, int scr_pitch /* samples per channel row of the slab */, float* __restrict__ dbg)
+              TpkState st, float4* __restrict__ scr, int scr_pitch /* samples per channel row of the slab */, float* __restrict__ dbg,
+              unsigned long long* __restrict__ tl /* timeline probe: [slot][2] = first CTA start, last CTA end (globaltimer ns); NULL = off */, int tl_slot)
 {
+    TimelineProbe tlp (tl, tl_slot);
     constexpr int CH = TPF_CH, TC = TPF_TC;
     constexpr int XP = 48 + TC + 4;                           // LPR = 16 lanes per row: any pitch is conflict free
     constexpr int GPC = TC / 4, LPR = TPK_THREADS / CH;       // 64 groups per row, 16 lanes per row: up to four items per thread
@@ -994,8 +1050,10 @@ constexpr int TPB_STAGES = 3;
 template <bool KM, bool DR>
 __global__ void __launch_bounds__ (64, 24)                   // <= 42 registers: seven of these CTAs must leave the register file to the FIR kernel's
 tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nch_total, int nfram,
-              int s_begin, int s_len, int first, int last, int aligned, int tp_on, TpkParams prm, TpkState st, TpkDr dr)
+              int s_begin, int s_len, int first, int last, int aligned, int tp_on, TpkParams prm, TpkState st, TpkDr dr,
+              unsigned long long* __restrict__ tl, int tl_slot)
 {
+    TimelineProbe tlp (tl, tl_slot);
     __shared__ __align__ (16) float tile[TPB_STAGES][16 * TPB_PITCH];       // |out| tiles (warp 0)
     __shared__ __align__ (16) float xin[TPB_STAGES][16 * (TPB_TILE + 4)];   // input tiles (warp 1)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1229,6 +1287,7 @@ struct b200m_tpk {
     int elide0 = 0;                         // phase 0 of the table is the unit-tap delay fir16's guard assumes
     int split = 1;                          // process() with true peak as the FIR / ballistics slab pipeline (tpfir_kernel + tpbal_kernel); B200M_TPK_SPLIT=0: fused tpk_kernel<16,64>
     float4* d_scr = nullptr; uint32_t slab = 0;       // two slabs of |out|: [2][n_chan][slab] float4
+    unsigned long long* d_tl = nullptr; int tl_next = 0;   // B200M_TPK_TIMELINE=1: [4096][2] globaltimer stamps of the pipeline's launches (managed memory)
     cudaStream_t sb = nullptr; cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_bal[2] = {nullptr, nullptr};
     int wide = 0, wide_min = 64 * 148;      // process() with 64-channel CTAs: opt-in (B200M_TPK_WIDE=1, or =<min channels of a bank>); measured slower, see below
     int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
@@ -1324,17 +1383,18 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
                 float4* scr = h->d_scr + (size_t)b * h->n_chan * h->slab + (size_t)cf * h->slab;
                 if (sidx >= 2) B200M_CUDA (cudaStreamWaitEvent (st, h->ev_bal[b], 0));          // the slab buffer is free again
                 const int nch = (sl_len + TPF_TC - 1) / TPF_TC;
-                if (h->imm && h->fma) tpfir_kernel<true, true><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg);
-                else if (h->imm) tpfir_kernel<true, false><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg);
-                else tpfir_kernel<false, false><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg);
+                if (h->imm && h->fma) tpfir_kernel<true, true><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg, h->d_tl, h->tl_next);
+                else if (h->imm) tpfir_kernel<true, false><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg, h->d_tl, h->tl_next);
+                else tpfir_kernel<false, false><<<ngrp * nch, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, sb0, sl_len, aligned, h->elide0, h->st, scr, (int)h->slab, h->d_dbg, h->d_tl, h->tl_next);
                 B200M_CUDA (cudaEventRecord (h->ev_fir[b], st));
                 B200M_CUDA (cudaStreamWaitEvent (h->sb, h->ev_fir[b], 0));
                 const int first = sidx == 0, last = sidx == nslab - 1;
-                if (km && drp.rms_sum) tpbal_kernel<true, true><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp);
-                else if (km) tpbal_kernel<true, false><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp);
-                else tpbal_kernel<false, false><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp);
+                if (km && drp.rms_sum) tpbal_kernel<true, true><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp, h->d_tl, h->tl_next + 1);
+                else if (km) tpbal_kernel<true, false><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp, h->d_tl, h->tl_next + 1);
+                else tpbal_kernel<false, false><<<nb16, 64, 0, h->sb>>> (scr, (int)h->slab, d_in, stride, cf, ce, (int)h->n_chan, (int)nfram, sb0, sl_len, first, last, aligned, 1, prm, h->st, drp, h->d_tl, h->tl_next + 1);
                 B200M_CUDA (cudaEventRecord (h->ev_bal[b], h->sb));
                 B200M_LAUNCHED (2);
+                if (h->d_tl) h->tl_next = (h->tl_next + 2) % 4096;
             }
             B200M_CUDA (cudaStreamWaitEvent (st, h->ev_bal[(nslab - 1) & 1], 0));              // the caller's stream sees the block complete
             if (nslab >= 2) B200M_CUDA (cudaStreamWaitEvent (st, h->ev_bal[(nslab - 2) & 1], 0));
@@ -1427,6 +1487,10 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
         while (slab < B200M_MAX_BLOCK && (size_t)2 * n * (2 * slab) * 16 <= ((size_t)64 << 20)) slab *= 2;
         if (const char* v = getenv ("B200M_TPK_SLAB")) { const int q = atoi (v); if (q >= 64 && q <= (int)B200M_MAX_BLOCK && q % 64 == 0) slab = (uint32_t)q; }
         h->slab = slab;
+        if (const char* v = getenv ("B200M_TPK_TIMELINE")) if (atoi (v) && e == cudaSuccess) {
+            e = cudaMallocManaged ((void**)&h->d_tl, 4096 * 2 * sizeof (unsigned long long));
+            if (e == cudaSuccess) for (int i = 0; i < 4096; ++i) { h->d_tl[2 * i] = ~0ull; h->d_tl[2 * i + 1] = 0ull; }
+        }
         A ((void**)&h->d_scr, (size_t)2 * n * slab * sizeof (float4));
         // the ballistics kernels are latency-bound and small: highest stream priority, so that SM slots freed by retiring FIR CTAs go to
         // them first (at equal priority the FIR grid keeps the register file full and lets one ballistics CTA per SM in at a time)
@@ -1465,7 +1529,7 @@ int b200m_tpk_destroy (b200m_tpk* h)
     DeviceGuard g (h->device);
     cudaDeviceSynchronize ();
     void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms,
-                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt, h->st.tmp, h->d_scr, h->st.sm_arr};
+                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt, h->st.tmp, h->d_scr, h->st.sm_arr, h->d_tl};
     for (void* p : ps) cudaFree (p);
     if (h->sb) cudaStreamDestroy (h->sb);
     for (int i = 0; i < 2; ++i) { if (h->ev_fir[i]) cudaEventDestroy (h->ev_fir[i]); if (h->ev_bal[i]) cudaEventDestroy (h->ev_bal[i]); }
@@ -1647,6 +1711,16 @@ int b200m_tpk_state (b200m_tpk* h, float* tp_m, float* tp_p, float* tp_z1, float
     }
     B200M_CUDA (cudaStreamSynchronize (st));
     return 0;
+}
+
+// timeline of the slab pipeline's launches (B200M_TPK_TIMELINE=1): n slots of {first CTA start, last CTA end} in globaltimer ns
+int b200m_tpk_debug_timeline (b200m_tpk* h, unsigned long long* out, int n)
+{
+    if (!h || !h->d_tl) return -1;
+    cudaDeviceSynchronize ();
+    const int m = n < h->tl_next ? n : h->tl_next;
+    memcpy (out, h->d_tl, (size_t)m * 2 * sizeof (unsigned long long));
+    return m;
 }
 
 int b200m_tpk_debug_capture (b200m_tpk* h, int enable)

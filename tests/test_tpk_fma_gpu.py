@@ -1,7 +1,8 @@
 """GPU parity of the tolerance mode of the true-peak FIR (B200M_PREC_FMA, include/b200meters.h).
 
-north_star: float outputs within +-1e-4 dB of the reference, integer results bit-exact.  The FMA mode changes only the
-4x polyphase FIR (zita-resampler/resampler.cc:213-230); the tolerance is written below as TOL_DB and checked on
+north_star: float outputs within +-1e-4 dB of the reference, integer results bit-exact.  The FMA mode changes the
+4x polyphase FIR (zita-resampler/resampler.cc:213-230) and, in the fused process() kernel, the attack filters of the true-peak
+ballistics (truepeakdsp.cc:57-84) and the K-meter's RMS filters (kmeterdsp.cc:80-97); the tolerance is written below as TOL_DB and checked on
  * the raw 4x stream against zita-resampler's own output (relative to the block peak, which is what a peak meter reads),
  * TruePeakdsp::process_max / process readings (jmeters/truepeakdsp.cc:41-124) in dB,
  * the EBUr128 cycle: dBTP hold within TOL_DB while every EBU float AND both histograms stay bit-identical.
@@ -79,14 +80,17 @@ def test_fma_readings_within_tolerance(mode):
         ot.process(blk, mode=mode, nthreads=8); ok.process(blk, nthreads=8)
         g.process(xd[:, b * 1024:(b + 1) * 1024], tp_mode=mode)
         r = g.read(); m, p = ot.read(); rms, pk = ok.read()
-        assert np.array_equal(u32(r["km_rms"]), u32(rms)) and np.array_equal(u32(r["km_peak"]), u32(pk)), "the K-meter does not depend on the FIR"
-        for got, ref in ((r["tp_m"], m),) + (((r["tp_p"], p),) if mode == 0 else ()):
+        # the K-meter's peak is a maximum of squares: exact in either mode; its two RMS filters contract mul + add in the fused
+        # process() kernel of the tolerance mode (the slab pipeline and process_max banks keep the exact ballistics)
+        assert np.array_equal(u32(r["km_peak"]), u32(pk))
+        for got, ref in ((r["tp_m"], m), (r["km_rms"], rms)) + (((r["tp_p"], p),) if mode == 0 else ()):
             nz = ref > 0
             assert np.array_equal(got[~nz], ref[~nz])
             d = np.abs(db(got[nz]) - db(ref[nz])).max()
             worst = max(worst, d)
     assert worst <= TOL_DB, worst
-    assert worst <= 2e-5, "measured 2e-6 dB on this input: something regressed (%g)" % worst
+    print("worst deviation %.3g dB" % worst)
+    assert worst <= 5e-5, "measured <= 1e-5 dB on this input: something regressed (%g)" % worst
 
 
 def test_fma_r128_cycle_histograms_stay_bit_exact():
