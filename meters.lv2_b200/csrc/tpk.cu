@@ -32,6 +32,9 @@ __constant__ float c_tp_tab[120];           // zita table for hl=24, np=4, fr=1.
 struct TpkParams {
     float w1, w2, w3, g;                    // TruePeakdsp::init (truepeakdsp.cc:153-157)
     float omega, fall; int hold;            // Kmeterdsp::init (kmeterdsp.cc:47-54), _fall for this n (:65-70)
+    // tolerance mode, four K-meter steps at once: z1 <- z1 - kc4 z1 + (kq[0] s0 + kq[1] s1 + kq[2] s2 + kq[3] s3) with a = 1 - omega,
+    // kq[i] = omega a^(3-i), kc4 = 1 - a^4 (all rounded once from double: the corner frequency keeps its 1e-7 relative accuracy)
+    float kq[4], kc4;
 };
 
 struct TpkState {                           // SoA, one entry per channel
@@ -1246,6 +1249,216 @@ tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __rest
     }
 }
 
+// ---- process() in tolerance mode: the FIR warps and the serial warp of a CTA decoupled ---------------------------------------
+// ncu on the fused tpk_kernel<16,64> (tolerance mode, 16384 x 1024): 46 % of all warp samples sit on the barrier that ends the serial
+// phase -- three of a CTA's four warps wait while the ballistics warp works through its ~21 instructions per input sample, each of
+// which has to win the scheduler against the FIR warps of the other six resident CTAs (measured ~190 cycles per sample where the
+// dependency chain alone needs ~45).  The serial stream is not short either: 23 M of the kernel's 117 M warp instructions.  So the
+// serial work is a fourth ROLE here, as heavy as a FIR warp's share, and never waited for:
+//   * three FIR warps (96 threads = 16 rows x 6 groups of 4 samples: one group per thread and 24-sample chunk) produce |out| tiles
+//     into a two-deep ring and never wait for the serial warp unless it falls two chunks behind;
+//   * one serial warp (lane = filter * 16 + channel, as in the fused kernel) consumes the tiles; it also runs the K-meter, whose
+//     four steps per group are folded into one affine step from partial sums the FIR threads compute from their register window
+//     (z1 <- z1 - c4 z1 + S, tolerance mode only: the exact mode keeps the sequential roundings and the fused kernel);
+//   * the serial warp is warp (blockIdx & 3), so that every SM sub-partition gets the same mix of roles;
+//   * the input tile is a sliding window (history + four chunk slots in one row, the 48-sample prefix copied once per lap) instead of
+//     two buffers with a prefix copy per chunk; chunk c + 1 is loaded (cp.async, one 16-byte piece per thread) under chunk c's FIR.
+//   * the peak-sample reading p is a plain maximum, so the FIR thread reduces its 16 values and the serial warp takes one per group.
+// Per CTA and chunk: FIR warps 3 x ~600 warp instructions, serial warp ~24 x 19 = 460.  128 threads, 64 registers, 26 KB of shared
+// memory: seven CTAs per SM as before (1024 CTAs for 16384 channels = 0.99 waves).
+// MEASURED (16384 channels x 1024 frames): 135 us per block against 157 us for the fused kernel in the same tolerance mode (and 173 us
+// before the ballistics loop was regrouped).  clock64 probes: the serial warp never waits and takes 170-230 k cycles per block, the FIR
+// warps wait for it for half of theirs; with the serial work stubbed out the FIR role alone takes 124 us, with the FIR stubbed out the
+// serial role alone 119 us, so the two roles overlap almost completely and each would have to get faster for the block to.  Neither
+// fewer instructions in the serial warp (22 -> 17 per sample), nor a chain of half the depth (pairs of values composed into one
+// fma -> max3 step), nor dropping its shuffle changed its pace; issue slots are 76 % busy (112 M warp instructions).
+// Used for PREC_FMA banks without the debug tap and without DR-14 accumulation; everything else runs the fused kernel.
+constexpr int TPD_CH = 16, TPD_TC = 24, TPD_NSLOT = 4, TPD_FIR = 96;
+constexpr int TPD_XL = 48 + TPD_NSLOT * TPD_TC + 8;          // 152 floats = 24 mod 32: the 6 + 2 lanes of a quarter warp (two rows) hit 32 different banks
+constexpr int TPD_GPC = TPD_TC / 4;
+constexpr int TPD_OP = 4 * TPD_TC + 4;                        // = 4 mod 32: the serial warp's 16 rows read conflict-free
+// barrier ids must be immediates: with an id in a register ptxas reserves all 16 named barriers for the CTA, and the SM's barrier
+// pool then holds four CTAs (measured: occupancy 4 instead of 7, 1.73 waves)
+template <int ID, int N> B200M_DEV void bar_sync_i () { asm volatile ("bar.sync %0, %1;" :: "n"(ID), "n"(N) : "memory"); }
+template <int ID, int N> B200M_DEV void bar_arrive_i () { asm volatile ("bar.arrive %0, %1;" :: "n"(ID), "n"(N) : "memory"); }
+template <int ID0, int N> B200M_DEV void bar_sync_2 (int b) { if (b) bar_sync_i<ID0 + 1, N> (); else bar_sync_i<ID0, N> (); }
+template <int ID0, int N> B200M_DEV void bar_arrive_2 (int b) { if (b) bar_arrive_i<ID0 + 1, N> (); else bar_arrive_i<ID0, N> (); }
+
+template <bool KM>
+__global__ void __launch_bounds__ (TPK_THREADS, 7)
+tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st)
+{
+    constexpr int CH = TPD_CH, TC = TPD_TC, GPC = TPD_GPC;
+    constexpr int BAR_FIR = 1, BAR_FULL = 2, BAR_EMPTY = 4;
+    __shared__ __align__ (16) float xs[CH][TPD_XL];          // [0,48): prefix of slot 0; [48 + 24 k, +24): chunk slot k
+    __shared__ __align__ (16) float ob[2][CH][TPD_OP];       // |out| of one chunk: float4 slot i * GPC + q = input sample 4 q + i
+    __shared__ __align__ (16) float4 kp[2][CH][GPC];         // per group, from the FIR thread: {K-meter sum kq[i] s_i, max s_i, max |out|, -}
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = c_first + blockIdx.x * CH;
+    const int nchunks = (nfram + TC - 1) / TC;
+    if (nchunks == 0) return;
+    const int swarp = blockIdx.x & 3;
+    const int km_n = (nfram / 4) * 4;                         // "n /= 4" drops n mod 4 samples (kmeterdsp.cc:79)
+
+    if (warp != swarp) {
+        // ------------------------------------------------------------------ FIR role
+        const int ftid = (warp - (warp > swarp ? 1 : 0)) * 32 + lane;          // 0..95
+        const int r = ftid / GPC, q = ftid - GPC * r;
+        const float* src = in + (size_t)min (c0 + r, n_chan - 1) * stride;
+        auto load_chunk = [&] (int c) {
+            const int sa = c * TC + 4 * q;                     // first sample of this thread's piece
+            float* dst = &xs[r][48 + (c & (TPD_NSLOT - 1)) * TC + 4 * q];
+            if (aligned) {
+                const int left = (nfram - sa) * 4;
+                const int nb = left >= 16 ? 16 : (left > 0 ? left : 0);
+                cp_async16 (dst, nb ? src + sa : in, nb);      // zero fill beyond the block's end
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { const bool ok = sa + i < nfram; cp_async4 (dst + i, ok ? src + sa + i : in, ok ? 4 : 0); }
+            }
+        };
+        for (int idx = ftid; idx < CH * 12; idx += TPD_FIR) {
+            const int rr = idx / 12, pc = idx - 12 * rr;
+            cp_async16 (&xs[rr][4 * pc], st.hist + (size_t)min (c0 + rr, n_chan - 1) * 48 + 4 * pc, 16);
+        }
+        load_chunk (0);
+        cp_async_commit ();
+        for (int c = 0; c < nchunks; ++c) {
+            const int slot = c & (TPD_NSLOT - 1), b = c & 1;
+            const int s0 = c * TC, len = min (TC, nfram - s0);
+            cp_async_wait<0> ();
+            bar_sync_i<BAR_FIR, TPD_FIR> ();                    // chunk c is in its slot; every FIR thread is done with chunk c - 1
+            if (c + 1 < nchunks) {
+                if (slot == TPD_NSLOT - 1)                     // next chunk starts a lap: its prefix = the last 48 samples = slots 2 and 3
+                    for (int idx = ftid; idx < CH * 12; idx += TPD_FIR) {
+                        const int rr = idx / 12, pc = idx - 12 * rr;
+                        *reinterpret_cast<float4*> (&xs[rr][4 * pc]) = *reinterpret_cast<const float4*> (&xs[rr][TPD_NSLOT * TC + 4 * pc]);
+                    }
+                load_chunk (c + 1);
+            }
+            cp_async_commit ();
+            const bool act = 4 * q < len;
+            float o[16]; float4 kpv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
+            if (act) {
+                float w[52];
+                const float4* xr = reinterpret_cast<const float4*> (&xs[r][slot * TC + 4 * q]);
+#pragma unroll
+                for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
+                if (KM) {
+                    const float q0 = __fmul_rn (w[48], w[48]), q1 = __fmul_rn (w[49], w[49]), q2 = __fmul_rn (w[50], w[50]), q3 = __fmul_rn (w[51], w[51]);
+                    kpv.x = fmaf (prm.kq[3], q3, fmaf (prm.kq[2], q2, fmaf (prm.kq[1], q1, __fmul_rn (prm.kq[0], q0))));
+                    kpv.y = fmax3 (fmax3 (q0, q1, q2), q3, 0.0f);
+                }
+                fir16_fma<true> (w, o);
+                // the group's contribution to the peak-sample reading p (`if (v > p) p = v` over every oversampled value, :71): a maximum,
+                // so the FIR thread takes it off the serial warp; positions beyond the block's end (zero-filled input) do not count
+                const int nv = min (4, len - 4 * q);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nv) kpv.z = fmax3 (kpv.z, max3_abs (o[4 * i], o[4 * i + 1], o[4 * i + 2]), fabsf (o[4 * i + 3]));
+            }
+            if (c >= 2) bar_sync_2<BAR_EMPTY, TPK_THREADS> (b);      // the serial warp is done with chunk c - 2
+            if (act) {
+                float4* d = reinterpret_cast<float4*> (&ob[b][r][0]);
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    d[i * GPC + q] = make_float4 (fabsf (o[4 * i]), fabsf (o[4 * i + 1]), fabsf (o[4 * i + 2]), fabsf (o[4 * i + 3]));
+                kp[b][r][q] = kpv;
+            }
+            bar_arrive_2<BAR_FULL, TPK_THREADS> (b);              // arrive releases this thread's tile stores to the warp that syncs on the barrier
+        }
+        // new history = the 48 samples that end the block: they sit right before the end of the last chunk's data
+        {
+            const int cl = nchunks - 1, base = (cl & (TPD_NSLOT - 1)) * TC + (nfram - cl * TC);
+            for (int idx = ftid; idx < CH * 48; idx += TPD_FIR) {
+                const int rr = idx / 48, j = idx - 48 * rr;
+                if (c0 + rr < n_chan) st.hist[(size_t)(c0 + rr) * 48 + j] = xs[rr][base + j];
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ serial role: lane = filter * 16 + channel
+        const int tch = lane & 15, filt = lane >> 4;
+        const int chs = min (c0 + tch, n_chan - 1);
+        const bool live = (c0 + tch) < n_chan;
+        const int res = st.tp_res[chs];
+        float m = res ? 0.0f : st.tp_m[chs];                                  // truepeakdsp.cc:52-55
+        float p = res ? 0.0f : st.tp_p[chs];
+        float z;
+        { const float a = filt ? st.tp_z2[chs] : st.tp_z1[chs]; z = a > 20 ? 20 : (a < 0 ? 0 : a); }
+        const float wf = filt ? prm.w2 : prm.w1;
+        // z <- max (z, (1 - w) z + w' v) with w' = 1 - fl (1 - w), as in tpk_kernel's tolerance mode
+        const float omw = __fsub_rn (1.0f, wf), wq = __fsub_rn (1.0f, omw), omw3 = __fmul_rn (omw, prm.w3);
+        float kz1 = 0, kz2 = 0, kt = 0;
+        if (KM) {
+            const float a = st.km_z1[chs], b = st.km_z2[chs];               // kmeterdsp.cc:74-75
+            kz1 = a > 50 ? 50 : (a < 0 ? 0 : a);
+            kz2 = b > 50 ? 50 : (b < 0 ? 0 : b);
+        }
+        const float om4 = __fmul_rn (4.0f, prm.omega), nkc4 = -prm.kc4;
+        auto step = [&] (const float4 v4) {
+            const float zd = __fmul_rn (z, prm.w3);
+            z = fmaxf (zd, fmaf (omw3, z, __fmul_rn (wq, v4.x)));
+            z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.y)));
+            z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.z)));
+            z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.w)));
+            m = fmaxf (m, __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16)));
+        };
+        for (int c = 0; c < nchunks; ++c) {
+            const int b = c & 1, s0 = c * TC, len = min (TC, nfram - s0);
+            bar_sync_2<BAR_FULL, TPK_THREADS> (b);
+            const float4* b4 = reinterpret_cast<const float4*> (&ob[b][tch][0]);
+            const float4* k4 = &kp[b][tch][0];
+            const int ng = len >> 2;
+#pragma unroll 2
+            for (int g = 0; g < ng; ++g) {
+                const float4 v0 = b4[g], v1 = b4[GPC + g], v2 = b4[2 * GPC + g], v3 = b4[3 * GPC + g];
+                const float4 k = k4[g];
+                step (v0); step (v1); step (v2); step (v3);
+                p = fmaxf (p, k.z);
+                if (KM && s0 + 4 * g + 4 <= km_n) {
+                    kz1 = __fadd_rn (kz1, fmaf (nkc4, kz1, k.x));
+                    kz2 = fmaf (om4, __fsub_rn (kz1, kz2), kz2);
+                    kt = fmaxf (kt, k.y);
+                }
+            }
+            if (4 * ng < len) {                                // a block that does not end on a multiple of 4: the last group is partial
+                for (int j = 4 * ng; j < len; ++j) step (b4[(j & 3) * GPC + (j >> 2)]);
+                p = fmaxf (p, k4[ng].z);
+            }
+            if (c + 2 < nchunks) bar_arrive_2<BAR_EMPTY, TPK_THREADS> (b);
+        }
+        if (live) {
+            if (filt) st.tp_z2[chs] = __fadd_rn (z, 1e-20f);    // :86-87
+            else {
+                st.tp_z1[chs] = __fadd_rn (z, 1e-20f);
+                m = __fmul_rn (m, prm.g);                       // :89
+                if (res) { st.tp_m[chs] = m; st.tp_p[chs] = p; st.tp_res[chs] = 0; }
+                else {
+                    if (m > st.tp_m[chs]) st.tp_m[chs] = m;
+                    if (p > st.tp_p[chs]) st.tp_p[chs] = p;
+                }
+                if (KM) {
+                    if (isnan (kz1)) kz1 = 0;                   // kmeterdsp.cc:101-103
+                    if (isnan (kz2)) kz2 = 0;
+                    if (!finitef_ (kt)) kt = 0;
+                    st.km_z1[chs] = __fadd_rn (kz1, 1e-20f);
+                    st.km_z2[chs] = __fadd_rn (kz2, 1e-20f);
+                    const float sr = __fsqrt_rn (__fmul_rn (2.0f, kz2));
+                    const float tr = __fsqrt_rn (kt);
+                    if (st.km_flag[chs]) { st.km_rms[chs] = sr; st.km_flag[chs] = 0; }
+                    else if (sr > st.km_rms[chs]) st.km_rms[chs] = sr;
+                    float pk = st.km_peak[chs]; int cnt = st.km_cnt[chs];
+                    if (tr >= pk) { pk = tr; cnt = prm.hold; }  // :125-139
+                    else if (cnt > 0) cnt -= nfram;
+                    else { pk = __fmul_rn (pk, prm.fall); pk = __fadd_rn (pk, 1e-10f); }
+                    st.km_peak[chs] = pk; st.km_cnt[chs] = cnt;
+                    st.km_fall[chs] = prm.fall; st.km_fpp[chs] = nfram;
+                }
+            }
+        }
+    }
+}
+
 // Tried and dropped (round 1): a warp-specialised pipeline for process() — four FIR warps + a K-meter warp in lock
 // step, the ballistics warp one chunk behind on a double-buffered |out| tile with full/empty named barriers.  It was
 // bit-exact but slower (372 us vs 286 us per 16384 x 1024 block): 48 KB of shared memory and 80 registers x 192 threads
@@ -1290,6 +1503,7 @@ struct b200m_tpk {
     unsigned long long* d_tl = nullptr; int tl_next = 0;   // B200M_TPK_TIMELINE=1: [4096][2] globaltimer stamps of the pipeline's launches (managed memory)
     cudaStream_t sb = nullptr; cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_bal[2] = {nullptr, nullptr};
     int wide = 0, wide_min = 64 * 148;      // process() with 64-channel CTAs: opt-in (B200M_TPK_WIDE=1, or =<min channels of a bank>); measured slower, see below
+    int dec = 1;                            // process() of a tolerance-mode bank runs tpdec_kernel (decoupled roles); B200M_TPK_DEC=0: the fused kernel
     int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
     int fma = 0;                            // B200M_PREC_FMA: tolerance-mode FIR (fir16_fma); needs the literal table (imm)
     TpkDr dr{}; bool dr_on = false;         // DR-14 accumulation of the next process() call (set by dr14.cu)
@@ -1324,6 +1538,11 @@ static void tpk_design (float fsamp, TpkParams& prm, float* ctab)
     prm.hold = (int)(0.5f * fsamp + 0.5f);
     prm.omega = 9.72f / fsamp;
     prm.fall = 0.0f;
+    {
+        const double om = (double)prm.omega, a = 1.0 - om;
+        prm.kq[0] = (float)(om * a * a * a); prm.kq[1] = (float)(om * a * a); prm.kq[2] = (float)(om * a); prm.kq[3] = (float)om;
+        prm.kc4 = (float)(1.0 - a * a * a * a);
+    }
     zita_table (ctab, 24, 4, 1.0);                  // setup (fsamp, fsamp * 4.0, 1, 24, 1.0): np = 4, ratio-only
 }
 
@@ -1401,6 +1620,11 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
             swap_hist = true;
             continue;
         }
+        else if (tp && h->dec && h->fma && h->imm && !h->d_dbg && !drp.rms_sum) {
+            const unsigned grid = (unsigned)((ce - cf + TPD_CH - 1) / TPD_CH);
+            if (km) tpdec_kernel<true><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st);
+            else tpdec_kernel<false><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st);
+        }
         else if (tp && h->wide && (ce - cf) >= h->wide_min) {
             // wide CTAs (64 channels x 32-sample chunks): every warp has ballistics lanes, so none idles through the serial phase
             if (km) { if (drp.rms_sum) TPK_GO (64, 32, true, false, true, true); else TPK_GO (64, 32, true, false, true, false); } else TPK_GO (64, 32, true, false, false, false);
@@ -1461,6 +1685,9 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, true, false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    // seven CTAs x 24 KB per SM: without the hint the driver picks a carveout that fits four (ncu: 1.73 waves instead of 0.99)
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1476,6 +1703,7 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     A ((void**)&h->st.hist_alt, n * 48 * sizeof (float));
     A ((void**)&h->st.blk_max, n * 4); A ((void**)&h->st.grp_cnt, n * 4);
     if (const char* v = getenv ("B200M_TPK_CHUNKED")) h->chunked = atoi (v) != 0;
+    if (const char* v = getenv ("B200M_TPK_DEC")) h->dec = atoi (v) != 0;
     // the slab pipeline is opt-in (B200M_TPK_SPLIT=2; =1: for banks of >= 512 channels): MEASURED slower than the fused kernel, see below
     h->split = 0;
     if (const char* v = getenv ("B200M_TPK_SPLIT")) { const int q = atoi (v); h->split = q >= 2 ? 1 : (q == 1 ? n_chan >= 512 : 0); }

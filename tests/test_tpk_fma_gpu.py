@@ -122,3 +122,40 @@ def test_fma_r128_cycle_histograms_stay_bit_exact():
         hm, hs = g.ebu.histogram(inst); om, os_, _ = oe.hist(inst)
         assert np.array_equal(hm, om) and np.array_equal(hs, os_)
     assert np.abs(tp.astype(np.float64) - tpmax.astype(np.float64)).max() <= TOL_DB
+
+
+@pytest.mark.parametrize("km", [True, False])
+def test_fma_process_ragged_blocks(km, process_form):
+    """process() of a tolerance-mode bank (decoupled-role kernel, csrc/tpk.cu tpdec_kernel) over block lengths that are not multiples
+    of its 24-sample chunks or of 4, from unaligned block starts, on a channel count that leaves a partial CTA"""
+    import torch
+    import meters_lv2_b200 as B
+    C = 37
+    sizes = [1, 3, 24, 25, 47, 48, 49, 95, 96, 97, 1000, 4096, 2, 8191, 1024, 5, 120]
+    total = sum(sizes)
+    x = S.white(C, total, seed=5)
+    x[2] = S.sine(total, 997.0, amp=0.9, phase=0.1)
+    x[5] = 0
+    x[6, 3000:] = 0                                        # a channel that falls silent: the filters decay
+    g = B.TruePeakKmeter(C, flags=(B.TPK_TRUEPEAK | B.TPK_KMETER) if km else B.TPK_TRUEPEAK)
+    g.set_precision(B.PREC_FMA)
+    ot = O.TruePeak(C); ok = O.Kmeter(C)
+    xd = torch.from_numpy(x).cuda()
+    a = 0; worst = 0.0
+    for n in sizes:
+        blk = np.ascontiguousarray(x[:, a:a + n])
+        ot.process(blk, mode=0, nthreads=4); ok.process(blk, nthreads=4)
+        g.process(xd[:, a:a + n], tp_mode=0)
+        a += n
+        r = g.read(); m, p = ot.read(); rms, pk = ok.read()
+        pairs = [(r["tp_m"], m), (r["tp_p"], p)]
+        if km:
+            assert np.array_equal(u32(r["km_peak"]), u32(pk)), n
+            pairs.append((r["km_rms"], rms))
+        for got, ref in pairs:
+            nz = ref > 1e-30
+            assert np.all(np.abs(got[~nz] - ref[~nz]) <= 1e-30), n
+            if nz.any():
+                worst = max(worst, np.abs(db(got[nz]) - db(ref[nz])).max())
+    print("worst deviation %.3g dB" % worst)
+    assert worst <= TOL_DB, worst
