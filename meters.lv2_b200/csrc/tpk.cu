@@ -1249,7 +1249,7 @@ tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __rest
     }
 }
 
-// ---- process() in tolerance mode: the FIR warps and the serial warp of a CTA decoupled ---------------------------------------
+// ---- process(): the FIR warps and the serial warp of a CTA decoupled ----------------------------------------------------------
 // ncu on the fused tpk_kernel<16,64> (tolerance mode, 16384 x 1024): 46 % of all warp samples sit on the barrier that ends the serial
 // phase -- three of a CTA's four warps wait while the ballistics warp works through its ~21 instructions per input sample, each of
 // which has to win the scheduler against the FIR warps of the other six resident CTAs (measured ~190 cycles per sample where the
@@ -1257,9 +1257,10 @@ tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __rest
 // serial work is a fourth ROLE here, as heavy as a FIR warp's share, and never waited for:
 //   * three FIR warps (96 threads = 16 rows x 6 groups of 4 samples: one group per thread and 24-sample chunk) produce |out| tiles
 //     into a two-deep ring and never wait for the serial warp unless it falls two chunks behind;
-//   * one serial warp (lane = filter * 16 + channel, as in the fused kernel) consumes the tiles; it also runs the K-meter, whose
-//     four steps per group are folded into one affine step from partial sums the FIR threads compute from their register window
-//     (z1 <- z1 - c4 z1 + S, tolerance mode only: the exact mode keeps the sequential roundings and the fused kernel);
+//   * one serial warp (lane = filter * 16 + channel, as in the fused kernel) consumes the tiles; it also runs the K-meter: in
+//     tolerance mode its four steps per group are folded into one affine step from partial sums the FIR threads compute from their
+//     register window (z1 <- z1 - c4 z1 + S); in exact mode it walks the raw samples of the chunk in the input window with the
+//     reference's sequential roundings, and the FIR is fir16 with its phase-0 guard evaluated on the thread's own 52-sample window;
 //   * the serial warp is warp (blockIdx & 3), so that every SM sub-partition gets the same mix of roles;
 //   * the input tile is a sliding window (history + four chunk slots in one row, the 48-sample prefix copied once per lap) instead of
 //     two buffers with a prefix copy per chunk; chunk c + 1 is loaded (cp.async, one 16-byte piece per thread) under chunk c's FIR.
@@ -1272,7 +1273,10 @@ tpbal_kernel (const float4* __restrict__ scr, int scr_pitch, const float* __rest
 // serial role alone 119 us, so the two roles overlap almost completely and each would have to get faster for the block to.  Neither
 // fewer instructions in the serial warp (22 -> 17 per sample), nor a chain of half the depth (pairs of values composed into one
 // fma -> max3 step), nor dropping its shuffle changed its pace; issue slots are 76 % busy (112 M warp instructions).
-// Used for PREC_FMA banks without the debug tap and without DR-14 accumulation; everything else runs the fused kernel.
+// Exact mode (bit-identical to the fused kernel and the reference): 245.5 vs 246.2 us for 16384 channels -- there the 288-instruction
+// FIR fills the issue slots either way -- but 75.9 vs 104.1 us for 2048 channels (tolerance mode 43.9 vs 65.8 us), where a CTA's own
+// critical path counts: the LV2 facade's batched hubs and the strong-scaling shards run at those sizes.
+// Used for banks without the debug tap and without DR-14 accumulation; those run the fused kernel.
 constexpr int TPD_CH = 16, TPD_TC = 24, TPD_NSLOT = 4, TPD_FIR = 96;
 constexpr int TPD_XL = 48 + TPD_NSLOT * TPD_TC + 8;          // 152 floats = 24 mod 32: the 6 + 2 lanes of a quarter warp (two rows) hit 32 different banks
 constexpr int TPD_GPC = TPD_TC / 4;
@@ -1284,9 +1288,9 @@ template <int ID, int N> B200M_DEV void bar_arrive_i () { asm volatile ("bar.arr
 template <int ID0, int N> B200M_DEV void bar_sync_2 (int b) { if (b) bar_sync_i<ID0 + 1, N> (); else bar_sync_i<ID0, N> (); }
 template <int ID0, int N> B200M_DEV void bar_arrive_2 (int b) { if (b) bar_arrive_i<ID0 + 1, N> (); else bar_arrive_i<ID0, N> (); }
 
-template <bool KM>
+template <bool KM, bool FMA>
 __global__ void __launch_bounds__ (TPK_THREADS, 7)
-tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, TpkParams prm, TpkState st)
+tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int aligned, int elide0, TpkParams prm, TpkState st)
 {
     constexpr int CH = TPD_CH, TC = TPD_TC, GPC = TPD_GPC;
     constexpr int BAR_FIR = 1, BAR_FULL = 2, BAR_EMPTY = 4;
@@ -1339,17 +1343,39 @@ tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
             cp_async_commit ();
             const bool act = 4 * q < len;
             float o[16]; float4 kpv = make_float4 (0.0f, 0.0f, 0.0f, 0.0f);
-            if (act) {
+            {
+                // every thread evaluates its group (beyond the block's end the window is zero-filled): the exact mode's votes below need
+                // the whole warp, and only the last chunk of a block has idle groups
                 float w[52];
-                const float4* xr = reinterpret_cast<const float4*> (&xs[r][slot * TC + 4 * q]);
+                const float* xw = &xs[r][slot * TC + 4 * q];
+                const float4* xr = reinterpret_cast<const float4*> (xw);
 #pragma unroll
                 for (int i = 0; i < 13; ++i) { const float4 v = xr[i]; w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w; }
-                if (KM) {
-                    const float q0 = __fmul_rn (w[48], w[48]), q1 = __fmul_rn (w[49], w[49]), q2 = __fmul_rn (w[50], w[50]), q3 = __fmul_rn (w[51], w[51]);
-                    kpv.x = fmaf (prm.kq[3], q3, fmaf (prm.kq[2], q2, fmaf (prm.kq[1], q1, __fmul_rn (prm.kq[0], q0))));
-                    kpv.y = fmax3 (fmax3 (q0, q1, q2), q3, 0.0f);
+                if (FMA) {
+                    if (KM) {
+                        const float q0 = __fmul_rn (w[48], w[48]), q1 = __fmul_rn (w[49], w[49]), q2 = __fmul_rn (w[50], w[50]), q3 = __fmul_rn (w[51], w[51]);
+                        kpv.x = fmaf (prm.kq[3], q3, fmaf (prm.kq[2], q2, fmaf (prm.kq[1], q1, __fmul_rn (prm.kq[0], q0))));
+                        kpv.y = fmax3 (fmax3 (q0, q1, q2), q3, 0.0f);
+                    }
+                    fir16_fma<true> (w, o);
+                } else {
+                    // exact mode: the reference's unfused sequence (fir16).  Its phase-0 guard and the digital-silence shortcut take the
+                    // maximum of |x| over this thread's own 52-sample window (the fused kernel uses the whole row: any superset of the
+                    // taps is valid, a tighter one elides more often); both decisions are warp votes, so no branch diverges
+                    bool full0 = true, silent = false;
+                    if (elide0) {
+                        float M = max3_abs_nan (w[0], w[1], w[2]);
+#pragma unroll
+                        for (int i = 3; i + 1 < 52; i += 2) M = max3_abs_nan (M, w[i], w[i + 1]);
+                        M = max3_abs_nan (M, w[51], 0.0f);
+                        silent = __all_sync (0xffffffffu, M == 0.0f);
+                        full0 = !__all_sync (0xffffffffu, phase0_is_delay (make_float4 (w[24], w[25], w[26], w[27]), M));
+                    }
+                    if (silent) {
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = 0.0f;
+                    } else fir16<true> (w, xw, o, full0);
                 }
-                fir16_fma<true> (w, o);
                 // the group's contribution to the peak-sample reading p (`if (v > p) p = v` over every oversampled value, :71): a maximum,
                 // so the FIR thread takes it off the serial warp; positions beyond the block's end (zero-filled input) do not count
                 const int nv = min (4, len - 4 * q);
@@ -1396,18 +1422,29 @@ tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
         }
         const float om4 = __fmul_rn (4.0f, prm.omega), nkc4 = -prm.kc4;
         auto step = [&] (const float4 v4) {
-            const float zd = __fmul_rn (z, prm.w3);
-            z = fmaxf (zd, fmaf (omw3, z, __fmul_rn (wq, v4.x)));
-            z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.y)));
-            z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.z)));
-            z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.w)));
-            m = fmaxf (m, __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16)));
+            if (FMA) {
+                const float zd = __fmul_rn (z, prm.w3);
+                z = fmaxf (zd, fmaf (omw3, z, __fmul_rn (wq, v4.x)));
+                z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.y)));
+                z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.z)));
+                z = fmaxf (z, fmaf (omw, z, __fmul_rn (wq, v4.w)));
+            } else {                                           // truepeakdsp.cc:57-84, operation for operation
+                z = __fmul_rn (z, prm.w3);
+                if (v4.x > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.x, z)));
+                if (v4.y > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.y, z)));
+                if (v4.z > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.z, z)));
+                if (v4.w > z) z = __fadd_rn (z, __fmul_rn (wf, __fsub_rn (v4.w, z)));
+            }
+            m = fmaxf (m, __fadd_rn (z, __shfl_xor_sync (0xffffffffu, z, 16)));       // `if (t > m) m = t`: m is never NaN
         };
         for (int c = 0; c < nchunks; ++c) {
             const int b = c & 1, s0 = c * TC, len = min (TC, nfram - s0);
             bar_sync_2<BAR_FULL, TPK_THREADS> (b);
             const float4* b4 = reinterpret_cast<const float4*> (&ob[b][tch][0]);
             const float4* k4 = &kp[b][tch][0];
+            // exact mode: the K-meter walks the raw samples of this chunk in the input window (both half warps carry a copy; the slot is
+            // not reloaded before this warp has released the chunk after next, see the FIR role)
+            const float4* x4 = reinterpret_cast<const float4*> (&xs[tch][48 + (c & (TPD_NSLOT - 1)) * TC]);
             const int ng = len >> 2;
 #pragma unroll 2
             for (int g = 0; g < ng; ++g) {
@@ -1416,9 +1453,21 @@ tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
                 step (v0); step (v1); step (v2); step (v3);
                 p = fmaxf (p, k.z);
                 if (KM && s0 + 4 * g + 4 <= km_n) {
-                    kz1 = __fadd_rn (kz1, fmaf (nkc4, kz1, k.x));
-                    kz2 = fmaf (om4, __fsub_rn (kz1, kz2), kz2);
-                    kt = fmaxf (kt, k.y);
+                    if (FMA) {
+                        kz1 = __fadd_rn (kz1, fmaf (nkc4, kz1, k.x));
+                        kz2 = fmaf (om4, __fsub_rn (kz1, kz2), kz2);
+                        kt = fmaxf (kt, k.y);
+                    } else {                                   // kmeterdsp.cc:80-97
+                        const float4 xv = x4[g];
+                        const float vv[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float sq = __fmul_rn (vv[i], vv[i]);
+                            if (kt < sq) kt = sq;
+                            kz1 = __fadd_rn (kz1, __fmul_rn (prm.omega, __fsub_rn (sq, kz1)));
+                        }
+                        kz2 = __fadd_rn (kz2, __fmul_rn (om4, __fsub_rn (kz1, kz2)));
+                    }
                 }
             }
             if (4 * ng < len) {                                // a block that does not end on a multiple of 4: the last group is partial
@@ -1503,7 +1552,7 @@ struct b200m_tpk {
     unsigned long long* d_tl = nullptr; int tl_next = 0;   // B200M_TPK_TIMELINE=1: [4096][2] globaltimer stamps of the pipeline's launches (managed memory)
     cudaStream_t sb = nullptr; cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_bal[2] = {nullptr, nullptr};
     int wide = 0, wide_min = 64 * 148;      // process() with 64-channel CTAs: opt-in (B200M_TPK_WIDE=1, or =<min channels of a bank>); measured slower, see below
-    int dec = 1;                            // process() of a tolerance-mode bank runs tpdec_kernel (decoupled roles); B200M_TPK_DEC=0: the fused kernel
+    int dec = 1;                            // process() runs tpdec_kernel (decoupled roles) unless the debug tap or DR-14 sums are on; B200M_TPK_DEC=0: the fused kernel
     int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
     int fma = 0;                            // B200M_PREC_FMA: tolerance-mode FIR (fir16_fma); needs the literal table (imm)
     TpkDr dr{}; bool dr_on = false;         // DR-14 accumulation of the next process() call (set by dr14.cu)
@@ -1620,10 +1669,15 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
             swap_hist = true;
             continue;
         }
-        else if (tp && h->dec && h->fma && h->imm && !h->d_dbg && !drp.rms_sum) {
+        else if (tp && h->dec && h->imm && !h->d_dbg && !drp.rms_sum) {
             const unsigned grid = (unsigned)((ce - cf + TPD_CH - 1) / TPD_CH);
-            if (km) tpdec_kernel<true><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st);
-            else tpdec_kernel<false><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, prm, h->st);
+            if (h->fma) {
+                if (km) tpdec_kernel<true, true><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st);
+                else tpdec_kernel<false, true><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st);
+            } else {
+                if (km) tpdec_kernel<true, false><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st);
+                else tpdec_kernel<false, false><<<grid, blk, 0, st>>> (d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st);
+            }
         }
         else if (tp && h->wide && (ce - cf) >= h->wide_min) {
             // wide CTAs (64 channels x 32-sample chunks): every warp has ballistics lanes, so none idles through the serial phase
@@ -1686,8 +1740,10 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpk_kernel<8, 256, true, true, false, false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     // seven CTAs x 24 KB per SM: without the hint the driver picks a carveout that fits four (ncu: 1.73 waves instead of 0.99)
-    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute (tpdec_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_kernel<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -8,18 +8,24 @@ import _signals as S
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["shortcut", "full", "slabs", "stagger"])
+@pytest.fixture(autouse=True, params=["shortcut", "full", "slabs", "stagger", "fused", "roles_full"])
 def phase0_mode(request, monkeypatch):
-    """every test runs four times: with the exact phase-0 shortcut of the FIR (default) and with phase 0 always evaluated; with
-    process() as the opt-in FIR / ballistics slab pipeline cut into 128-sample slabs; and with the opt-in phase stagger of co-resident
-    process() CTAs (every second CTA of an SM shortens its first chunk)."""
+    """every test runs six times: with the exact phase-0 shortcut of the FIR (default) and with phase 0 always evaluated; with
+    process() as the opt-in FIR / ballistics slab pipeline cut into 128-sample slabs; with the opt-in phase stagger of co-resident
+    process() CTAs (every second CTA of an SM shortens its first chunk); with process() forced onto the fused kernel (the default is
+    the decoupled-role kernel, csrc/tpk.cu tpdec_kernel); and with the decoupled roles evaluating phase 0 always."""
     monkeypatch.delenv("B200M_TPK_ELIDE0", raising=False)
+    monkeypatch.delenv("B200M_TPK_DEC", raising=False)
     if request.param == "full":
+        monkeypatch.setenv("B200M_TPK_ELIDE0", "0"); monkeypatch.setenv("B200M_TPK_DEC", "0")
+    elif request.param == "fused":
+        monkeypatch.setenv("B200M_TPK_DEC", "0")
+    elif request.param == "roles_full":
         monkeypatch.setenv("B200M_TPK_ELIDE0", "0")
     elif request.param == "slabs":
         monkeypatch.setenv("B200M_TPK_SLAB", "128"); monkeypatch.setenv("B200M_TPK_SPLIT", "2")
     elif request.param == "stagger":
-        monkeypatch.setenv("B200M_TPK_STAGGER", "1")
+        monkeypatch.setenv("B200M_TPK_STAGGER", "1"); monkeypatch.setenv("B200M_TPK_DEC", "0")
     return request.param
 
 
