@@ -52,6 +52,13 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def bf16_peak_tflops():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("bf16_tflops", 0.0)) or None
+    return None
+
+
 def traffic_for(kernel):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
@@ -146,6 +153,7 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)      # NCCL_DEBUG is left exactly as the caller set it
     K, W = args.steps, max(args.warmup, 3)
     hbm_peak, peak_src = peaks()
+    bf16_peak = bf16_peak_tflops()
     x = make_ring(torch, dev, rank)
     stride = x.stride(0)
     base = x.data_ptr()
@@ -186,8 +194,9 @@ def run_b200(args):
            "config": {"workload": "8192 stereo EBU R128 M+S+I (integrating) + dBTP true-peak 4x (ebur128_run audio cycle) per GPU",
                       "instances_per_gpu": N_INST, "channels_per_instance": 2, "block": NFRAM, "fs": FS,
                       "value_is": "aggregate over all %d GPUs (samples/s); value_per_gpu = value / n_gpus" % ws,
-                      "precision": "dBTP FIR in tolerance mode B200M_PREC_FMA (readings within +-1e-4 dB of the reference, the contract's "
-                                   "float tolerance; tests/test_tpk_fma_gpu.py); EBU R128 floats + histograms bit-exact; "
+                      "precision": "dBTP FIR in tolerance mode B200M_PREC_FMA: on the tensor cores as a 3xTF32 Toeplitz GEMM (fp32 accumulate; "
+                                   "readings within 1e-5 dB of the reference measured, +-1e-4 dB is the contract's float tolerance; "
+                                   "tests/test_tpk_fma_gpu.py); EBU R128 floats + histograms bit-exact (fp32, unfused); "
                                    "value_bit_exact = all floats bit-identical (B200M_PREC_EXACT, library default)",
                       "input": "device ring of %d distinct 64 MiB blocks (512 MiB > L2), no L2 flush needed" % RING,
                       "prime_blocks": PRIME, "parallelism": "channel-shard x%d, no data-path collective" % ws},
@@ -236,6 +245,15 @@ def run_b200(args):
     del hbank
 
     # ---- per-kernel timings for the roofline (kernel alone, same ring, CUDA events) -----------------------------
+    # the same FIR on the CUDA cores (tpmax_kernel<IMM,FMA>), for the record: the tensor-core kernel is the default for banks this size
+    os.environ["B200M_TPK_TC"] = "0"
+    tpc = B.TruePeakKmeter(2 * N_INST, FS, flags=B.TPK_TRUEPEAK, device=local)
+    tpc.set_precision(B.PREC_FMA)
+    for s in range(W):
+        tpc.process_ptr(blk(s), stride, NFRAM, B.TP_MODE_MAX)
+    ms_tpc = timed_loop(torch, dist, ws, lambda s: tpc.process_ptr(blk(s), stride, NFRAM, B.TP_MODE_MAX), K)
+    del tpc
+    os.environ.pop("B200M_TPK_TC", None)
     tpb = B.TruePeakKmeter(2 * N_INST, FS, flags=B.TPK_TRUEPEAK, device=local)
     tpb.set_precision(B.PREC_FMA)
     ebb = B.Ebu_r128_proc(N_INST, 2, FS, device=local); ebb.integr_start()
@@ -257,13 +275,23 @@ def run_b200(args):
     eb_gbs = alg_bytes / (ms_eb / K * 1e-3) / 1e9
     # fp32 instructions the FIR executes per input sample: tolerance mode 120 (72 FFMA + 48 FADD, csrc/tpk.cu fir16_fma);
     # exact mode 288 unfused FMUL/FADD for phases 1-3 (+96 for phase 0 where the exact-delay guard fails: never on this noise)
-    out["roofline"] = {"kernel": "tpk_kernel<8,256,TP,MAX,FMA> (4x polyphase FIR + max, tolerance mode)", "bound": "hbm", "achieved": tp_gbs, "peak": hbm_peak,
-                       "unit": "GB/s", "frac": tp_gbs / hbm_peak, "traffic": traffic_for("tpk_kernel_fma"), "peak_source": peak_src,
+    out["roofline"] = {"kernel": "tpmax_tc_kernel (4x polyphase FIR as a Toeplitz GEMM on tcgen05 kind::tf32 with the 3xTF32 split, + max; tolerance mode)",
+                       "bound": "hbm", "achieved": tp_gbs, "peak": hbm_peak,
+                       "unit": "GB/s", "frac": tp_gbs / hbm_peak, "traffic": traffic_for("tpmax_tc_kernel"), "peak_source": peak_src,
                        "ms_per_launch": ms_tp / K, "algorithmic_bytes_per_launch": alg_bytes,
-                       "note": "this kernel is fp32-issue bound (120 fp32 instructions per sample), see roofline_alu; share of the cycle: %.0f%%" % (100.0 * ms_tp / ms)}
-    out["roofline_alu"] = {"kernel": "tpk_kernel<8,256,TP,MAX,FMA>", "bound": "fp32 issue (fma pipe)", "achieved": SAMPLES_PER_STEP * 120.0 / (ms_tp / K * 1e-3) / 1e9,
-                           "peak": fp32_peak, "unit": "1e9 lane-ops/s", "frac": SAMPLES_PER_STEP * 120.0 / (ms_tp / K * 1e-3) / 1e9 / fp32_peak,
-                           "ops_per_sample": 120, "peak_source": "b200m_peak_probe(0) measured in this run",
+                       "note": "bound by its producer / epilogue warps (window -> {hi, lo} -> TMEM, TMEM -> maxima), not by HBM or the tensor pipe, see roofline_tensor and DESIGN.md; share of the cycle: %.0f%%" % (100.0 * ms_tp / ms)}
+    # executed tensor-core work: per [8 channels x 256 samples] tile 8 K-steps x (128 x 96 x 8 + 128 x 48 x 8) MACs (25 % of the Toeplitz B is zero,
+    # and the three products of the split count three times): 1152 flop per input sample, of which 288 (3 phases x 48 taps x 2) are the FIR's own
+    tf32_peak = (bf16_peak / 2.0) if bf16_peak else None
+    tc_tflops = SAMPLES_PER_STEP * 1152.0 / (ms_tp / K * 1e-3) / 1e12
+    out["roofline_tensor"] = {"kernel": "tpmax_tc_kernel", "bound": "tensor (kind::tf32)", "achieved": tc_tflops, "peak": tf32_peak, "unit": "TFLOP/s",
+                              "frac": (tc_tflops / tf32_peak) if tf32_peak else None, "executed_flop_per_sample": 1152, "fir_flop_per_sample": 288,
+                              "peak_source": "half of MEASURED_PEAKS.json's dense bf16 rate (tf32 runs at half the bf16 rate)" if tf32_peak else "none"}
+    out["roofline_alu"] = {"kernel": "tpmax_kernel<IMM,FMA> (the same FIR on the CUDA cores: B200M_TPK_TC=0, and every bank too small for the tensor-core grid)",
+                           "bound": "fp32 issue (fma pipe)", "achieved": SAMPLES_PER_STEP * 120.0 / (ms_tpc / K * 1e-3) / 1e9,
+                           "peak": fp32_peak, "unit": "1e9 lane-ops/s", "frac": SAMPLES_PER_STEP * 120.0 / (ms_tpc / K * 1e-3) / 1e9 / fp32_peak,
+                           "ops_per_sample": 120, "ms_per_launch": ms_tpc / K, "hbm_frac": alg_bytes / (ms_tpc / K * 1e-3) / 1e9 / hbm_peak,
+                           "peak_source": "b200m_peak_probe(0) measured in this run",
                            "bit_exact_mode": {"ops_per_sample": 288, "ms_per_launch": ms_tpx / K, "hbm_frac": tpx_gbs / hbm_peak,
                                               "frac": SAMPLES_PER_STEP * 288.0 / (ms_tpx / K * 1e-3) / 1e9 / fp32_peak}}
     out["roofline_kernels"] = [

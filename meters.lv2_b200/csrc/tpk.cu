@@ -1508,6 +1508,302 @@ tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
     }
 }
 
+// ---- process_max in tolerance mode on the tensor cores -----------------------------------------------------------------------
+// The three non-trivial phases of the 4x oversampler as a Toeplitz GEMM on tcgen05 (kind::tf32), fp32 accuracy from the 3xTF32 split:
+//   rows     = 16-sample blocks of one channel: 128 rows = 8 channels x 256 samples = the (group, chunk) item of tpmax_kernel;
+//   A[r][k]  = x[16 tb - 48 + k], k < 64 (the block's 16 samples and the 48 before them), split x = hi + lo with hi = the top 11
+//              significand bits (what a tf32 operand keeps), written to TMEM by the builder warps (tcgen05.st): lane = row, column = k;
+//   B[k][n]  = h_ph[j + 48 - k] for n = 16 (ph - 1) + j, zero outside the 48 taps (h_ph[d] multiplies x[n - d], see fir16), as
+//              [B_hi | B_lo] (96 rows) in shared memory, K-major, no swizzle: 8-row x 16-byte core matrices, K chunks 1536 bytes apart;
+//   D        = A_hi [B_hi | B_lo] + A_lo B_hi: two instructions per K step (M = 128, K = 8: N = 96 and N = 48), 16 per tile, accumulators
+//              in TMEM; the epilogue adds columns n and 48 + n.  The lo x lo term (2^-20 relative) is dropped.
+// Phase 0 of the table is the input delayed by 24 samples (to 7.7e-16, see phase0_is_delay) and is taken from the window directly.
+// Every stage of a tile has its own warps and the stages are chained by mbarriers only (nobody waits on a CTA-wide barrier):
+//   warp 9    one thread: the tile's 8 rows x 304 floats by cp.async.bulk onto xfull[s], eight stages ahead of the builders;
+//   warps 0-3 builders: row window -> registers -> {hi, lo} -> TMEM A[b]; phase-0 maximum; the block's last 48 samples -> next history;
+//   warp 8    one thread issues the tile's 16 MMAs when A[b] is written and D[b] is read out, and commits them onto done[b];
+//   warps 4-7 epilogue: D[b] -> registers, maxima over the row's valid positions, per-channel maximum -> atomicMax on blk_max,
+//             then tpmax_kernel's group book-keeping (last chunk of a group: m = max (m, v), the EBUr128 epilogue).
+// A and D are double-buffered in TMEM (512 columns: one CTA per SM, persistent over its tiles).
+// Accuracy: readings within 6.7e-7 relative of a float64 FIR (profiles/r2_tcfir_probe.txt; the contract's tolerance is 1.15e-5).
+// Non-finite input: a NaN or Inf sample makes every output of the (up to four) rows whose window holds it NaN, which the maxima
+// ignore like the reference ignores its own NaN outputs; |Inf| itself is still seen through phase 0.
+// Needs 16-byte aligned rows and nfram % 4 == 0 (bulk copies); everything else runs tpmax_kernel.
+constexpr int TCF_XPITCH = 308;                            // floats per channel row of an input stage: 48 + 256 + 4; = 20 mod 32
+constexpr int TCF_XSTAGES = 8;
+constexpr int TCF_BLBO = 96 * 16;                          // bytes between K chunks of [B_hi | B_lo]
+constexpr int TCF_BBYTES = 16 * TCF_BLBO;                  // 24576
+constexpr int TCF_SMEM = TCF_BBYTES + TCF_XSTAGES * 8 * TCF_XPITCH * 4 + 4 * 128 * 4 + 256;
+constexpr int TCF_THREADS = 320;
+
+B200M_DEV uint32_t tcf_smem_u32 (const void* p) { return (uint32_t)__cvta_generic_to_shared (p); }
+B200M_DEV uint64_t tcf_desc (uint32_t saddr, uint32_t lbo, uint32_t sbo)      // K-major, SWIZZLE_NONE shared-memory matrix descriptor (version 1)
+{
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+B200M_DEV void tcf_mma (uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t acc)
+{
+    asm volatile ("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                  "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %6, %7, %8}, p;\n\t}\n"
+                  :: "r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(acc), "r"(0u), "r"(0u), "r"(0u), "r"(0u) : "memory");
+}
+B200M_DEV void tcf_wait (uint32_t bar, uint32_t parity)
+{
+    uint32_t ok = 0;
+    while (!ok) asm volatile ("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+}
+B200M_DEV void tcf_arrive (uint32_t bar) { asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory"); }
+B200M_DEV void tcf_st32 (uint32_t taddr, const uint32_t (&r)[32])
+{
+    asm volatile ("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+                  "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n"
+                  :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                     "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+                     "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+                     "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+B200M_DEV void tcf_ld16 (uint32_t taddr, uint32_t (&r)[16])                    // no wait: the caller issues tcgen05.wait::ld once
+{
+    asm volatile ("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                    "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+}
+
+__global__ void __launch_bounds__ (TCF_THREADS, 1)
+tpmax_tc_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_chan, int nfram, int nchunks, const float* __restrict__ bcanon,
+                 TpkState st, float* __restrict__ r128_tpmax)
+{
+    extern __shared__ __align__ (128) uint8_t tcf_smem[];
+    uint8_t* sB = tcf_smem;
+    float* xbuf = reinterpret_cast<float*> (tcf_smem + TCF_BBYTES);                                        // [XSTAGES][8][XPITCH]
+    float* p0buf = reinterpret_cast<float*> (tcf_smem + TCF_BBYTES + TCF_XSTAGES * 8 * TCF_XPITCH * 4);     // [4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*> (tcf_smem + TCF_BBYTES + TCF_XSTAGES * 8 * TCF_XPITCH * 4 + 4 * 128 * 4);
+    uint64_t* afull = bars; uint64_t* done = bars + 2; uint64_t* dempty = bars + 4; uint64_t* xfull = bars + 6; uint64_t* xempty = bars + 6 + TCF_XSTAGES;
+    __shared__ uint32_t s_tmem;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // a CTA takes whole channel groups (group blockIdx.x, + gridDim.x, ...) and walks each group's chunks in order: the block's maximum
+    // of a channel then never leaves the CTA (no global atomics or fences between the chunks, unlike tpmax_kernel's item grid)
+    const int ngroups = (n_chan - c_first + 7) / 8;
+    const int n_it = (int)blockIdx.x < ngroups ? ((ngroups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x) * nchunks : 0;
+    __shared__ unsigned s_gmax[8];
+    if (tid < 8) s_gmax[tid] = 0u;
+
+    for (int i = tid; i < TCF_BBYTES / 16; i += TCF_THREADS) reinterpret_cast<float4*> (sB)[i] = reinterpret_cast<const float4*> (bcanon)[i];
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tcf_smem_u32 (&afull[i])));
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tcf_smem_u32 (&done[i])));
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tcf_smem_u32 (&dempty[i])));
+        }
+        for (int i = 0; i < TCF_XSTAGES; ++i) {
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(tcf_smem_u32 (&xfull[i])));
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(tcf_smem_u32 (&xempty[i])));
+        }
+        asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile ("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(tcf_smem_u32 (&s_tmem)), "n"(512) : "memory");
+        asm volatile ("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile ("fence.proxy.async.shared::cta;" ::: "memory");             // B: generic-proxy stores, read by the tensor core (async proxy)
+    asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads ();
+    asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = s_tmem;
+    // instruction descriptors: D fp32 (bit 4), A and B tf32 (2 << 7, 2 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+    const uint32_t idesc96 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc48 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // TMEM columns: A[b] hi at 128 b, lo at 128 b + 64; D[b] at 256 + 128 b: [0,48) = hi hi + lo hi, [48,96) = hi lo.
+    // lane -> row (channel c8, block tb): the eight lanes of an LDS.128 phase are four channels x two blocks = 32 different banks
+    const int wq = warp & 3;
+    const int c8 = (wq & 1) * 4 + (lane & 3);
+    const int tb = ((wq >> 1) * 4 + (lane >> 3)) * 2 + ((lane >> 2) & 1);
+    const int row = 32 * wq + lane;
+    const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
+
+    if (warp == 9) {
+        // ---------------- input loads
+        if (lane == 0)
+            for (int it = 0; it < n_it; ++it) {
+                const int sg = it % TCF_XSTAGES;
+                if (it >= TCF_XSTAGES) tcf_wait (tcf_smem_u32 (&xempty[sg]), (uint32_t)((it / TCF_XSTAGES - 1) & 1));
+                const int gk = it / nchunks, chunk = it - gk * nchunks;
+                const int c0 = c_first + ((int)blockIdx.x + gk * (int)gridDim.x) * 8, s0 = chunk * 256;
+                const uint32_t xb = tcf_smem_u32 (xbuf + (size_t)sg * 8 * TCF_XPITCH), bar = tcf_smem_u32 (&xfull[sg]);
+                const uint32_t nfl = (uint32_t)min (304, nfram - (s0 - 48));      // floats of every row that lie inside the block (or its history)
+                asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(8u * nfl * 4u) : "memory");
+                for (int cc = 0; cc < 8; ++cc) {
+                    const size_t ch = (size_t)min (c0 + cc, n_chan - 1);
+                    const uint32_t dst = xb + (uint32_t)(cc * TCF_XPITCH * 4);
+                    if (chunk == 0) {                                              // the 48 samples before the block are the bank's history
+                        asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                      :: "r"(dst), "l"(st.hist + ch * 48), "r"(192u), "r"(bar) : "memory");
+                        asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                      :: "r"(dst + 192u), "l"(in + ch * stride), "r"((nfl - 48u) * 4u), "r"(bar) : "memory");
+                    } else
+                        asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                      :: "r"(dst), "l"(in + ch * stride + (s0 - 48)), "r"(nfl * 4u), "r"(bar) : "memory");
+                }
+            }
+    } else if (warp == 8) {
+        // ---------------- MMA issue
+        if (lane == 0) {
+            const uint32_t bb = tcf_smem_u32 (sB);
+            for (int it = 0; it < n_it; ++it) {
+                const int b = it & 1;
+                tcf_wait (tcf_smem_u32 (&afull[b]), (uint32_t)((it >> 1) & 1));
+                if (it >= 2) tcf_wait (tcf_smem_u32 (&dempty[b]), (uint32_t)(((it - 2) >> 1) & 1));
+                asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d = tmem + 256u + 128u * b, ah = tmem + 128u * b, al = ah + 64u;
+#pragma unroll
+                for (int s = 0; s < 8; ++s) {
+                    const uint64_t db = tcf_desc (bb + 2 * s * TCF_BLBO, TCF_BLBO, 128);
+                    tcf_mma (d, ah + 8 * s, db, idesc96, s > 0 ? 1u : 0u);          // A_hi x [B_hi | B_lo]
+                    tcf_mma (d, al + 8 * s, db, idesc48, 1u);                        // A_lo x B_hi
+                }
+                asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(tcf_smem_u32 (&done[b])) : "memory");
+            }
+        }
+    } else if (warp < 4) {
+        // ---------------- builders
+        for (int it = 0; it < n_it; ++it) {
+            const int gk = it / nchunks, chunk = it - gk * nchunks;
+            const int c0 = c_first + ((int)blockIdx.x + gk * (int)gridDim.x) * 8, s0 = chunk * 256;
+            const int b = it & 1, sg = it % TCF_XSTAGES;
+            tcf_wait (tcf_smem_u32 (&xfull[sg]), (uint32_t)((it / TCF_XSTAGES) & 1));
+            const float* xt = xbuf + (size_t)sg * 8 * TCF_XPITCH;
+            const float* xw = xt + c8 * TCF_XPITCH + 16 * tb;
+            float4 v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = *reinterpret_cast<const float4*> (xw + 4 * c);
+            if (chunk == nchunks - 1 && tid < 96) {
+                // history of the next block = the 48 samples that end this one: stage positions nfram - s0 + j (prefix + chunk >= 48 samples)
+                const int rr = tid / 12, k4 = (tid - 12 * rr) * 4;
+                if (c0 + rr < n_chan)
+                    *reinterpret_cast<float4*> (st.hist_alt + (size_t)(c0 + rr) * 48 + k4) = *reinterpret_cast<const float4*> (xt + rr * TCF_XPITCH + (nfram - s0) + k4);
+            }
+            tcf_arrive (tcf_smem_u32 (&xempty[sg]));
+            const int vj = min (16, max (0, nfram - (s0 + 16 * tb)));            // valid output positions of this row
+            const int nin = nfram - (s0 - 48) - 16 * tb;                         // window elements k < nin lie inside the block; the stage holds stale data beyond
+            if (nin < 64) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (4 * c + 0 >= nin) v[c].x = 0.0f;
+                    if (4 * c + 1 >= nin) v[c].y = 0.0f;
+                    if (4 * c + 2 >= nin) v[c].z = 0.0f;
+                    if (4 * c + 3 >= nin) v[c].w = 0.0f;
+                }
+            }
+            float p0 = 0.0f;                                                     // phase 0: window elements 24 + j for output position j
+            if (vj == 16) {
+#pragma unroll
+                for (int c = 6; c < 10; ++c) p0 = fmax3 (p0, max3_abs (v[c].x, v[c].y, v[c].z), fabsf (v[c].w));
+            } else {
+#pragma unroll
+                for (int c = 6; c < 10; ++c) {
+                    const int j0 = 4 * (c - 6);
+                    if (j0 + 0 < vj) p0 = fmaxf (p0, fabsf (v[c].x));
+                    if (j0 + 1 < vj) p0 = fmaxf (p0, fabsf (v[c].y));
+                    if (j0 + 2 < vj) p0 = fmaxf (p0, fabsf (v[c].z));
+                    if (j0 + 3 < vj) p0 = fmaxf (p0, fabsf (v[c].w));
+                }
+            }
+            if (it >= 2) tcf_wait (tcf_smem_u32 (&done[b]), (uint32_t)(((it - 2) >> 1) & 1));       // the MMAs of tile it - 2 have read A[b]
+            asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+            p0buf[(it & 3) * 128 + row] = p0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 q = v[8 * half + c];
+                    const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t hbits = __float_as_uint (vv[e]) & 0xffffe000u;
+                        hi[4 * c + e] = hbits; lo[4 * c + e] = __float_as_uint (__fsub_rn (vv[e], __uint_as_float (hbits)));
+                    }
+                }
+                tcf_st32 (tmem + lane_base + 128u * b + 32u * half, hi);
+                tcf_st32 (tmem + lane_base + 128u * b + 64u + 32u * half, lo);
+            }
+            asm volatile ("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tcf_arrive (tcf_smem_u32 (&afull[b]));
+        }
+    } else {
+        // ---------------- epilogue warps 4..7
+        for (int it = 0; it < n_it; ++it) {
+            const int gk = it / nchunks, chunk = it - gk * nchunks;
+            const int c0 = c_first + ((int)blockIdx.x + gk * (int)gridDim.x) * 8, s0 = chunk * 256;
+            const int b = it & 1;
+            tcf_wait (tcf_smem_u32 (&done[b]), (uint32_t)((it >> 1) & 1));
+            asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t taddr = tmem + lane_base + 256u + 128u * b;
+            uint32_t u[3][16], w[3][16];
+#pragma unroll
+            for (int ph = 0; ph < 3; ++ph) { tcf_ld16 (taddr + 16 * ph, u[ph]); tcf_ld16 (taddr + 48 + 16 * ph, w[ph]); }
+            asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float mx = p0buf[(it & 3) * 128 + row];
+            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+            tcf_arrive (tcf_smem_u32 (&dempty[b]));
+            const int vj = min (16, max (0, nfram - (s0 + 16 * tb)));
+            if (vj == 16) {
+#pragma unroll
+                for (int ph = 0; ph < 3; ++ph)
+#pragma unroll
+                    for (int j = 0; j < 16; j += 2)
+                        mx = fmax3 (mx, fabsf (__fadd_rn (__uint_as_float (u[ph][j]), __uint_as_float (w[ph][j]))),
+                                    fabsf (__fadd_rn (__uint_as_float (u[ph][j + 1]), __uint_as_float (w[ph][j + 1]))));
+            } else {
+#pragma unroll
+                for (int ph = 0; ph < 3; ++ph)
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (j < vj) mx = fmaxf (mx, fabsf (__fadd_rn (__uint_as_float (u[ph][j]), __uint_as_float (w[ph][j]))));
+            }
+            mx = fmaxf (mx, __shfl_xor_sync (0xffffffffu, mx, 4));
+            mx = fmaxf (mx, __shfl_xor_sync (0xffffffffu, mx, 8));
+            mx = fmaxf (mx, __shfl_xor_sync (0xffffffffu, mx, 16));
+            if (lane < 4 && mx > 0.0f) atomicMax (&s_gmax[c8], __float_as_uint (mx));
+            if (chunk == nchunks - 1) {
+                // the group's block is complete: process_max's m = max (m, v) (truepeakdsp.cc:108-123) and the EBUr128 epilogue
+                asm volatile ("bar.sync 2, 128;" ::: "memory");     // the four epilogue warps: every maximum of the group is in s_gmax
+                if (warp == 4) {
+                    const int cc = c0 + lane;
+                    const bool own = lane < 8 && cc < n_chan;
+                    float mm = 0.0f;
+                    if (lane < 8) { const float bm = __uint_as_float (s_gmax[lane]); s_gmax[lane] = 0u; mm = bm; }
+                    if (own) {
+                        const float m0 = st.tp_res[cc] ? 0.0f : st.tp_m[cc];
+                        if (!(mm > m0)) mm = m0;
+                        st.tp_m[cc] = mm;
+                    }
+                    if (r128_tpmax) {
+                        // src/ebulv2.cc:227-230,360-367, one lane per stereo instance: read() both meters, coef_to_db, hold
+                        const float bo = __shfl_xor_sync (0xffffffffu, mm, 1);
+                        if (own && (lane & 1) == 0 && cc + 1 < n_chan) {
+                            const float vv = mm > bo ? mm : bo;
+                            const float tp = (vv == 0) ? -INFINITY : __double2float_rn (__dmul_rn (20.0, (double)log10f_glibc (vv)));
+                            if (tp > r128_tpmax[cc >> 1]) r128_tpmax[cc >> 1] = tp;
+                            st.tp_res[cc] = 1; st.tp_res[cc + 1] = 1;
+                        }
+                    }
+                }
+                asm volatile ("bar.sync 2, 128;" ::: "memory");     // s_gmax is reset before the next group's maxima arrive
+            }
+        }
+    }
+    asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads ();
+    if (warp == 0) asm volatile ("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem), "n"(512) : "memory");
+    if (r128_tpmax && tid == 0) {
+        // launched with programmatic serialization behind the K-weighting kernel (r128.cu): see tpmax_kernel
+        const unsigned dn = atomicAdd (st.done_cnt, 1u);
+        if (dn == gridDim.x - 1) { *st.done_cnt = 0u; asm volatile ("griddepcontrol.wait;" ::: "memory"); }
+    }
+}
+
 // Tried and dropped (round 1): a warp-specialised pipeline for process() — four FIR warps + a K-meter warp in lock
 // step, the ballistics warp one chunk behind on a double-buffered |out| tile with full/empty named barriers.  It was
 // bit-exact but slower (372 us vs 286 us per 16384 x 1024 block): 48 KB of shared memory and 80 registers x 192 threads
@@ -1553,6 +1849,8 @@ struct b200m_tpk {
     cudaStream_t sb = nullptr; cudaEvent_t ev_fir[2] = {nullptr, nullptr}, ev_bal[2] = {nullptr, nullptr};
     int wide = 0, wide_min = 64 * 148;      // process() with 64-channel CTAs: opt-in (B200M_TPK_WIDE=1, or =<min channels of a bank>); measured slower, see below
     int dec = 1;                            // process() runs tpdec_kernel (decoupled roles) unless the debug tap or DR-14 sums are on; B200M_TPK_DEC=0: the fused kernel
+    int tc = 1;                             // tolerance-mode process_max of large banks on the tensor cores (tpmax_tc_kernel); B200M_TPK_TC=0: tpmax_kernel
+    float* d_btc = nullptr; int n_sm = 0;   // [B_hi | B_lo] in tcgen05's K-major layout; SM count (persistent grid)
     int chunked = 1;                        // process_max without K-meter runs as (channel group x time chunk) CTAs (tpmax_kernel); B200M_TPK_CHUNKED=0: one CTA per group
     int fma = 0;                            // B200M_PREC_FMA: tolerance-mode FIR (fir16_fma); needs the literal table (imm)
     TpkDr dr{}; bool dr_on = false;         // DR-14 accumulation of the next process() call (set by dr14.cu)
@@ -1631,7 +1929,16 @@ int tpk_process_sliced (b200m_tpk* h, const float* d_in, size_t stride, uint32_t
             if (h->imm && h->fma) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true, DRM, true>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); \
             else if (h->imm) B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, true, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); \
             else B200M_CUDA (cudaLaunchKernelEx (&cfg, tpk_kernel<CH, TC, TP, MX, KM, false, DRM>, d_in, stride, cf, ce, (int)nfram, aligned, h->elide0, prm, h->st, h->d_dbg, r128_tpmax, drp)); } while (0)
-        if (tp && tp_mode == B200M_TP_MODE_MAX && !km && h->chunked) {
+        if (tp && tp_mode == B200M_TP_MODE_MAX && !km && h->chunked && h->tc && h->fma && h->imm && h->d_btc && aligned && nfram % 4 == 0 && !h->d_dbg
+            && (ce - cf + 7) / 8 >= h->n_sm) {
+            // tensor-core path: persistent CTAs, each takes whole 8-channel groups (a bank too small to give every SM a group runs tpmax_kernel)
+            const int nchunks = ((int)nfram + 255) / 256;
+            cfg.blockDim = dim3 (TCF_THREADS); cfg.gridDim = dim3 ((unsigned)std::min ((ce - cf + 7) / 8, h->n_sm)); cfg.dynamicSmemBytes = TCF_SMEM;
+            B200M_CUDA (cudaLaunchKernelEx (&cfg, tpmax_tc_kernel, d_in, stride, cf, ce, (int)nfram, nchunks, (const float*)h->d_btc, h->st, r128_tpmax));
+            cfg.blockDim = blk;
+            swap_hist = true;
+        }
+        else if (tp && tp_mode == B200M_TP_MODE_MAX && !km && h->chunked) {
             // chunk-parallel process_max (tpmax_kernel): stereo pairs of the EBUr128 epilogue need c_first even, which every caller guarantees
             const int nchunks = ((int)nfram + 255) / 256;
             cfg.gridDim = dim3 ((unsigned)(((ce - cf + 7) / 8) * nchunks));
@@ -1759,6 +2066,27 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
     A ((void**)&h->st.hist_alt, n * 48 * sizeof (float));
     A ((void**)&h->st.blk_max, n * 4); A ((void**)&h->st.grp_cnt, n * 4);
     if (const char* v = getenv ("B200M_TPK_CHUNKED")) h->chunked = atoi (v) != 0;
+    if (const char* v = getenv ("B200M_TPK_TC")) h->tc = atoi (v) != 0;
+    if ((flags & B200M_TPK_TRUEPEAK) && h->imm && e == cudaSuccess) {
+        // B[k][n] = h_ph[j + 48 - k] for n = 16 (ph - 1) + j: h_ph[d] multiplies x[n - d] (fir16: d >= 24 -> tab[24 ph + 47 - d], else tab[24 (4 - ph) + d]);
+        // element (n, k) of the hi part at (k / 4) * 1536 + n * 16 + (k % 4) * 4 bytes, the lo part 48 rows further
+        float* hb = new (std::nothrow) float[TCF_BBYTES / 4];
+        if (hb) {
+            memset (hb, 0, TCF_BBYTES);
+            for (int n = 0; n < 48; ++n) for (int k = 0; k < 64; ++k) {
+                const int ph = n / 16 + 1, j = n % 16, d = j + 48 - k;
+                const float c = (d >= 0 && d <= 47) ? (d >= 24 ? h->ctab[24 * ph + 47 - d] : h->ctab[24 * (4 - ph) + d]) : 0.0f;
+                uint32_t u; memcpy (&u, &c, 4); u &= 0xffffe000u; float hi; memcpy (&hi, &u, 4);
+                const size_t off = ((size_t)(k / 4) * TCF_BLBO + (size_t)n * 16 + (size_t)(k % 4) * 4) / 4;
+                hb[off] = hi; hb[off + 48 * 4] = c - hi;
+            }
+            e = cudaMalloc ((void**)&h->d_btc, TCF_BBYTES);
+            if (e == cudaSuccess) e = cudaMemcpy (h->d_btc, hb, TCF_BBYTES, cudaMemcpyHostToDevice);
+            delete[] hb;
+        }
+        if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM);
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute (&h->n_sm, cudaDevAttrMultiProcessorCount, device);
+    }
     if (const char* v = getenv ("B200M_TPK_DEC")) h->dec = atoi (v) != 0;
     // the slab pipeline is opt-in (B200M_TPK_SPLIT=2; =1: for banks of >= 512 channels): MEASURED slower than the fused kernel, see below
     h->split = 0;
@@ -1813,7 +2141,7 @@ int b200m_tpk_destroy (b200m_tpk* h)
     DeviceGuard g (h->device);
     cudaDeviceSynchronize ();
     void* ps[] = {h->st.hist, h->st.tp_z1, h->st.tp_z2, h->st.tp_m, h->st.tp_p, h->st.tp_res, h->st.km_z1, h->st.km_z2, h->st.km_rms,
-                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt, h->st.tmp, h->d_scr, h->st.sm_arr, h->d_tl};
+                  h->st.km_peak, h->st.km_fall, h->st.km_cnt, h->st.km_fpp, h->st.km_flag, h->d_res, h->d_dbg, h->st.done_cnt, h->st.hist_alt, h->st.blk_max, h->st.grp_cnt, h->st.tmp, h->d_scr, h->st.sm_arr, h->d_tl, h->d_btc};
     for (void* p : ps) cudaFree (p);
     if (h->sb) cudaStreamDestroy (h->sb);
     for (int i = 0; i < 2; ++i) { if (h->ev_fir[i]) cudaEventDestroy (h->ev_fir[i]); if (h->ev_bal[i]) cudaEventDestroy (h->ev_bal[i]); }

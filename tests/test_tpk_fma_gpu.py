@@ -159,3 +159,35 @@ def test_fma_process_ragged_blocks(km, process_form):
                 worst = max(worst, np.abs(db(got[nz]) - db(ref[nz])).max())
     print("worst deviation %.3g dB" % worst)
     assert worst <= TOL_DB, worst
+
+
+def test_fma_process_max_tensor_core_path(monkeypatch):
+    """process_max of a bank large enough for the tensor-core kernel (csrc/tpk.cu tpmax_tc_kernel: every SM gets an 8-channel group),
+    over block lengths with partial tiles, a channel count that leaves a partial group, silent and constant channels, read every block"""
+    import torch
+    import meters_lv2_b200 as B
+    monkeypatch.setenv("B200M_TPK_TC", "1")
+    C = 148 * 8 + 21
+    sizes = [1024, 1000, 512, 260, 4, 2048, 1024]
+    total = sum(sizes)
+    x = S.white(C, total, seed=11)
+    x[3] = S.sine(total, 11025.0, amp=0.8, phase=0.4)       # inter-sample peaks above the sample peaks
+    x[5] = 0
+    x[9] = 0.25
+    x[C - 1] *= 1e-5
+    g = B.TruePeakKmeter(C, flags=B.TPK_TRUEPEAK); g.set_precision(B.PREC_FMA)
+    ot = O.TruePeak(C)
+    xd = torch.from_numpy(x).cuda()
+    a = 0; worst = 0.0
+    for n in sizes:
+        blk = np.ascontiguousarray(x[:, a:a + n])
+        ot.process(blk, mode=1, nthreads=8)
+        g.process(xd[:, a:a + n], tp_mode=1)
+        a += n
+        r = g.read(); m, _ = ot.read()
+        nz = m > 0
+        assert np.array_equal(r["tp_m"][~nz], m[~nz]), n
+        worst = max(worst, np.abs(db(r["tp_m"][nz]) - db(m[nz])).max())
+    print("worst deviation %.3g dB" % worst)
+    assert worst <= TOL_DB, worst
+    assert worst <= 3e-5, worst
