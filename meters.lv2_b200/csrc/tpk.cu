@@ -1522,9 +1522,11 @@ tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
 //   warp 9    one thread: the tile's 8 rows x 304 floats by cp.async.bulk onto xfull[s], eight stages ahead of the builders;
 //   warps 0-3 builders: row window -> registers -> {hi, lo} -> TMEM A[b]; phase-0 maximum; the block's last 48 samples -> next history;
 //   warp 8    one thread issues the tile's 16 MMAs when A[b] is written and D[b] is read out, and commits them onto done[b];
-//   warps 4-7 epilogue: D[b] -> registers, maxima over the row's valid positions, per-channel maximum -> atomicMax on blk_max,
-//             then tpmax_kernel's group book-keeping (last chunk of a group: m = max (m, v), the EBUr128 epilogue).
-// A and D are double-buffered in TMEM (512 columns: one CTA per SM, persistent over its tiles).
+//   warps 4-7 epilogue: D[b] -> registers, maxima over the row's valid positions, per-channel maximum into shared memory; after a
+//             group's last chunk: m = max (m, v) (truepeakdsp.cc:108-123) and the EBUr128 epilogue (read x2, coef_to_db, hold).
+// A and D are double-buffered in TMEM (512 columns: one CTA per SM, persistent).  A CTA takes WHOLE channel groups and walks their
+// chunks in order, so a block's maximum never leaves the CTA: tpmax_kernel's (group, chunk) item grid needs a __threadfence and two
+// global atomics per item, which cost this kernel 90 us per block when it still used them (one fence per ~1 us tile).
 // Accuracy: readings within 6.7e-7 relative of a float64 FIR (profiles/r2_tcfir_probe.txt; the contract's tolerance is 1.15e-5).
 // Non-finite input: a NaN or Inf sample makes every output of the (up to four) rows whose window holds it NaN, which the maxima
 // ignore like the reference ignores its own NaN outputs; |Inf| itself is still seen through phase 0.
