@@ -2091,6 +2091,8 @@ int b200m_tpk_create (b200m_tpk** out, int device, uint32_t n_chan, float fsamp,
             delete[] hb;
         }
         if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TCF_SMEM);
+        // it shares SMs with the K-weighting kernel in the EBUr128 cycle (106 KB + 104 KB): same (maximum) carveout as that one
+        if (e == cudaSuccess) e = cudaFuncSetAttribute (tpmax_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (e == cudaSuccess) e = cudaDeviceGetAttribute (&h->n_sm, cudaDevAttrMultiProcessorCount, device);
     }
     if (const char* v = getenv ("B200M_TPK_DEC")) h->dec = atoi (v) != 0;
