@@ -1532,7 +1532,9 @@ tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
 // ignore like the reference ignores its own NaN outputs; |Inf| itself is still seen through phase 0.
 // MEASURED (16384 channels x 1024 frames): 60.1 us against 81.4 us for tpmax_kernel<IMM,FMA>; the EBUr128 cycle 0.0760 ms against 0.0987.
 // ncu: pipe tensor 31 %, issue slots 28 % busy, 17.3 M warp instructions (tpmax_kernel: 79.8 M).  Eight builder + eight epilogue warps
-// (each thread half a row) were tried: 63.4 us, no gain -- the per-thread arithmetic is not what paces the tile.
+// (each thread half a row) were tried: 63.4 us, no gain -- the per-thread arithmetic is not what paces the tile; nor is the latency of
+// the builder / epilogue chains: two builder groups and two epilogue groups taking alternate tiles (18 warps) ran the kernel in the
+// same 60.4 us and slowed the EBUr128 cycle to 0.0868 ms (more warps competing with the K-weighting kernel).
 // Needs 16-byte aligned rows and nfram % 4 == 0 (bulk copies) and a bank of at least one 8-channel group per SM; everything else runs
 // tpmax_kernel.
 constexpr int TCF_XPITCH = 308;                            // floats per channel row of an input stage: 48 + 256 + 4; = 20 mod 32
