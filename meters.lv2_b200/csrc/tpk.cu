@@ -1535,10 +1535,11 @@ tpdec_kernel (const float* __restrict__ in, size_t stride, int c_first, int n_ch
 // (each thread half a row) were tried: 63.4 us, no gain -- the per-thread arithmetic is not what paces the tile; nor is the latency of
 // the builder / epilogue chains: two builder groups and two epilogue groups taking alternate tiles (18 warps) ran the kernel in the
 // same 60.4 us and slowed the EBUr128 cycle to 0.0868 ms (more warps competing with the K-weighting kernel).
-// What does pace it: the tile's 16 MMAs accumulate into the same TMEM columns, and a dependent K = 8 tcgen05.mma costs >= 110 cycles
-// whatever its N (profiles/r2_mma_bench.cu): 16 x 110 = 1760 of the ~2050 cycles per tile.  Independent accumulators (separate column
-// sets for the N = 96 and N = 48 products, or for even / odd K steps, summed in the epilogue) are the next step; they need TMEM columns
-// (2 x 144 beside a single-buffered A).
+// What does pace it: the MMA instructions themselves.  A K = 8 tcgen05.mma costs >= 110 cycles whatever its N <= 128 (192 with A in TMEM;
+// profiles/r2_mma_bench.cu), and it is a cost per instruction, not a dependency latency: accumulating even and odd K steps into two
+// separate column sets (two independent chains) ran the kernel in 62.0 us.  16 instructions x 110 = 1760 of the ~2050 cycles per tile.
+// The next step is fewer, wider instructions: 32 output positions per row (N = 192 and 96, K = 80: 20 instructions per 4096 samples
+// instead of 32); A (2 x 160 columns) and a single D (192) then fill the 512 TMEM columns exactly.
 // Needs 16-byte aligned rows and nfram % 4 == 0 (bulk copies) and a bank of at least one 8-channel group per SM; everything else runs
 // tpmax_kernel.
 constexpr int TCF_XPITCH = 308;                            // floats per channel row of an input stage: 48 + 256 + 4; = 20 mod 32
