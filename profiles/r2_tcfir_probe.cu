@@ -6,20 +6,23 @@
 // A_lo B_hi, as two instructions per K step: A_hi x [B_hi | B_lo] (N = 96) and A_lo x B_hi (N = 48), kind::tf32, M = 128, K = 8,
 // accumulators in TMEM.  Phase 0 of the filter is the input delayed by 24 samples and is taken from the window directly.
 // v1 (tcfir_kernel): A im2col'd into shared memory (K-major, no swizzle, 16-byte chunks), all warps in lock step.
-// v4 (tcfir2_kernel): A written to TMEM by eight producer warps (tcgen05.st), B in shared memory, a dedicated MMA warp, double-buffered
-//     A and D in TMEM (512 columns), four input stages filled by cp.async.bulk on mbarriers, epilogue = tcgen05.ld + max + atomicMax.
+// v5 (tcfir2_kernel; v2 - v4 were steps towards it): A written to TMEM by four builder warps (tcgen05.st), B in shared memory, a dedicated
+//     MMA warp, four epilogue warps (tcgen05.ld + max + atomicMax), a loader thread filling eight input stages by cp.async.bulk; every
+//     hand-over is an mbarrier; A and D double-buffered in TMEM (512 columns).  The library's tpmax_tc_kernel is this kernel plus the
+//     bank's history, the group book-keeping and the EBUr128 epilogue.
 //
 // MEASURED on B200 (round 2; 16384 channels x 1024 frames, the headline's bank):
 //   * numerics: channel maxima within 6.7e-7 relative of a float64 FIR (the contract's tolerance is 1.15e-5), ragged block lengths
 //     and channel counts included -- descriptors, instruction descriptor and TMEM layout as written here are right;
-//   * time: v1 203 us, v2 (A in TMEM) 87 us, v4 81-85 us -- the same as the CUDA-core tpmax_kernel (81 us), not faster;
-//   * ablation of v4 (mode bits of argv[5]): no MMA 78 us, no tcgen05.st 76, no tcgen05.ld 86, NO INPUT LOADS 54, nothing but the
-//     producers' ALU work and barriers 45: the bulk copies (8 rows x 1216 B per tile, three tiles ahead) and the latency of the
-//     per-tile producer chain bound it, not the tensor pipe (16 MMAs per tile take ~900 cycles of the ~2800 per tile);
+//   * time: v1 203 us, v2 (A in TMEM) 87 us, v4 (8 producer warps, 4 input stages) 81-85 us = the CUDA-core tpmax_kernel (81 us);
+//     v5 52.8 us;
+//   * ablation of v4: no MMA 78 us, no tcgen05.st 76, no tcgen05.ld 86, NO INPUT LOADS 54, only the producers' ALU work and barriers
+//     45: too few bytes in flight (three tiles of bulk copies) and all stages of a tile in the same warps; v5 fixes both;
+//   * ablation of v5 (mode bits of argv[5]): no input loads 49.4, no MMAs 47.3, no TMEM stores / loads / epilogue arithmetic 43.2,
+//     everything stubbed 28.8;
 //   * r2_mma_bench.cu: a tcgen05.mma with K = 8 costs >= ~110 cycles whatever N <= 128 (1890 MAC/clk at N = 256 with A in TMEM), so
 //     small-N Toeplitz tiles waste the tensor pipe as well.
-// Not shipped: no gain yet.  What would have to change: input via plain LDG prefetched in registers or wider TMA boxes, producer and
-// epilogue roles on separate warps, two CTAs per SM.  Build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tcfir r2_tcfir_probe.cu
+// Shipped as tpmax_tc_kernel (csrc/tpk.cu).  Build: nvcc -O2 -gencode arch=compute_100a,code=sm_100a -o tcfir r2_tcfir_probe.cu
 // Run: ./tcfir <channels> <frames> <compare every output 0|1> <kernel 1|2> <ablation mode bits>
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -233,30 +236,38 @@ __device__ __forceinline__ void tmem_ld8_nowait (uint32_t taddr, uint32_t (&r)[8
     asm volatile ("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
                   : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
 }
-constexpr int XSTAGES = 4;
-constexpr int V4_SMEM = B2_BYTES + XSTAGES * 8 * XPITCH * 4 + 128;
-constexpr int NPROD = 256;
+constexpr int XSTAGES = 8;
+constexpr int V4_SMEM = B2_BYTES + XSTAGES * 8 * XPITCH * 4 + 4 * 128 * 4 + 256;
+constexpr int NTHREADS = 320;                              // warps 0-3 build A, 4-7 epilogue, 8 MMA issue, 9 input loads
 
-// v4: eight producer / epilogue warps (warp w and w + 4 share TMEM lanes 32 (w % 4) ..: w < 4 takes window elements 0..31 and output
-// positions 0..7 of its rows, w >= 4 elements 32..63 and positions 8..15), one MMA warp, four input stages filled by bulk copies
-__global__ void __launch_bounds__ (NPROD + 32, 1)
+// v5: every stage of a tile on its own warps.  mbarriers: afull[2] A[b] written (128), done[2] MMAs of the tile complete (commit),
+// dempty[2] D[b] read out (128), xfull[s] input stage landed (tx), xempty[s] input stage read (128).
+__global__ void __launch_bounds__ (NTHREADS, 1)
 tcfir2_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfram, const float* __restrict__ bcanon, unsigned* __restrict__ out_max, float* __restrict__ dbg, int mode)
 {
     extern __shared__ __align__ (128) uint8_t smem[];
     uint8_t* sB = smem;                                                        // [B_hi | B_lo], K-major canonical, 96 rows
     float* xbuf = reinterpret_cast<float*> (smem + B2_BYTES);                  // [XSTAGES][8][XPITCH]
-    uint64_t* bars = reinterpret_cast<uint64_t*> (smem + B2_BYTES + XSTAGES * 8 * XPITCH * 4);   // full[2], done[2], xfull[XSTAGES]
+    float* p0buf = reinterpret_cast<float*> (smem + B2_BYTES + XSTAGES * 8 * XPITCH * 4);       // [4][128]
+    uint64_t* bars = reinterpret_cast<uint64_t*> (smem + B2_BYTES + XSTAGES * 8 * XPITCH * 4 + 4 * 128 * 4);
+    uint64_t* afull = bars; uint64_t* done = bars + 2; uint64_t* dempty = bars + 4; uint64_t* xfull = bars + 6; uint64_t* xempty = bars + 6 + XSTAGES;
     __shared__ uint32_t s_tmem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nchunks = (nfram + TILE_S - 1) / TILE_S;
     const int ntiles = ((n_chan + 7) / 8) * nchunks;
     const int n_it = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-    for (int i = tid; i < B2_BYTES / 16; i += NPROD + 32) reinterpret_cast<float4*> (sB)[i] = reinterpret_cast<const float4*> (bcanon)[i];
+    for (int i = tid; i < B2_BYTES / 16; i += NTHREADS) reinterpret_cast<float4*> (sB)[i] = reinterpret_cast<const float4*> (bcanon)[i];
     if (tid == 0) {
-        asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (&bars[0])), "r"(NPROD));
-        asm volatile ("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32 (&bars[1])), "r"(NPROD));
-        for (int i = 2; i < 4 + XSTAGES; ++i) asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32 (&bars[i])));
+        for (int i = 0; i < 2; ++i) {
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(smem_u32 (&afull[i])));
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32 (&done[i])));
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(smem_u32 (&dempty[i])));
+        }
+        for (int i = 0; i < XSTAGES; ++i) {
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32 (&xfull[i])));
+            asm volatile ("mbarrier.init.shared::cta.b64 [%0], 128;" :: "r"(smem_u32 (&xempty[i])));
+        }
         asm volatile ("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -271,146 +282,146 @@ tcfir2_kernel (const float* __restrict__ in, size_t stride, int n_chan, int nfra
     const uint32_t idesc96 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(96 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
     const uint32_t idesc48 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(48 >> 3) << 17) | ((uint32_t)(ROWS >> 4) << 24);
     // TMEM columns: A[b] hi at 128 b, lo at 128 b + 64; D[b] at 256 + 128 b: [0,48) hi hi + lo hi, [48,96) hi lo
+    // lane -> (channel, 16-sample block) of the row it owns, chosen so that an LDS.128 phase of the builders is conflict-free
+    const int wq = warp & 3;
+    const int c8 = (wq & 1) * 4 + (lane & 3);
+    const int tb = ((wq >> 1) * 4 + (lane >> 3)) * 2 + ((lane >> 2) & 1);
+    const int row = 32 * wq + lane;
+    const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
 
-    if (warp == NPROD / 32) {
+    if (warp == 9) {
+        // ---------------- input loads: one thread, XSTAGES tiles ahead
+        if (lane == 0 && !(mode & 8))
+            for (int it = 0; it < n_it; ++it) {
+                const int st = it % XSTAGES;
+                if (it >= XSTAGES) mbar_wait (smem_u32 (&xempty[st]), (uint32_t)((it / XSTAGES - 1) & 1));
+                const int tile = blockIdx.x + it * gridDim.x;
+                const int grp = tile / nchunks, chunk = tile - grp * nchunks;
+                const int c0 = grp * 8, s0 = chunk * TILE_S;
+                const uint32_t xb = smem_u32 (xbuf + (size_t)st * 8 * XPITCH), bar = smem_u32 (&xfull[st]);
+                const uint32_t bytes = (uint32_t)min (304, nfram - (s0 - 48)) * 4u;
+                asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(8u * bytes) : "memory");
+                for (int cc = 0; cc < 8; ++cc) {
+                    const float* src = in + (size_t)min (c0 + cc, n_chan - 1) * stride + (s0 - 48);
+                    asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                  :: "r"(xb + (uint32_t)(cc * XPITCH * 4)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+                }
+            }
+    } else if (warp == 8) {
         // ---------------- MMA issuer
         if (lane == 0) {
             const uint32_t bb = smem_u32 (sB);
             for (int it = 0; it < n_it; ++it) {
-                const int b = it & 1; const uint32_t par = (uint32_t)((it >> 1) & 1);
-                mbar_wait (smem_u32 (&bars[b]), par);
+                const int b = it & 1;
+                mbar_wait (smem_u32 (&afull[b]), (uint32_t)((it >> 1) & 1));
+                if (it >= 2) mbar_wait (smem_u32 (&dempty[b]), (uint32_t)(((it - 2) >> 1) & 1));
                 asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d = tmem + 256u + 128u * b, ah = tmem + 128u * b, al = ah + 64u;
                 if (!(mode & 1)) {
 #pragma unroll
-                for (int s = 0; s < 8; ++s) {
-                    const uint64_t db = make_desc (bb + 2 * s * B2_LBO, B2_LBO, SBO);
-                    mma_tf32_ts (d, ah + 8 * s, db, idesc96, s > 0 ? 1u : 0u);      // A_hi x [B_hi | B_lo]
-                    mma_tf32_ts (d, al + 8 * s, db, idesc48, 1u);                    // A_lo x B_hi
+                    for (int s = 0; s < 8; ++s) {
+                        const uint64_t db = make_desc (bb + 2 * s * B2_LBO, B2_LBO, SBO);
+                        mma_tf32_ts (d, ah + 8 * s, db, idesc96, s > 0 ? 1u : 0u);      // A_hi x [B_hi | B_lo]
+                        mma_tf32_ts (d, al + 8 * s, db, idesc48, 1u);                    // A_lo x B_hi
+                    }
                 }
-                }
-                asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32 (&bars[2 + b])) : "memory");
+                asm volatile ("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32 (&done[b])) : "memory");
             }
         }
+    } else if (warp < 4) {
+        // ---------------- builders: this row's 64-sample window -> {hi, lo} -> TMEM lane
+        for (int it = 0; it < n_it; ++it) {
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int chunk = tile % nchunks, s0 = chunk * TILE_S;
+            const int b = it & 1, st = it % XSTAGES;
+            if (!(mode & 8)) mbar_wait (smem_u32 (&xfull[st]), (uint32_t)((it / XSTAGES) & 1));
+            const float* xw = xbuf + (size_t)st * 8 * XPITCH + c8 * XPITCH + 16 * tb;
+            float4 v[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) v[c] = *reinterpret_cast<const float4*> (xw + 4 * c);
+            if (!(mode & 8)) asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&xempty[st])) : "memory");
+            const int vj = min (16, max (0, nfram - (s0 + 16 * tb)));
+            const int nin = nfram - (s0 - 48) - 16 * tb;          // window elements k < nin lie inside the block; the rest read as 0
+            if (nin < 64) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    if (4 * c + 0 >= nin) v[c].x = 0.0f;
+                    if (4 * c + 1 >= nin) v[c].y = 0.0f;
+                    if (4 * c + 2 >= nin) v[c].z = 0.0f;
+                    if (4 * c + 3 >= nin) v[c].w = 0.0f;
+                }
+            }
+            float p0 = 0.0f;                                       // phase 0 = the input delayed by 24 samples: elements 24 + j
+#pragma unroll
+            for (int c = 6; c < 10; ++c) {
+                const int j0 = 4 * (c - 6);
+                if (j0 + 0 < vj) p0 = fmaxf (p0, fabsf (v[c].x));
+                if (j0 + 1 < vj) p0 = fmaxf (p0, fabsf (v[c].y));
+                if (j0 + 2 < vj) p0 = fmaxf (p0, fabsf (v[c].z));
+                if (j0 + 3 < vj) p0 = fmaxf (p0, fabsf (v[c].w));
+            }
+            if (it >= 2) mbar_wait (smem_u32 (&done[b]), (uint32_t)(((it - 2) >> 1) & 1));       // the MMAs of tile it - 2 have read A[b]
+            asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
+            p0buf[(it & 3) * 128 + row] = p0;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float4 q = v[8 * half + c];
+                    const float vv[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const uint32_t h = __float_as_uint (vv[e]) & 0xffffe000u;
+                        hi[4 * c + e] = h; lo[4 * c + e] = __float_as_uint (vv[e] - __uint_as_float (h));
+                    }
+                }
+                if (!(mode & 2)) {
+                    tmem_st32 (tmem + lane_base + 128u * b + 32u * half, hi);
+                    tmem_st32 (tmem + lane_base + 128u * b + 64u + 32u * half, lo);
+                }
+            }
+            asm volatile ("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&afull[b])) : "memory");
+        }
     } else {
-        // ---------------- producer + epilogue warps: lane -> (channel, 16-sample block) so that an LDS.128 phase is conflict-free
-        const int wq = warp & 3, half = warp >> 2;
-        const int c8 = (wq & 1) * 4 + (lane & 3);
-        const int tb = ((wq >> 1) * 4 + (lane >> 3)) * 2 + ((lane >> 2) & 1);
-        const uint32_t lane_base = (uint32_t)(32 * wq) << 16;
-        auto load_tile = [&] (int it) {                        // one thread: 8 row copies onto xfull[it % XSTAGES]
+        // ---------------- epilogue warps 4..7: D[b] -> registers -> maxima
+        for (int it = 0; it < n_it; ++it) {
             const int tile = blockIdx.x + it * gridDim.x;
             const int grp = tile / nchunks, chunk = tile - grp * nchunks;
             const int c0 = grp * 8, s0 = chunk * TILE_S;
-            const int st = it % XSTAGES;
-            const uint32_t xb = smem_u32 (xbuf + (size_t)st * 8 * XPITCH), bar = smem_u32 (&bars[4 + st]);
-            const int nfl = min (304, nfram - (s0 - 48));      // floats of every row inside the block
-            const uint32_t bytes = (uint32_t)nfl * 4u;
-            asm volatile ("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(8u * bytes) : "memory");
-            for (int cc = 0; cc < 8; ++cc) {
-                const float* src = in + (size_t)min (c0 + cc, n_chan - 1) * stride + (s0 - 48);
-                asm volatile ("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                              :: "r"(xb + (uint32_t)(cc * XPITCH * 4)), "l"(src), "r"(bytes), "r"(bar) : "memory");
-            }
-        };
-        float p0_prev = 0.0f; int prev_tile = -1;
-        long long pa = 0, pb = 0, pc = 0, pd = 0, pe = 0, pf = 0;
-        auto epilogue = [&] (int tile, int b, uint32_t par, float p0) {
-            const int grp = tile / nchunks, chunk = tile - grp * nchunks;
-            const int c0 = grp * 8, s0 = chunk * TILE_S;
-            long long e0 = clock64 ();
-            mbar_wait (smem_u32 (&bars[2 + b]), par);
-            pd += clock64 () - e0;
+            const int b = it & 1;
+            mbar_wait (smem_u32 (&done[b]), (uint32_t)((it >> 1) & 1));
             asm volatile ("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int vj = min (16, max (0, nfram - (s0 + 16 * tb))) - 8 * half;      // valid positions among this thread's eight
-            float mx = p0;
-            const uint32_t taddr = tmem + lane_base + 256u + 128u * b + 8u * half;
-            uint32_t u[3][8], w[3][8];
+            const uint32_t taddr = tmem + lane_base + 256u + 128u * b;
+            uint32_t u[3][16], w[3][16];
             if (mode & 4) {
 #pragma unroll
-                for (int ph = 0; ph < 3; ++ph) for (int j = 0; j < 8; ++j) { u[ph][j] = 0x3f000000u + tile + j; w[ph][j] = ph; }
+                for (int ph = 0; ph < 3; ++ph) for (int j = 0; j < 16; ++j) { u[ph][j] = 0x3f000000u + tile + j; w[ph][j] = ph; }
             } else {
 #pragma unroll
-            for (int ph = 0; ph < 3; ++ph) { tmem_ld8_nowait (taddr + 16 * ph, u[ph]); tmem_ld8_nowait (taddr + 48 + 16 * ph, w[ph]); }
+            for (int ph = 0; ph < 3; ++ph) { tmem_ld16_nowait (taddr + 16 * ph, u[ph]); tmem_ld16_nowait (taddr + 48 + 16 * ph, w[ph]); }
             asm volatile ("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             }
+            float mx = p0buf[(it & 3) * 128 + row];
+            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
+            asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&dempty[b])) : "memory");
+            const int vj = min (16, max (0, nfram - (s0 + 16 * tb)));
+            if (mode & 16) { mx = fmaxf (mx, __uint_as_float (u[0][0] ^ w[2][15])); } else
 #pragma unroll
             for (int ph = 0; ph < 3; ++ph)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float v = __uint_as_float (u[ph][j]) + __uint_as_float (w[ph][j]);
-                    if (dbg) dbg[((size_t)tile * 128 + c8 * 16 + tb) * 48 + ph * 16 + 8 * half + j] = v;
-                    if (j < vj) mx = fmaxf (mx, fabsf (v));
+                for (int j = 0; j < 16; ++j) {
+                    const float val = __uint_as_float (u[ph][j]) + __uint_as_float (w[ph][j]);
+                    if (dbg) dbg[((size_t)tile * 128 + c8 * 16 + tb) * 48 + ph * 16 + j] = val;
+                    if (j < vj) mx = fmaxf (mx, fabsf (val));
                 }
             mx = fmaxf (mx, __shfl_xor_sync (0xffffffffu, mx, 4));
             mx = fmaxf (mx, __shfl_xor_sync (0xffffffffu, mx, 8));
             mx = fmaxf (mx, __shfl_xor_sync (0xffffffffu, mx, 16));
             if (lane < 4 && c0 + c8 < n_chan && mx > 0.0f) atomicMax (out_max + c0 + c8, __float_as_uint (mx));
-            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
-        };
-        if (tid == 0 && !(mode & 8)) for (int i = 0; i < XSTAGES - 1 && i < n_it; ++i) load_tile (i);
-        for (int it = 0; it < n_it; ++it) {
-            const int tile = blockIdx.x + it * gridDim.x;
-            const int chunk = tile % nchunks, s0 = chunk * TILE_S;
-            const int b = it & 1, st = it % XSTAGES;
-            long long q0 = clock64 ();
-            asm volatile ("bar.sync 1, %0;" :: "n"(NPROD) : "memory");            // nobody still reads the stage of tile it - 1
-            long long q1 = clock64 (); pa += q1 - q0;
-            if (!(mode & 8)) {
-            if (tid == 0 && it + XSTAGES - 1 < n_it) load_tile (it + XSTAGES - 1);
-            mbar_wait (smem_u32 (&bars[4 + st]), (uint32_t)((it / XSTAGES) & 1));     // tile `it` has landed
-            }
-            long long q2 = clock64 (); pb += q2 - q1;
-            // half of this row's 64-sample window -> {hi, lo} -> TMEM lane, 32 columns of A hi / A lo
-            const float* xw = xbuf + (size_t)st * 8 * XPITCH + c8 * XPITCH + 16 * tb + 32 * half;
-            const int vj = min (16, max (0, nfram - (s0 + 16 * tb)));
-            const int nin = nfram - (s0 - 48) - 16 * tb - 32 * half;      // window elements k < nin lie inside the block; the rest read as 0
-            float p0 = 0.0f;
-            {
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float4 v = *reinterpret_cast<const float4*> (xw + 4 * c);
-                    float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int k = 4 * c + e;
-                        if (k >= nin) vv[e] = 0.0f;
-                        const uint32_t h = __float_as_uint (vv[e]) & 0xffffe000u;
-                        hi[k] = h; lo[k] = __float_as_uint (vv[e] - __uint_as_float (h));
-                    }
-                }
-                // phase 0 = the input delayed by 24 samples: window elements 24 + j; this thread owns positions j = 8 half .. 8 half + 7,
-                // i.e. elements 24..31 of the first half or 0..7 of the second
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int k = half ? j : 24 + j;
-                    const float xv = __uint_as_float (hi[0]) * 0.0f;   // placeholder to keep types; replaced below
-                    (void)xv; (void)k;
-                }
-                if (!(mode & 2)) {
-                tmem_st32 (tmem + lane_base + 128u * b + 32u * half, hi);
-                tmem_st32 (tmem + lane_base + 128u * b + 64u + 32u * half, lo);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float xa = __uint_as_float (hi[24 + j]) + __uint_as_float (lo[24 + j]);     // half 0: elements 24..31
-                    const float xb2 = __uint_as_float (hi[j]) + __uint_as_float (lo[j]);              // half 1: elements 32..39
-                    const float xv = half ? xb2 : xa;
-                    if (8 * half + j < vj) p0 = fmaxf (p0, fabsf (xv));
-                }
-            }
-            long long q3 = clock64 (); pc += q3 - q2;
-            asm volatile ("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
-            asm volatile ("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32 (&bars[b])) : "memory");
-            long long q4 = clock64 (); pe += q4 - q3;
-            if (prev_tile >= 0) epilogue (prev_tile, b ^ 1, (uint32_t)(((it - 1) >> 1) & 1), p0_prev);
-            pf += clock64 () - q4;
-            prev_tile = tile; p0_prev = p0;
         }
-        if (blockIdx.x == 3 && (tid == 0 || tid == 200) && n_it > 20) printf ("producer %d: per tile bar %lld xwait %lld build %lld st-wait+arrive %lld epilogue %lld (mma-wait %lld)\n", tid, pa / n_it, pb / n_it, pc / n_it, pe / n_it, pf / n_it, pd / n_it);
-        if (prev_tile >= 0) epilogue (prev_tile, (n_it - 1) & 1, (uint32_t)(((n_it - 1) >> 1) & 1), p0_prev);
     }
     asm volatile ("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads ();
@@ -468,7 +479,7 @@ int main (int argc, char** argv)
     int dev = 0, sms = 0; CK (cudaDeviceGetAttribute (&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = ntiles < sms ? ntiles : sms;
     printf ("n_chan %d nfram %d tiles %d grid %d smem %d\n", n_chan, nfram, ntiles, grid, SMEM_BYTES);
-    if (ver == 2) tcfir2_kernel<<<grid, NPROD + 32, V4_SMEM>>> (d_x + 48, stride, n_chan, nfram, d_b2, d_max, d_dbg, mode); else tcfir_kernel<<<grid, 128, SMEM_BYTES>>> (d_x + 48, stride, n_chan, nfram, d_b, d_max, d_dbg);
+    if (ver == 2) tcfir2_kernel<<<grid, NTHREADS, V4_SMEM>>> (d_x + 48, stride, n_chan, nfram, d_b2, d_max, d_dbg, mode); else tcfir_kernel<<<grid, 128, SMEM_BYTES>>> (d_x + 48, stride, n_chan, nfram, d_b, d_max, d_dbg);
     CK (cudaGetLastError ()); CK (cudaDeviceSynchronize ());
     std::vector<unsigned> gm (n_chan); CK (cudaMemcpy (gm.data (), d_max, n_chan * 4, cudaMemcpyDeviceToHost));
     // CPU reference (double)
@@ -499,9 +510,9 @@ int main (int argc, char** argv)
     printf ("worst relative error of the channel maxima %.3g; worst abs error of single outputs %.3g\n", worst, worst_d);
     if (!want_dbg) {
         cudaEvent_t e0, e1; cudaEventCreate (&e0); cudaEventCreate (&e1);
-        for (int i = 0; i < 3; ++i) if (ver == 2) tcfir2_kernel<<<grid, NPROD + 32, V4_SMEM>>> (d_x + 48, stride, n_chan, nfram, d_b2, d_max, nullptr, mode); else tcfir_kernel<<<grid, 128, SMEM_BYTES>>> (d_x + 48, stride, n_chan, nfram, d_b, d_max, nullptr);
+        for (int i = 0; i < 3; ++i) if (ver == 2) tcfir2_kernel<<<grid, NTHREADS, V4_SMEM>>> (d_x + 48, stride, n_chan, nfram, d_b2, d_max, nullptr, mode); else tcfir_kernel<<<grid, 128, SMEM_BYTES>>> (d_x + 48, stride, n_chan, nfram, d_b, d_max, nullptr);
         cudaEventRecord (e0);
-        for (int i = 0; i < 20; ++i) if (ver == 2) tcfir2_kernel<<<grid, NPROD + 32, V4_SMEM>>> (d_x + 48, stride, n_chan, nfram, d_b2, d_max, nullptr, mode); else tcfir_kernel<<<grid, 128, SMEM_BYTES>>> (d_x + 48, stride, n_chan, nfram, d_b, d_max, nullptr);
+        for (int i = 0; i < 20; ++i) if (ver == 2) tcfir2_kernel<<<grid, NTHREADS, V4_SMEM>>> (d_x + 48, stride, n_chan, nfram, d_b2, d_max, nullptr, mode); else tcfir_kernel<<<grid, 128, SMEM_BYTES>>> (d_x + 48, stride, n_chan, nfram, d_b, d_max, nullptr);
         cudaEventRecord (e1); CK (cudaDeviceSynchronize ());
         float ms; cudaEventElapsedTime (&ms, e0, e1);
         printf ("%.2f us per launch, %.1f G samples/s\n", ms * 1000 / 20, (double)n_chan * nfram / (ms / 20 * 1e-3) / 1e9);
